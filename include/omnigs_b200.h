@@ -1,0 +1,173 @@
+/*
+ * omnigs_b200.h — C ABI of libomnigs_b200.so: the B200-native (sm_100a) equirectangular
+ * ("lonlat", camera_type = 3) Gaussian-splatting rasterizer.
+ *
+ * This is the drop-in boundary underneath the reference's LibTorch entry points
+ * (raikuma/OmniGS-fork, paths relative to its root):
+ *
+ *   reference interface                                       replaced by
+ *   --------------------------------------------------------  ------------------------------------
+ *   CudaRasterizer::LonlatRasterizer::forward                  ogs_lonlat_forward_stage1 +
+ *     cuda_rasterizer/rasterizer.h:102-122,                      ogs_lonlat_forward_stage2
+ *     rasterizer_impl.cu:540-697
+ *   CudaRasterizer::LonlatRasterizer::backward                 ogs_lonlat_backward
+ *     rasterizer.h:125-154, rasterizer_impl.cu:701-795
+ *   CudaRasterizer::LonlatRasterizer::markVisible              ogs_mark_all_visible
+ *     rasterizer.h:98-100, rasterizer_impl.cu:185-192
+ *   required<GeometryState/ImageState/BinningState>(n)         ogs_geom_bytes / ogs_img_bytes /
+ *     rasterizer_impl.h:96-102, rasterizer_impl.cu:198-245       ogs_binning_bytes
+ *
+ * The reference passes std::function<char*(size_t)> allocators (rasterize_points.cu:41-47,92-94);
+ * a C ABI cannot, so the forward is split in two at the one point where a buffer size depends on a
+ * device result (num_rendered, rasterizer_impl.cu:627-632): stage 1 returns num_rendered, the caller
+ * sizes and allocates the binning buffer, stage 2 finishes the frame.
+ *
+ * Conventions (identical to the reference unless stated):
+ *   - every pointer is a DEVICE pointer (float32 / int32 / uint8) unless the name says "host";
+ *   - optional inputs are NULL when absent: exactly one of {shs, colors_precomp} and one of
+ *     {(scales, rotations), cov3D_precomp} is non-NULL (gaussian_rasterizer.cpp:190-208);
+ *   - viewmatrix is Tcw stored column-major (16 floats), campos the camera centre (3 floats),
+ *     rotations are (w,x,y,z) and are NOT normalised by the kernels (forward.cu:203);
+ *   - the three byte buffers are opaque: their layout is private to this library (it is NOT the
+ *     reference's layout) and only has to survive from forward to backward of the same frame;
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream);
+ *   - all calls return 0 on success or a negative OGS_ERR_* code; ogs_last_error() gives text.
+ *     Like the reference, kernels are launched asynchronously; only stage 1 blocks (for the
+ *     num_rendered read-back, as the reference does at rasterizer_impl.cu:627-628).
+ */
+#ifndef OMNIGS_B200_H
+#define OMNIGS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OGS_OK 0
+#define OGS_ERR_INVALID_ARG (-1)   /* NULL/negative/inconsistent argument                      */
+#define OGS_ERR_CUDA (-2)          /* a CUDA runtime call failed (see ogs_last_error)            */
+#define OGS_ERR_TOO_MANY (-3)      /* num_rendered >= 2^30 or image larger than 2^16 tiles/axis  */
+#define OGS_ERR_NO_DEVICE (-4)     /* no usable sm_100 device                                    */
+
+#define OGS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define OGS_API __attribute__((visibility("default")))
+#else
+#define OGS_API
+#endif
+
+OGS_API int ogs_abi_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+OGS_API const char* ogs_last_error(void);
+
+/* ---- workspace sizes (replace required<...State>(n), rasterizer_impl.h:96-102) ---- */
+OGS_API size_t ogs_geom_bytes(int P);
+OGS_API size_t ogs_img_bytes(int W, int H);
+OGS_API size_t ogs_binning_bytes(int64_t num_rendered, int W, int H);
+
+/*
+ * Forward, stage 1: per-Gaussian preprocessing (forward.cu:593-703), the tile-count prefix
+ * structures, the depth ordering of the Gaussians and the num_rendered read-back
+ * (rasterizer_impl.cu:592-628).  Writes radii[P] (0 for culled Gaussians) and *num_rendered_host.
+ * geom_buffer >= ogs_geom_bytes(P), img_buffer >= ogs_img_bytes(W,H).
+ */
+OGS_API int ogs_lonlat_forward_stage1(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* campos,
+	int* radii, char* geom_buffer, char* img_buffer,
+	int64_t* num_rendered_host, void* stream);
+
+/*
+ * Forward, stage 2: tile-instance emission (duplicateWithKeys, rasterizer_impl.cu:94-140), the
+ * radix sort (:651-661), tile ranges (:664-679) and the alpha-blend (forward.cu:346-467).
+ * binning_buffer >= ogs_binning_bytes(num_rendered, W, H).  out_color is planar [3,H,W] and is
+ * fully written (background where nothing is rendered).
+ */
+OGS_API int ogs_lonlat_forward_stage2(
+	int P, int W, int H, int64_t num_rendered, const float* background,
+	char* geom_buffer, char* binning_buffer, char* img_buffer,
+	float* out_color, void* stream);
+
+/*
+ * Backward (rasterizer_impl.cu:701-795): render backward (backward.cu:672-843) then the fused
+ * per-Gaussian backward (backward.cu:297-485 and :613-669).
+ * Every element of every output is written (culled rows get exact zeros), so outputs need NOT be
+ * zero-filled by the caller (the reference's shim zero-fills them, rasterize_points.cu:200-208).
+ * Shapes: dL_dmean2D [P,3] (z = 0), dL_dcolor [P,3], dL_dopacity [P], dL_dmean3D [P,3],
+ * dL_dcov3D [P,6], dL_dsh [P,M,3] (may be NULL when M == 0), dL_dscale [P,3], dL_drot [P,4].
+ * dL_dconic [P,4] is optional (NULL to skip): the reference's intermediate (.x,.y,.w used).
+ */
+OGS_API int ogs_lonlat_backward(
+	int P, int D, int M, int64_t num_rendered, int W, int H,
+	const float* background,
+	const float* means3D, const float* shs, const float* colors_precomp,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* campos, const int* radii,
+	char* geom_buffer, char* binning_buffer, char* img_buffer,
+	const float* dL_dpix,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+	void* stream);
+
+/* markAllVisible (rasterizer_impl.cu:82-90): present[i] = true for i < P (1 byte per flag). */
+OGS_API int ogs_mark_all_visible(int P, uint8_t* present, void* stream);
+
+/*
+ * Latitude-band variant of stage 1: identical to stage 1 except that every
+ * tile rect is clipped to tile rows [band_ty0, band_ty1) before counting, so this rank emits,
+ * sorts and renders only its band.  radii are the unclipped reference radii.  With
+ * band = [0, ceil(H/16)) it is exactly stage 1.
+ */
+OGS_API int ogs_lonlat_forward_stage1_band(
+	int P, int D, int M, int W, int H, int band_ty0, int band_ty1,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* campos,
+	int* radii, char* geom_buffer, char* img_buffer,
+	int64_t* num_rendered_host, void* stream);
+
+/*
+ * Introspection for the parity tests: re-express our private state in the reference's terms
+ * (the arrays GeometryState / BinningState / ImageState hold, rasterizer_impl.cu:198-245).
+ * Any output pointer may be NULL.  Rows of culled Gaussians are zero-filled.
+ */
+OGS_API int ogs_export_geometry(
+	int P, const char* geom_buffer,
+	float* means2D /*[P,2]*/, float* depths /*[P]*/, float* conic_opacity /*[P,4]*/, float* rgb /*[P,3]*/,
+	uint32_t* tiles_touched /*[P]*/, uint8_t* clamped /*[P,3]*/, float* cov3D /*[P,6]*/, void* stream);
+OGS_API int ogs_export_binning(
+	int P, int W, int H, int64_t num_rendered,
+	const char* geom_buffer, const char* binning_buffer, const char* img_buffer,
+	uint32_t* point_list /*[R]*/, uint64_t* point_list_keys /*[R]*/, uint32_t* ranges /*[T,2]*/,
+	float* final_T /*[H*W]*/, uint32_t* n_contrib /*[H*W]*/, void* stream);
+
+/*
+ * Host-buffer convenience call used for end-to-end measurement: per-view inputs
+ * (viewmatrix, campos, dL_dpix) are HOST pointers copied in, the image is copied back to
+ * out_color_host, all inside the call; the scene parameters stay resident on the device.
+ * Equivalent to stage1 + stage2 + backward with the copies around them; synchronises on return.
+ * binning_buffer/binning_capacity: a device scratch the caller owns; if num_rendered needs more
+ * the call fails with OGS_ERR_INVALID_ARG after writing the required size to *binning_needed.
+ */
+OGS_API int ogs_lonlat_train_view_host(
+	int P, int D, int M, int W, int H,
+	const float* background,
+	const float* means3D, const float* shs, const float* opacities,
+	const float* scales, float scale_modifier, const float* rotations,
+	const float* viewmatrix_host, const float* campos_host, const float* dL_dpix_host,
+	float* view_scratch /*device, >= 19 floats*/, float* dL_dpix_dev /*device [3,H,W]*/,
+	int* radii, char* geom_buffer, char* binning_buffer, size_t binning_capacity, char* img_buffer,
+	float* out_color_dev, float* out_color_host,
+	float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+	int64_t* num_rendered_host, size_t* binning_needed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMNIGS_B200_H */

@@ -1,0 +1,519 @@
+// binning.cu — from per-Gaussian tile rects to per-tile, depth-ordered Gaussian lists.
+//
+// Replaces the reference's InclusiveSum + duplicateWithKeys + 64-bit DeviceRadixSort::SortPairs +
+// memset + identifyTileRanges (cuda_rasterizer/rasterizer_impl.cu:622-679) with a B200-first
+// pipeline that yields bit-identical ranges / point lists:
+//
+//   The reference sorts R = num_rendered (tile<<32 | depth_bits) keys with a stable LSD radix sort
+//   over 32+bit bits.  An LSD sort processes the low 32 (depth) bits first, and all tile instances
+//   of a Gaussian share them, so those passes commute with the duplication step:
+//     1. stable-sort the P Gaussians by depth bits            (P-sized, 4 x 8-bit onesweep passes)
+//     2. emit tile instances in that order, row-major inside each rect (load-balanced expansion)
+//     3. stable-sort the R instances by tile id only           (ceil(bit/9) <= 2 onesweep passes)
+//   Equal (tile, depth) keys end in ascending Gaussian index, as with the reference (stability).
+//   Tile ranges never need the sorted keys: the per-tile instance counts come from a 2-D
+//   difference array that preprocess fills with 4 atomics per Gaussian; their prefix sum IS
+//   `ranges`, and the radix digit histograms are its marginals.
+//
+// HBM traffic at R instances: 8R (emit) + 16R + 12R (two passes) = 36R bytes, against
+// 12R + (8 + 24*6)R = 164R for the reference's data flow.
+#include "ogs_common.cuh"
+#include "launchers.cuh"
+
+namespace ogs {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = kSortItemsPerBlock / kSortThreads;   // 16 keys per thread
+constexpr uint32_t kFlagPartial = 1u << 30;
+constexpr uint32_t kFlagInclusive = 2u << 30;
+constexpr uint32_t kValueMask = (1u << 30) - 1;
+
+// ------------------------------------------------------------------ block-wide exclusive scan
+// Exclusive prefix sum over `n` (<= 2*kSortThreads) smem words, in place; returns nothing.
+// All kSortThreads threads must call.
+__device__ void block_exclusive_scan_512(uint32_t* data, int n, uint32_t* warp_tmp /*>= 8*/)
+{
+	const int tid = threadIdx.x;
+	uint32_t a = (2 * tid < n) ? data[2 * tid] : 0u;
+	uint32_t b = (2 * tid + 1 < n) ? data[2 * tid + 1] : 0u;
+	uint32_t sum = a + b;
+	uint32_t incl = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+		if ((tid & 31) >= o) incl += v;
+	}
+	if ((tid & 31) == 31) warp_tmp[tid >> 5] = incl;
+	__syncthreads();
+	uint32_t warp_off = 0;
+#pragma unroll
+	for (int w = 0; w < kSortThreads / 32; w++)
+		if (w < (tid >> 5)) warp_off += warp_tmp[w];
+	uint32_t excl = warp_off + incl - sum;
+	if (2 * tid < n) data[2 * tid] = excl;
+	if (2 * tid + 1 < n) data[2 * tid + 1] = excl + a;
+	__syncthreads();
+}
+
+// ------------------------------------------------------------------ depth-key digit histogram
+// 4 x 256 counts of the 8-bit digits of n 32-bit keys (the upfront histogram of onesweep).
+__global__ void __launch_bounds__(256) depth_histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+                                                              uint32_t* __restrict__ hist /*4*256*/)
+{
+	__shared__ uint32_t s[4 * 256];
+	for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) s[i] = 0;
+	__syncthreads();
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		uint32_t k = keys[i];
+		atomicAdd(&s[k & 255u], 1u);
+		atomicAdd(&s[256 + ((k >> 8) & 255u)], 1u);
+		atomicAdd(&s[512 + ((k >> 16) & 255u)], 1u);
+		atomicAdd(&s[768 + (k >> 24)], 1u);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x)
+		if (s[i]) atomicAdd(&hist[i], s[i]);
+}
+
+// ------------------------------------------------------------------ onesweep radix pass
+// One stable LSD pass over (key,value) pairs on digit (key >> shift) & (2^bits - 1), bits <= 9.
+// Chained-scan ("onesweep") formulation: every block takes a dynamic tile id, ranks its 4096
+// keys locally, publishes its per-digit counts and resolves its global offsets by decoupled
+// look-back over the predecessors' status words; digit totals come from `digit_counts`.
+// vals_in == nullptr means value i = i (first depth pass); keys_out == nullptr skips the key
+// write (last tile pass).
+struct OnesweepSmem {
+	uint32_t warp_hist[kSortThreads / 32][kMaxBins]; // per-warp digit counters -> warp offsets
+	uint32_t bin_start[kMaxBins];                    // exclusive prefix of the tile's digit totals
+	uint32_t global_base[kMaxBins];                  // global offset of digit run minus bin_start
+	uint32_t keys[kSortItemsPerBlock];
+	uint32_t vals[kSortItemsPerBlock];
+	uint32_t warp_tmp[8];
+	uint32_t tile;
+};
+
+__global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
+	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+	uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+	uint32_t n, int shift, int bits,
+	const uint32_t* __restrict__ digit_counts, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int nbins = 1 << bits;
+	const uint32_t mask = (uint32_t)nbins - 1u;
+
+	if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+	for (int i = tid; i < (kSortThreads / 32) * kMaxBins; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
+	// global digit starts: exclusive scan of the pass histogram
+	for (int b = tid; b < nbins; b += kSortThreads) sm.global_base[b] = digit_counts[b];
+	__syncthreads();
+	block_exclusive_scan_512(sm.global_base, nbins, sm.warp_tmp);
+
+	const uint32_t tile = sm.tile;
+	const uint32_t tile_base = tile * (uint32_t)kSortItemsPerBlock;
+	const uint32_t tile_count = min((uint32_t)kSortItemsPerBlock, n - tile_base);
+
+	// ---- load (warp-striped) and rank ----
+	uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+	const uint32_t warp_base = tile_base + warp * (32 * kSortItems);
+#pragma unroll
+	for (int k = 0; k < kSortItems; k++) {
+		uint32_t idx = warp_base + k * 32 + lane;
+		bool valid = idx < n;
+		key[k] = valid ? keys_in[idx] : 0xFFFFFFFFu;
+		val[k] = valid ? (vals_in ? vals_in[idx] : idx) : 0u;
+	}
+#pragma unroll
+	for (int k = 0; k < kSortItems; k++) {
+		uint32_t idx = warp_base + k * 32 + lane;
+		bool valid = idx < n;
+		uint32_t d = valid ? ((key[k] >> shift) & mask) : 0xFFFFFFFFu;
+		unsigned peers = __match_any_sync(0xffffffffu, d);
+		int rank_in = __popc(peers & lanemask_lt());
+		uint32_t prev = 0;
+		if (valid && rank_in == 0) {
+			prev = sm.warp_hist[warp][d];
+			sm.warp_hist[warp][d] = prev + __popc(peers);
+		}
+		__syncwarp();
+		prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
+		rank[k] = prev + rank_in;
+	}
+	__syncthreads();
+
+	// ---- per-digit totals, warp offsets, tile-local digit starts ----
+	for (int b = tid; b < nbins; b += kSortThreads) {
+		uint32_t run = 0;
+#pragma unroll
+		for (int w = 0; w < kSortThreads / 32; w++) {
+			uint32_t c = sm.warp_hist[w][b];
+			sm.warp_hist[w][b] = run;
+			run += c;
+		}
+		sm.bin_start[b] = run; // total for now
+	}
+	__syncthreads();
+
+	// ---- decoupled look-back (one thread per digit) ----
+	for (int b = tid; b < nbins; b += kSortThreads) {
+		const uint32_t total = sm.bin_start[b];
+		uint32_t excl = 0;
+		if (tile == 0) {
+			st_release(&status[b], kFlagInclusive | total);
+		} else {
+			st_release(&status[(size_t)tile * nbins + b], kFlagPartial | total);
+			int t = (int)tile - 1;
+			while (true) {
+				uint32_t s = ld_acquire(&status[(size_t)t * nbins + b]);
+				uint32_t flag = s & ~kValueMask;
+				if (flag == 0) continue; // predecessor has not published yet
+				excl += s & kValueMask;
+				if (flag == kFlagInclusive) break;
+				t--;
+			}
+			st_release(&status[(size_t)tile * nbins + b], kFlagInclusive | (excl + total));
+		}
+		sm.global_base[b] += excl; // digit start + keys of this digit in earlier tiles
+	}
+	__syncthreads();
+	block_exclusive_scan_512(sm.bin_start, nbins, sm.warp_tmp); // totals -> tile-local starts
+	for (int b = tid; b < nbins; b += kSortThreads) sm.global_base[b] -= sm.bin_start[b];
+	__syncthreads();
+
+	// ---- stage into digit order, then coalesced scatter ----
+#pragma unroll
+	for (int k = 0; k < kSortItems; k++) {
+		uint32_t idx = warp_base + k * 32 + lane;
+		if (idx < n) {
+			uint32_t d = (key[k] >> shift) & mask;
+			uint32_t pos = sm.bin_start[d] + sm.warp_hist[warp][d] + rank[k];
+			sm.keys[pos] = key[k];
+			sm.vals[pos] = val[k];
+		}
+	}
+	__syncthreads();
+	for (uint32_t j = tid; j < tile_count; j += kSortThreads) {
+		uint32_t kk = sm.keys[j];
+		uint32_t d = (kk >> shift) & mask;
+		uint32_t out = sm.global_base[d] + j;
+		if (keys_out) keys_out[out] = kk;
+		vals_out[out] = sm.vals[j];
+	}
+}
+
+// ------------------------------------------------------------------ exclusive scan (look-back)
+// out[i] = sum_{j<i} counts[order[j]] for i in [0, n]; out has n+1 entries.
+struct ScanSmem {
+	uint32_t warp_tmp[8];
+	uint32_t tile;
+	uint32_t tile_excl;
+};
+__global__ void __launch_bounds__(kSortThreads) gather_scan_kernel(
+	const uint32_t* __restrict__ counts, const uint32_t* __restrict__ order, uint32_t n,
+	uint32_t* __restrict__ out, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket)
+{
+	__shared__ ScanSmem sm;
+	const int tid = threadIdx.x;
+	if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+	__syncthreads();
+	const uint32_t tile = sm.tile;
+	const uint32_t base = tile * (uint32_t)kSortItemsPerBlock + tid * kSortItems; // blocked arrangement
+
+	uint32_t v[kSortItems];
+	uint32_t sum = 0;
+#pragma unroll
+	for (int k = 0; k < kSortItems; k++) {
+		uint32_t i = base + k;
+		v[k] = (i < n) ? counts[order[i]] : 0u;
+		sum += v[k];
+	}
+	uint32_t incl = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+		if ((tid & 31) >= o) incl += u;
+	}
+	if ((tid & 31) == 31) sm.warp_tmp[tid >> 5] = incl;
+	__syncthreads();
+	uint32_t warp_off = 0, tile_total = 0;
+#pragma unroll
+	for (int w = 0; w < kSortThreads / 32; w++) {
+		uint32_t t = sm.warp_tmp[w];
+		if (w < (tid >> 5)) warp_off += t;
+		tile_total += t;
+	}
+	if (tid == 0) {
+		uint32_t excl = 0;
+		if (tile == 0) {
+			st_release(&status[0], kFlagInclusive | tile_total);
+		} else {
+			st_release(&status[tile], kFlagPartial | tile_total);
+			int t = (int)tile - 1;
+			while (true) {
+				uint32_t s = ld_acquire(&status[t]);
+				uint32_t flag = s & ~kValueMask;
+				if (flag == 0) continue;
+				excl += s & kValueMask;
+				if (flag == kFlagInclusive) break;
+				t--;
+			}
+			st_release(&status[tile], kFlagInclusive | (excl + tile_total));
+		}
+		sm.tile_excl = excl;
+	}
+	__syncthreads();
+	uint32_t run = sm.tile_excl + warp_off + incl - sum;
+#pragma unroll
+	for (int k = 0; k < kSortItems; k++) {
+		uint32_t i = base + k;
+		if (i < n) out[i] = run;
+		run += v[k];
+		if (i == n - 1) out[n] = run;
+	}
+}
+
+// ------------------------------------------------------------------ tile counts -> ranges + digit histograms
+// Single block.  tile_diff is the (gy+1) x (gx+1) 2-D difference array (+1 at (y0,x0) and (y1,x1),
+// -1 at (y0,x1) and (y1,x0) per Gaussian).  Produces per-tile counts (2-D prefix sum), `ranges`
+// (their exclusive prefix in row-major tile order; empty tiles stay (0,0) like the reference's
+// memset + identifyTileRanges) and the per-pass digit histograms of the tile-id sort.
+__global__ void __launch_bounds__(1024) tile_ranges_kernel(
+	int* __restrict__ tile_diff, int gx, int gy, uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
+	uint32_t* __restrict__ tile_hist, TileSortPlan plan)
+{
+	__shared__ uint32_t s_warp[32];
+	__shared__ uint32_t s_hist[kMaxTilePasses * kMaxBins];
+	const int tid = threadIdx.x, nthreads = blockDim.x;
+	const int T = gx * gy, pitch = gx + 1;
+
+	for (int i = tid; i < kMaxTilePasses * kMaxBins; i += nthreads) s_hist[i] = 0;
+	// column prefix (down the rows)
+	for (int x = tid; x < pitch; x += nthreads) {
+		int run = 0;
+		for (int y = 0; y <= gy; y++) {
+			run += tile_diff[y * pitch + x];
+			tile_diff[y * pitch + x] = run;
+		}
+	}
+	__syncthreads();
+	// row prefix (along x), one warp per row at a time -> tile_count
+	const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+	for (int y = warp; y < gy; y += nwarps) {
+		int carry = 0;
+		for (int x0 = 0; x0 < gx; x0 += 32) {
+			int x = x0 + lane;
+			int v = (x < gx) ? tile_diff[y * pitch + x] : 0;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				int u = __shfl_up_sync(0xffffffffu, v, o);
+				if (lane >= o) v += u;
+			}
+			v += carry;
+			if (x < gx) tile_count[y * gx + x] = (uint32_t)v;
+			carry = __shfl_sync(0xffffffffu, v, 31);
+		}
+	}
+	__syncthreads();
+	// exclusive scan over T tiles (row-major): contiguous chunk per thread
+	const int chunk = (T + nthreads - 1) / nthreads;
+	const int begin = min(T, tid * chunk), end = min(T, begin + chunk);
+	uint32_t sum = 0;
+	for (int t = begin; t < end; t++) sum += tile_count[t];
+	uint32_t incl = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += u;
+	}
+	if (lane == 31) s_warp[warp] = incl;
+	__syncthreads();
+	uint32_t warp_off = 0;
+	for (int w = 0; w < warp; w++) warp_off += s_warp[w];
+	uint32_t run = warp_off + incl - sum;
+	for (int t = begin; t < end; t++) {
+		uint32_t c = tile_count[t];
+		ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+		if (c) {
+			for (int p = 0; p < plan.passes; p++)
+				atomicAdd(&s_hist[p * kMaxBins + (((uint32_t)t >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))], c);
+		}
+		run += c;
+	}
+	__syncthreads();
+	for (int i = tid; i < kMaxTilePasses * kMaxBins; i += nthreads) tile_hist[i] = s_hist[i];
+}
+
+// ------------------------------------------------------------------ load-balanced emission
+// Output slot o in [0, R) belongs to the depth-ordered Gaussian i with emit_offset[i] <= o <
+// emit_offset[i+1]; inside a Gaussian, slots walk its tile rect row-major (the order of
+// duplicateWithKeys, rasterizer_impl.cu:127-138).  Each block produces kEmitPerBlock consecutive
+// slots, so work is even no matter how many tiles a single (e.g. polar) Gaussian covers, and all
+// stores are fully coalesced.
+constexpr int kEmitThreads = 256;
+constexpr int kEmitPerBlock = 2048;
+
+__global__ void __launch_bounds__(kEmitThreads) emit_instances_kernel(
+	const uint32_t* __restrict__ emit_offset /*P+1*/, const uint32_t* __restrict__ order /*P*/,
+	const uint2* __restrict__ rect, uint32_t P, uint32_t R, int gx,
+	uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ values)
+{
+	__shared__ uint32_t s_off[kEmitPerBlock + 2];
+	__shared__ uint32_t s_gid[kEmitPerBlock + 1];
+	__shared__ uint2 s_rect[kEmitPerBlock + 1];
+	__shared__ uint32_t s_first, s_last;
+
+	const uint32_t o0 = blockIdx.x * (uint32_t)kEmitPerBlock;
+	if (o0 >= R) return;
+	const uint32_t o1 = min(R, o0 + (uint32_t)kEmitPerBlock);
+	const int tid = threadIdx.x;
+
+	if (tid < 2) {
+		// largest i with emit_offset[i] <= target (upper_bound - 1) over i in [0, P)
+		uint32_t target = tid == 0 ? o0 : o1 - 1;
+		uint32_t lo = 0, hi = P; // invariant: emit_offset[lo] <= target, answer in [lo, hi)
+		while (hi - lo > 1) {
+			uint32_t mid = (lo + hi) >> 1;
+			if (emit_offset[mid] <= target) lo = mid; else hi = mid;
+		}
+		if (tid == 0) s_first = lo; else s_last = lo;
+	}
+	__syncthreads();
+	const uint32_t first = s_first, last = s_last;
+	const uint32_t ns = last - first + 1; // <= kEmitPerBlock + 1: every source in range owns >= 1 slot here
+	for (uint32_t i = tid; i < ns; i += kEmitThreads) {
+		uint32_t g = order[first + i];
+		s_off[i] = emit_offset[first + i];
+		s_gid[i] = g;
+		s_rect[i] = rect[g];
+	}
+	if (tid == 0) s_off[ns] = 0xFFFFFFFFu;
+	__syncthreads();
+
+	for (uint32_t o = o0 + tid; o < o1; o += kEmitThreads) {
+		uint32_t lo = 0, hi = ns;
+		while (hi - lo > 1) {
+			uint32_t mid = (lo + hi) >> 1;
+			if (s_off[mid] <= o) lo = mid; else hi = mid;
+		}
+		uint2 rc = s_rect[lo];
+		uint32_t x0 = rc.x & 0xFFFFu, x1 = rc.x >> 16, y0 = rc.y & 0xFFFFu;
+		uint32_t w = x1 - x0;
+		uint32_t local = o - s_off[lo];
+		uint32_t y = y0 + local / w, x = x0 + local % w;
+		tile_keys[o] = y * (uint32_t)gx + x;
+		values[o] = s_gid[lo];
+	}
+}
+
+// ------------------------------------------------------------------ test-only: rebuild the 64-bit keys
+__global__ void rebuild_keys_kernel(const uint2* __restrict__ ranges, int T, const uint32_t* __restrict__ point_list,
+                                    const float* __restrict__ depth, unsigned long long* __restrict__ keys)
+{
+	int t = blockIdx.x;
+	if (t >= T) return;
+	uint2 r = ranges[t];
+	for (uint32_t i = r.x + threadIdx.x; i < r.y; i += blockDim.x)
+		keys[i] = ((unsigned long long)(uint32_t)t << 32) | (unsigned long long)__float_as_uint(depth[point_list[i]]);
+}
+
+// ------------------------------------------------------------------ host-side launch helpers
+TileSortPlan make_tile_sort_plan(int W, int H)
+{
+	TileSortPlan p{};
+	int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
+	p.bit = (int)higher_msb((uint32_t)(gx * gy));
+	p.passes = (p.bit + 8) / 9;
+	if (p.passes < 1) p.passes = 1;
+	int per = (p.bit + p.passes - 1) / p.passes, s = 0;
+	for (int i = 0; i < p.passes; i++) {
+		p.shift[i] = s;
+		p.bits[i] = (p.bit - s < per) ? (p.bit - s) : per;
+		if (p.bits[i] < 1) p.bits[i] = 1;
+		s += p.bits[i];
+	}
+	return p;
+}
+
+static cudaError_t ensure_onesweep_smem()
+{
+	static bool done = false;
+	if (done) return cudaSuccess;
+	cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                     (int)sizeof(OnesweepSmem));
+	if (e == cudaSuccess) done = true;
+	return e;
+}
+
+// Depth ordering of the P Gaussians (stage 1).  Keys: g.sort_key[0]; result order in g.sort_val[0];
+// then emit_offset (P+1) in that order.
+int launch_depth_order(const GeomState& g, int P, cudaStream_t st)
+{
+	OGS_CUDA_TRY(ensure_onesweep_smem());
+	const uint32_t n = (uint32_t)P;
+	const int tiles = ceil_div(P, kSortItemsPerBlock);
+	int hist_blocks = min(ceil_div(P, 256 * 8), kNumSMs * 4);
+	if (hist_blocks < 1) hist_blocks = 1;
+	depth_histogram_kernel<<<hist_blocks, 256, 0, st>>>(g.sort_key[0], n, g.depth_hist);
+	unsigned int* tickets = reinterpret_cast<unsigned int*>(g.scalars + 2);
+	for (int p = 0; p < 4; p++) {
+		const uint32_t* kin = g.sort_key[p & 1];
+		const uint32_t* vin = p == 0 ? nullptr : g.sort_val[p & 1];
+		uint32_t* kout = g.sort_key[(p + 1) & 1];
+		uint32_t* vout = g.sort_val[(p + 1) & 1];
+		onesweep_pass_kernel<<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(
+			kin, vin, kout, vout, n, 8 * p, 8, g.depth_hist + 256 * p,
+			g.depth_status + (size_t)p * tiles * 256, tickets + p);
+	}
+	// 4 passes: result back in buffer 0
+	gather_scan_kernel<<<tiles, kSortThreads, 0, st>>>(g.tiles_touched, g.sort_val[0], n, g.emit_offset,
+	                                                  g.scan_status, tickets + 4);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+int launch_tile_ranges(const ImageState& img, int W, int H, cudaStream_t st)
+{
+	int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
+	tile_ranges_kernel<<<1, 1024, 0, st>>>(img.tile_diff, gx, gy, img.tile_count, img.ranges, img.tile_hist,
+	                                       make_tile_sort_plan(W, H));
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+// Emission + tile-id sort (stage 2).  Leaves the sorted Gaussian list in b.point_list.
+int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const BinningState& b,
+                              int P, int64_t R, int W, int H, cudaStream_t st)
+{
+	if (R <= 0) return OGS_OK;
+	OGS_CUDA_TRY(ensure_onesweep_smem());
+	const int gx = ceil_div(W, kTile);
+	const TileSortPlan plan = make_tile_sort_plan(W, H);
+	const uint32_t n = (uint32_t)R;
+	emit_instances_kernel<<<(unsigned)((R + kEmitPerBlock - 1) / kEmitPerBlock), kEmitThreads, 0, st>>>(
+		g.emit_offset, g.sort_val[0], g.rect, (uint32_t)P, n, gx, b.key[0], b.val[0]);
+	const int tiles = (int)((R + kSortItemsPerBlock - 1) / kSortItemsPerBlock);
+	size_t status_off = 0;
+	for (int p = 0; p < plan.passes; p++) {
+		const bool last = (p == plan.passes - 1);
+		onesweep_pass_kernel<<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(
+			b.key[p & 1], b.val[p & 1], last ? nullptr : b.key[(p + 1) & 1], b.val[(p + 1) & 1],
+			n, plan.shift[p], plan.bits[p], img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p);
+		status_off += (size_t)tiles << plan.bits[p];
+	}
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+int launch_rebuild_keys(const ImageState& img, const BinningState& b, const GeomState& g, int W, int H,
+                        uint64_t* keys, cudaStream_t st)
+{
+	int T = ceil_div(W, kTile) * ceil_div(H, kTile);
+	rebuild_keys_kernel<<<T, 128, 0, st>>>(img.ranges, T, b.point_list, g.depth,
+	                                       reinterpret_cast<unsigned long long*>(keys));
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+} // namespace ogs

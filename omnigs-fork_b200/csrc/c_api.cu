@@ -1,0 +1,450 @@
+// c_api.cu — the C ABI of libomnigs_b200.so (include/omnigs_b200.h): buffer layouts,
+// orchestration of the forward (two stages) and backward, test-only exports.
+//
+// Orchestration mirrors CudaRasterizer::LonlatRasterizer::{forward,backward,markVisible}
+// (reference cuda_rasterizer/rasterizer_impl.cu:540-697, :701-795, :185-192).
+#include "ogs_common.cuh"
+#include "launchers.cuh"
+
+#include <mutex>
+#include <string>
+
+namespace ogs {
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+int fail(int code, const char* msg)
+{
+	g_last_error = msg ? msg : "";
+	return code;
+}
+int fail_cuda(cudaError_t e)
+{
+	g_last_error = std::string("CUDA error: ") + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
+	return OGS_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ layouts
+namespace {
+constexpr size_t kAlign = 256;
+
+struct Carver {
+	char* base;
+	size_t off = 0;
+	explicit Carver(char* b) : base(b) {}
+	template <typename T>
+	T* take(size_t count)
+	{
+		off = align_up(off, kAlign);
+		T* p = reinterpret_cast<T*>(base + off);
+		off += count * sizeof(T);
+		return p;
+	}
+};
+
+int sort_tiles(int64_t n) { return (int)((n + kSortItemsPerBlock - 1) / kSortItemsPerBlock); }
+
+GeomState carve_geom(char* base, int P, size_t* total)
+{
+	Carver c(base);
+	GeomState g{};
+	const size_t p = (size_t)P;
+	g.g0 = c.take<float4>(p);
+	g.g1 = c.take<float4>(p);
+	g.gb = c.take<float>(p);
+	g.depth = c.take<float>(p);
+	g.rect = c.take<uint2>(p);
+	g.tiles_touched = c.take<uint32_t>(p);
+	g.cov3D = c.take<float>(6 * p);
+	g.clamped = c.take<uint8_t>(p);
+	g.sort_key[0] = c.take<uint32_t>(p);
+	g.sort_key[1] = c.take<uint32_t>(p);
+	g.sort_val[0] = c.take<uint32_t>(p);
+	g.sort_val[1] = c.take<uint32_t>(p);
+	g.emit_offset = c.take<uint32_t>(p + 1);
+	g.grad_acc = c.take<float>(12 * p);
+	// ---- zero-filled every forward ----
+	const int tiles = sort_tiles(P);
+	g.depth_hist = c.take<uint32_t>(4 * 256);
+	g.zero_begin = reinterpret_cast<char*>(g.depth_hist);
+	g.depth_status = c.take<uint32_t>((size_t)4 * tiles * 256);
+	g.scan_status = c.take<uint32_t>((size_t)tiles + 1);
+	g.scalars = c.take<unsigned long long>(8);
+	g.scalars_bytes = 64;
+	c.off = align_up(c.off, kAlign);
+	g.zero_bytes = (size_t)((base + c.off) - g.zero_begin);
+	if (total) *total = c.off + kAlign;
+	return g;
+}
+
+ImageState carve_img(char* base, int W, int H, size_t* total)
+{
+	Carver c(base);
+	ImageState s{};
+	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
+	const size_t N = (size_t)W * H, T = (size_t)gx * gy;
+	s.final_T = c.take<float>(N);
+	s.n_contrib = c.take<uint32_t>(N);
+	s.ranges = c.take<uint2>(T);
+	s.tile_diff = c.take<int>((size_t)(gx + 1) * (gy + 1));
+	s.tile_count = c.take<uint32_t>(T);
+	s.tile_hist = c.take<uint32_t>((size_t)kMaxTilePasses * kMaxBins);
+	if (total) *total = align_up(c.off, kAlign) + kAlign;
+	return s;
+}
+
+BinningState carve_binning(char* base, int64_t R, int W, int H, size_t* total)
+{
+	Carver c(base);
+	BinningState b{};
+	const size_t r = (size_t)(R > 0 ? R : 0);
+	const TileSortPlan plan = make_tile_sort_plan(W, H);
+	b.key[0] = c.take<uint32_t>(r);
+	b.key[1] = c.take<uint32_t>(r);
+	b.val[0] = c.take<uint32_t>(r);
+	b.val[1] = c.take<uint32_t>(r);
+	b.point_list = b.val[plan.passes & 1];
+	size_t status_words = 0;
+	const int tiles = sort_tiles(R);
+	for (int p = 0; p < plan.passes; p++) status_words += (size_t)tiles << plan.bits[p];
+	b.status = c.take<uint32_t>(status_words);
+	b.zero_begin = reinterpret_cast<char*>(b.status);
+	b.tickets = c.take<unsigned int>(kMaxTilePasses);
+	c.off = align_up(c.off, kAlign);
+	b.zero_bytes = (size_t)((base + c.off) - b.zero_begin);
+	if (total) *total = c.off + kAlign;
+	return b;
+}
+
+char* aligned_base(char* p)
+{
+	return reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p), kAlign));
+}
+} // namespace
+
+size_t GeomState::bytes(int P) { size_t t; carve_geom(nullptr, P, &t); return t; }
+GeomState GeomState::carve(char* base, int P) { return carve_geom(aligned_base(base), P, nullptr); }
+size_t ImageState::bytes(int W, int H) { size_t t; carve_img(nullptr, W, H, &t); return t; }
+ImageState ImageState::carve(char* base, int W, int H) { return carve_img(aligned_base(base), W, H, nullptr); }
+size_t BinningState::bytes(int64_t R, int W, int H) { size_t t; carve_binning(nullptr, R, W, H, &t); return t; }
+BinningState BinningState::carve(char* base, int64_t R, int W, int H) { return carve_binning(aligned_base(base), R, W, H, nullptr); }
+
+// ------------------------------------------------------------------ num_rendered read-back slot
+namespace {
+struct Readback {
+	unsigned long long* pinned = nullptr;
+	cudaEvent_t event = nullptr;
+};
+constexpr int kMaxDevices = 64;
+std::mutex g_rb_mutex;
+thread_local Readback g_rb[kMaxDevices];
+
+int get_readback(Readback** out)
+{
+	int dev = 0;
+	OGS_CUDA_TRY(cudaGetDevice(&dev));
+	if (dev < 0 || dev >= kMaxDevices) return fail(OGS_ERR_NO_DEVICE, "device ordinal out of range");
+	Readback& rb = g_rb[dev];
+	if (!rb.pinned) {
+		std::lock_guard<std::mutex> lock(g_rb_mutex);
+		OGS_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&rb.pinned), 64));
+		OGS_CUDA_TRY(cudaEventCreateWithFlags(&rb.event, cudaEventDisableTiming));
+	}
+	*out = &rb;
+	return OGS_OK;
+}
+
+__global__ void export_geometry_kernel(int P, const float4* g0, const float4* g1, const float* gb, const float* depth,
+                                       const uint32_t* tiles, const uint8_t* clamped, const float* cov3D_in,
+                                       float* means2D, float* depths, float* conic_opacity, float* rgb,
+                                       uint32_t* tiles_touched, uint8_t* clamped_out, float* cov3D)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	const bool vis = tiles[i] > 0;
+	float4 a = vis ? g0[i] : make_float4(0, 0, 0, 0);
+	float4 b = vis ? g1[i] : make_float4(0, 0, 0, 0);
+	float cb = vis ? gb[i] : 0.f;
+	if (means2D) { means2D[2 * i] = a.x; means2D[2 * i + 1] = a.y; }
+	if (depths) depths[i] = vis ? depth[i] : 0.f;
+	if (conic_opacity) { conic_opacity[4 * i] = a.z; conic_opacity[4 * i + 1] = a.w; conic_opacity[4 * i + 2] = b.x; conic_opacity[4 * i + 3] = b.y; }
+	if (rgb) { rgb[3 * i] = b.z; rgb[3 * i + 1] = b.w; rgb[3 * i + 2] = cb; }
+	if (tiles_touched) tiles_touched[i] = tiles[i];
+	if (clamped_out) {
+		unsigned m = vis ? clamped[i] : 0u;
+		clamped_out[3 * i] = m & 1u; clamped_out[3 * i + 1] = (m >> 1) & 1u; clamped_out[3 * i + 2] = (m >> 2) & 1u;
+	}
+	if (cov3D)
+		for (int k = 0; k < 6; k++) cov3D[6 * (size_t)i + k] = vis ? cov3D_in[6 * (size_t)i + k] : 0.f;
+}
+
+int check_image(int W, int H)
+{
+	if (W <= 0 || H <= 0) return fail(OGS_ERR_INVALID_ARG, "image size must be positive");
+	if (ceil_div(W, kTile) > 65535 || ceil_div(H, kTile) > 65535)
+		return fail(OGS_ERR_TOO_MANY, "more than 65535 tiles along an axis");
+	if ((int64_t)ceil_div(W, kTile) * ceil_div(H, kTile) >= (1ll << 30))
+		return fail(OGS_ERR_TOO_MANY, "too many tiles");
+	return OGS_OK;
+}
+
+int forward_stage1_impl(
+	int P, int D, int M, int W, int H, int band_y0, int band_y1,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* campos,
+	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, cudaStream_t st)
+{
+	if (P < 0 || !num_rendered_host) return fail(OGS_ERR_INVALID_ARG, "bad P / num_rendered_host");
+	if (int rc = check_image(W, H)) return rc;
+	*num_rendered_host = 0;
+	if (!img_buffer) return fail(OGS_ERR_INVALID_ARG, "img_buffer is NULL");
+	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
+	ImageState img = ImageState::carve(img_buffer, W, H);
+	OGS_CUDA_TRY(cudaMemsetAsync(img.tile_diff, 0, sizeof(int) * (size_t)(gx + 1) * (gy + 1), st));
+	if (P == 0) return launch_tile_ranges(img, W, H, st);
+
+	if (!means3D || !opacities || !viewmatrix || !campos || !radii || !geom_buffer)
+		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	if ((shs == nullptr) == (colors_precomp == nullptr))
+		return fail(OGS_ERR_INVALID_ARG, "exactly one of shs / colors_precomp must be given");
+	if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+		return fail(OGS_ERR_INVALID_ARG, "exactly one of (scales, rotations) / cov3D_precomp must be given");
+	if (shs && (M <= 0 || (D + 1) * (D + 1) > M || D < 0 || D > 3))
+		return fail(OGS_ERR_INVALID_ARG, "SH degree / coefficient count mismatch");
+	band_y0 = max(0, band_y0);
+	band_y1 = min(gy, band_y1);
+
+	GeomState g = GeomState::carve(geom_buffer, P);
+	OGS_CUDA_TRY(cudaMemsetAsync(g.zero_begin, 0, g.zero_bytes, st));
+
+	PreprocessFwdArgs a{};
+	a.P = P; a.D = D; a.M = M; a.W = W; a.H = H; a.gx = gx; a.gy = gy; a.band_y0 = band_y0; a.band_y1 = band_y1;
+	a.scale_modifier = scale_modifier;
+	a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
+	a.scales = scales; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+	a.viewmatrix = viewmatrix; a.campos = campos; a.radii = radii;
+	a.g0 = g.g0; a.g1 = g.g1; a.gb = g.gb; a.depth = g.depth; a.rect = g.rect;
+	a.tiles_touched = g.tiles_touched; a.cov3D = g.cov3D; a.clamped = g.clamped;
+	a.sort_key = g.sort_key[0]; a.tile_diff = img.tile_diff; a.total_tiles = g.scalars;
+	if (int rc = launch_preprocess_fwd(a, st)) return rc;
+
+	// num_rendered read-back (the reference blocks here too, rasterizer_impl.cu:627-628); the
+	// R-independent kernels are queued behind the copy so they overlap the host round trip.
+	Readback* rb = nullptr;
+	if (int rc = get_readback(&rb)) return rc;
+	OGS_CUDA_TRY(cudaMemcpyAsync(rb->pinned, g.scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	OGS_CUDA_TRY(cudaEventRecord(rb->event, st));
+	if (int rc = launch_depth_order(g, P, st)) return rc;
+	if (int rc = launch_tile_ranges(img, W, H, st)) return rc;
+	OGS_CUDA_TRY(cudaEventSynchronize(rb->event));
+	const unsigned long long total = *rb->pinned;
+	if (total >= (1ull << 30)) {
+		*num_rendered_host = (int64_t)total;
+		return fail(OGS_ERR_TOO_MANY, "num_rendered >= 2^30 tile instances");
+	}
+	*num_rendered_host = (int64_t)total;
+	return OGS_OK;
+}
+} // namespace
+
+} // namespace ogs
+
+using namespace ogs;
+
+extern "C" {
+
+OGS_API int ogs_abi_version(void) { return OGS_ABI_VERSION; }
+OGS_API const char* ogs_last_error(void) { return g_last_error.c_str(); }
+
+OGS_API size_t ogs_geom_bytes(int P) { return GeomState::bytes(P < 0 ? 0 : P); }
+OGS_API size_t ogs_img_bytes(int W, int H) { return (W <= 0 || H <= 0) ? 0 : ImageState::bytes(W, H); }
+OGS_API size_t ogs_binning_bytes(int64_t R, int W, int H) { return (W <= 0 || H <= 0) ? 0 : BinningState::bytes(R, W, H); }
+
+OGS_API int ogs_lonlat_forward_stage1(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* campos,
+	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, void* stream)
+{
+	return forward_stage1_impl(P, D, M, W, H, 0, 1 << 30, means3D, shs, colors_precomp, opacities, scales,
+	                           scale_modifier, rotations, cov3D_precomp, viewmatrix, campos, radii,
+	                           geom_buffer, img_buffer, num_rendered_host, (cudaStream_t)stream);
+}
+
+OGS_API int ogs_lonlat_forward_stage1_band(
+	int P, int D, int M, int W, int H, int band_ty0, int band_ty1,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* campos,
+	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, void* stream)
+{
+	if (band_ty0 < 0 || band_ty1 < band_ty0) return fail(OGS_ERR_INVALID_ARG, "bad latitude band");
+	return forward_stage1_impl(P, D, M, W, H, band_ty0, band_ty1, means3D, shs, colors_precomp, opacities, scales,
+	                           scale_modifier, rotations, cov3D_precomp, viewmatrix, campos, radii,
+	                           geom_buffer, img_buffer, num_rendered_host, (cudaStream_t)stream);
+}
+
+OGS_API int ogs_lonlat_forward_stage2(
+	int P, int W, int H, int64_t num_rendered, const float* background,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, float* out_color, void* stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (P < 0 || num_rendered < 0 || !background || !img_buffer || !out_color)
+		return fail(OGS_ERR_INVALID_ARG, "bad argument to forward stage 2");
+	if (int rc = check_image(W, H)) return rc;
+	if (num_rendered >= (1ll << 30)) return fail(OGS_ERR_TOO_MANY, "num_rendered >= 2^30 tile instances");
+	ImageState img = ImageState::carve(img_buffer, W, H);
+	GeomState g{};
+	BinningState b{};
+	if (P > 0) {
+		if (!geom_buffer) return fail(OGS_ERR_INVALID_ARG, "geom_buffer is NULL");
+		g = GeomState::carve(geom_buffer, P);
+	}
+	if (num_rendered > 0) {
+		if (!binning_buffer) return fail(OGS_ERR_INVALID_ARG, "binning_buffer is NULL");
+		b = BinningState::carve(binning_buffer, num_rendered, W, H);
+		OGS_CUDA_TRY(cudaMemsetAsync(b.zero_begin, 0, b.zero_bytes, st));
+		if (int rc = launch_emit_and_tile_sort(g, img, b, P, num_rendered, W, H, st)) return rc;
+	}
+	return launch_render_fwd(img.ranges, b.point_list, W, H, g.g0, g.g1, g.gb, background,
+	                         img.final_T, img.n_contrib, out_color, st);
+}
+
+OGS_API int ogs_lonlat_backward(
+	int P, int D, int M, int64_t num_rendered, int W, int H,
+	const float* background,
+	const float* means3D, const float* shs, const float* colors_precomp,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* campos, const int* radii,
+	char* geom_buffer, char* binning_buffer, char* img_buffer,
+	const float* dL_dpix,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+	void* stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	(void)colors_precomp;
+	if (P < 0 || num_rendered < 0) return fail(OGS_ERR_INVALID_ARG, "bad P / num_rendered");
+	if (P == 0) return OGS_OK;
+	if (int rc = check_image(W, H)) return rc;
+	if (!background || !means3D || !viewmatrix || !campos || !radii || !geom_buffer || !img_buffer || !dL_dpix ||
+	    !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot)
+		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	if (shs && M > 0 && !dL_dsh) return fail(OGS_ERR_INVALID_ARG, "dL_dsh is NULL");
+	if (num_rendered > 0 && !binning_buffer) return fail(OGS_ERR_INVALID_ARG, "binning_buffer is NULL");
+	if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+		return fail(OGS_ERR_INVALID_ARG, "exactly one of (scales, rotations) / cov3D_precomp must be given");
+
+	GeomState g = GeomState::carve(geom_buffer, P);
+	ImageState img = ImageState::carve(img_buffer, W, H);
+	BinningState b{};
+	if (num_rendered > 0) b = BinningState::carve(binning_buffer, num_rendered, W, H);
+
+	OGS_CUDA_TRY(cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * (size_t)P, st));
+	if (int rc = launch_render_bwd(img.ranges, b.point_list, W, H, background, g.g0, g.g1, g.gb,
+	                               img.final_T, img.n_contrib, dL_dpix, g.grad_acc, st)) return rc;
+
+	PreprocessBwdArgs a{};
+	a.P = P; a.D = D; a.M = shs ? M : 0; a.W = W; a.H = H; a.scale_modifier = scale_modifier;
+	a.means3D = means3D; a.shs = shs; a.scales = scales; a.rotations = rotations;
+	a.cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
+	a.viewmatrix = viewmatrix; a.campos = campos; a.radii = radii; a.clamped = g.clamped; a.grad_acc = g.grad_acc;
+	a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
+	a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = shs ? dL_dsh : nullptr;
+	a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+	return launch_preprocess_bwd(a, st);
+}
+
+OGS_API int ogs_mark_all_visible(int P, uint8_t* present, void* stream)
+{
+	if (P < 0 || (P > 0 && !present)) return fail(OGS_ERR_INVALID_ARG, "bad argument to mark_all_visible");
+	if (P == 0) return OGS_OK;
+	return launch_mark_all_visible(P, present, (cudaStream_t)stream);
+}
+
+OGS_API int ogs_export_geometry(
+	int P, const char* geom_buffer,
+	float* means2D, float* depths, float* conic_opacity, float* rgb,
+	uint32_t* tiles_touched, uint8_t* clamped, float* cov3D, void* stream)
+{
+	if (P <= 0) return OGS_OK;
+	if (!geom_buffer) return fail(OGS_ERR_INVALID_ARG, "geom_buffer is NULL");
+	GeomState g = GeomState::carve(const_cast<char*>(geom_buffer), P);
+	export_geometry_kernel<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(
+		P, g.g0, g.g1, g.gb, g.depth, g.tiles_touched, g.clamped, g.cov3D,
+		means2D, depths, conic_opacity, rgb, tiles_touched, clamped, cov3D);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+OGS_API int ogs_export_binning(
+	int P, int W, int H, int64_t num_rendered,
+	const char* geom_buffer, const char* binning_buffer, const char* img_buffer,
+	uint32_t* point_list, uint64_t* point_list_keys, uint32_t* ranges,
+	float* final_T, uint32_t* n_contrib, void* stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (int rc = check_image(W, H)) return rc;
+	if (!img_buffer) return fail(OGS_ERR_INVALID_ARG, "img_buffer is NULL");
+	ImageState img = ImageState::carve(const_cast<char*>(img_buffer), W, H);
+	const size_t N = (size_t)W * H, T = (size_t)ceil_div(W, kTile) * ceil_div(H, kTile);
+	if (ranges) OGS_CUDA_TRY(cudaMemcpyAsync(ranges, img.ranges, sizeof(uint2) * T, cudaMemcpyDeviceToDevice, st));
+	if (final_T) OGS_CUDA_TRY(cudaMemcpyAsync(final_T, img.final_T, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+	if (n_contrib) OGS_CUDA_TRY(cudaMemcpyAsync(n_contrib, img.n_contrib, sizeof(uint32_t) * N, cudaMemcpyDeviceToDevice, st));
+	if (num_rendered > 0 && (point_list || point_list_keys)) {
+		if (!binning_buffer || !geom_buffer || P <= 0) return fail(OGS_ERR_INVALID_ARG, "buffers missing");
+		BinningState b = BinningState::carve(const_cast<char*>(binning_buffer), num_rendered, W, H);
+		GeomState g = GeomState::carve(const_cast<char*>(geom_buffer), P);
+		if (point_list)
+			OGS_CUDA_TRY(cudaMemcpyAsync(point_list, b.point_list, sizeof(uint32_t) * (size_t)num_rendered,
+			                             cudaMemcpyDeviceToDevice, st));
+		if (point_list_keys)
+			if (int rc = launch_rebuild_keys(img, b, g, W, H, point_list_keys, st)) return rc;
+	}
+	return OGS_OK;
+}
+
+OGS_API int ogs_lonlat_train_view_host(
+	int P, int D, int M, int W, int H,
+	const float* background,
+	const float* means3D, const float* shs, const float* opacities,
+	const float* scales, float scale_modifier, const float* rotations,
+	const float* viewmatrix_host, const float* campos_host, const float* dL_dpix_host,
+	float* view_scratch, float* dL_dpix_dev,
+	int* radii, char* geom_buffer, char* binning_buffer, size_t binning_capacity, char* img_buffer,
+	float* out_color_dev, float* out_color_host,
+	float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+	int64_t* num_rendered_host, size_t* binning_needed, void* stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (!viewmatrix_host || !campos_host || !dL_dpix_host || !view_scratch || !dL_dpix_dev || !out_color_dev ||
+	    !out_color_host || !num_rendered_host)
+		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	if (int rc = check_image(W, H)) return rc;
+	const size_t img_bytes = sizeof(float) * 3 * (size_t)W * H;
+	OGS_CUDA_TRY(cudaMemcpyAsync(view_scratch, viewmatrix_host, sizeof(float) * 16, cudaMemcpyHostToDevice, st));
+	OGS_CUDA_TRY(cudaMemcpyAsync(view_scratch + 16, campos_host, sizeof(float) * 3, cudaMemcpyHostToDevice, st));
+	OGS_CUDA_TRY(cudaMemcpyAsync(dL_dpix_dev, dL_dpix_host, img_bytes, cudaMemcpyHostToDevice, st));
+	if (int rc = ogs_lonlat_forward_stage1(P, D, M, W, H, means3D, shs, nullptr, opacities, scales, scale_modifier,
+	                                       rotations, nullptr, view_scratch, view_scratch + 16, radii, geom_buffer,
+	                                       img_buffer, num_rendered_host, stream)) return rc;
+	const size_t need = ogs_binning_bytes(*num_rendered_host, W, H);
+	if (binning_needed) *binning_needed = need;
+	if (need > binning_capacity) return fail(OGS_ERR_INVALID_ARG, "binning_buffer too small (see *binning_needed)");
+	if (int rc = ogs_lonlat_forward_stage2(P, W, H, *num_rendered_host, background, geom_buffer, binning_buffer,
+	                                       img_buffer, out_color_dev, stream)) return rc;
+	OGS_CUDA_TRY(cudaMemcpyAsync(out_color_host, out_color_dev, img_bytes, cudaMemcpyDeviceToHost, st));
+	if (int rc = ogs_lonlat_backward(P, D, M, *num_rendered_host, W, H, background, means3D, shs, nullptr, scales,
+	                                 scale_modifier, rotations, nullptr, view_scratch, view_scratch + 16, radii,
+	                                 geom_buffer, binning_buffer, img_buffer, dL_dpix_dev, dL_dmean2D, nullptr,
+	                                 dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot,
+	                                 stream)) return rc;
+	OGS_CUDA_TRY(cudaStreamSynchronize(st));
+	return OGS_OK;
+}
+
+} // extern "C"

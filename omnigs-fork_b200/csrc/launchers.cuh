@@ -1,0 +1,74 @@
+// launchers.cuh — kernel argument blocks and host-side launchers shared between the
+// translation units of libomnigs_b200.so.
+#pragma once
+#include "ogs_common.cuh"
+
+namespace ogs {
+
+struct PreprocessFwdArgs {
+	int P, D, M, W, H, gx, gy, band_y0, band_y1;
+	float scale_modifier;
+	const float* means3D;
+	const float* shs;
+	const float* colors_precomp;
+	const float* opacities;
+	const float* scales;
+	const float* rotations;
+	const float* cov3D_precomp;
+	const float* viewmatrix;
+	const float* campos;
+	int* radii;
+	float4* g0;
+	float4* g1;
+	float* gb;
+	float* depth;
+	uint2* rect;
+	uint32_t* tiles_touched;
+	float* cov3D;
+	uint8_t* clamped;
+	uint32_t* sort_key;
+	int* tile_diff;
+	unsigned long long* total_tiles;
+};
+struct PreprocessBwdArgs {
+	int P, D, M, W, H;
+	float scale_modifier;
+	const float* means3D;
+	const float* shs;
+	const float* scales;
+	const float* rotations;
+	const float* cov3D;
+	const float* viewmatrix;
+	const float* campos;
+	const int* radii;
+	const uint8_t* clamped;
+	const float* grad_acc;
+	float* dL_dmean2D;
+	float* dL_dconic;
+	float* dL_dopacity;
+	float* dL_dcolor;
+	float* dL_dmean3D;
+	float* dL_dcov3D;
+	float* dL_dsh;
+	float* dL_dscale;
+	float* dL_drot;
+};
+int launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t st);
+int launch_mark_all_visible(int P, uint8_t* present, cudaStream_t st);
+int launch_depth_order(const GeomState& g, int P, cudaStream_t st);
+int launch_tile_ranges(const ImageState& img, int W, int H, cudaStream_t st);
+int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const BinningState& b,
+                              int P, int64_t R, int W, int H, cudaStream_t st);
+int launch_rebuild_keys(const ImageState& img, const BinningState& b, const GeomState& g, int W, int H,
+                        uint64_t* keys, cudaStream_t st);
+int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
+                      const float4* g0, const float4* g1, const float* gb, const float* bg,
+                      float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st);
+int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, int H, const float* bg,
+                      const float4* g0, const float4* g1, const float* gb,
+                      const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
+                      float* grad_acc, cudaStream_t st);
+int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st);
+
+
+} // namespace ogs

@@ -1,0 +1,129 @@
+// preprocess_bwd.cu — fused per-Gaussian backward.
+//
+// One kernel does what the reference spreads over computeCov2DLonLatCUDA + preprocessLonLatCUDA
+// (cuda_rasterizer/backward.cu:297-485, :613-669) plus the zero-fills of its LibTorch shim
+// (src/rasterize_points.cu:200-208,246-247):
+//   packed render-backward accumulators -> dL/dmean2D, dL/dconic, dL/dopacity, dL/dcolour,
+//   conic/covariance branch (incl. the projection's second derivatives) -> dL/dcov3D, dL/dmean,
+//   screen-position branch through the Jacobian rows (kept in registers; the reference round-trips
+//   them through the dpx_dt / dpy_dt tensors) -> dL/dmean,
+//   SH backward -> dL/dsh, dL/dmean;  scale/rotation backward -> dL/dscale, dL/drot.
+// Every output element is written, exact zeros for culled Gaussians, so callers may pass
+// uninitialised memory.
+#include "lonlat_math.cuh"
+#include "launchers.cuh"
+
+namespace ogs {
+
+constexpr int kPreBwdThreads = 256;
+
+__global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(const PreprocessBwdArgs a)
+{
+	__shared__ float sV[16];
+	__shared__ float sCam[3];
+	if (threadIdx.x < 16) sV[threadIdx.x] = a.viewmatrix[threadIdx.x];
+	if (threadIdx.x < 3) sCam[threadIdx.x] = a.campos[threadIdx.x];
+	__syncthreads();
+	const int idx = blockIdx.x * kPreBwdThreads + threadIdx.x;
+	if (idx >= a.P) return;
+
+	const bool visible = a.radii[idx] > 0;
+
+	float g[9];
+	if (visible) {
+		const float4* row = reinterpret_cast<const float4*>(a.grad_acc + (size_t)idx * 12);
+		const float4 r0 = row[0], r1 = row[1];
+		g[0] = r0.x; g[1] = r0.y; g[2] = r0.z; g[3] = r0.w;
+		g[4] = r1.x; g[5] = r1.y; g[6] = r1.z; g[7] = r1.w;
+		g[8] = a.grad_acc[(size_t)idx * 12 + 8];
+	} else {
+#pragma unroll
+		for (int k = 0; k < 9; k++) g[k] = 0.f;
+	}
+
+	// the render-backward outputs in the reference's layouts
+	a.dL_dmean2D[3 * (size_t)idx + 0] = g[0];
+	a.dL_dmean2D[3 * (size_t)idx + 1] = g[1];
+	a.dL_dmean2D[3 * (size_t)idx + 2] = 0.f;
+	if (a.dL_dconic) reinterpret_cast<float4*>(a.dL_dconic)[idx] = make_float4(g[2], g[3], 0.f, g[4]);
+	a.dL_dopacity[idx] = g[5];
+	a.dL_dcolor[3 * (size_t)idx + 0] = g[6];
+	a.dL_dcolor[3 * (size_t)idx + 1] = g[7];
+	a.dL_dcolor[3 * (size_t)idx + 2] = g[8];
+
+	float dcov6[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+	float3 dmean = { 0.f, 0.f, 0.f };
+	float3 dscale = { 0.f, 0.f, 0.f };
+	float4 drot = { 0.f, 0.f, 0.f, 0.f };
+	float* dsh_row = a.dL_dsh ? a.dL_dsh + (size_t)idx * a.M * 3 : nullptr;
+
+	if (visible) {
+		float V[16];
+#pragma unroll
+		for (int i = 0; i < 16; i++) V[i] = sV[i];
+		const float3 mean = { a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2] };
+		float cov6[6];
+#pragma unroll
+		for (int i = 0; i < 6; i++) cov6[i] = a.cov3D[6 * (size_t)idx + i];
+
+		// covariance / conic branch (backward.cu:297-485); assigns dL/dmean
+		float3 dpx_dt, dpy_dt;
+		cov2d_lonlat_backward(mean, cov6, V, a.W, a.H, float3{ g[2], g[3], g[4] }, dcov6, dmean, dpx_dt, dpy_dt);
+
+		// screen-position branch (backward.cu:642-660)
+		const float dsx_dpx = 2.0f / (float)a.W;
+		const float dsy_dpy = 2.0f / (float)a.H;
+		const float dL_dpx = g[0] * dsx_dpx;
+		const float dL_dpy = g[1] * dsy_dpy;
+		const float dL_dtx = dL_dpx * dpx_dt.x + dL_dpy * dpy_dt.x;
+		const float dL_dty = dL_dpx * dpx_dt.y + dL_dpy * dpy_dt.y;
+		const float dL_dtz = dL_dpx * dpx_dt.z + dL_dpy * dpy_dt.z;
+		const float3 dm2 = view_vec_t(V, float3{ dL_dtx, dL_dty, dL_dtz });
+		dmean.x += dm2.x; dmean.y += dm2.y; dmean.z += dm2.z;
+
+		// SH backward (backward.cu:30-151)
+		if (a.shs != nullptr) {
+			const unsigned cm = a.clamped[idx];
+			V3 dRGB = { g[6], g[7], g[8] };
+			dRGB.x *= (cm & 1u) ? 0 : 1;
+			dRGB.y *= (cm & 2u) ? 0 : 1;
+			dRGB.z *= (cm & 4u) ? 0 : 1;
+			const float* shp = a.shs + (size_t)idx * a.M * 3;
+			auto sh = [shp](int k) { return V3{ shp[3 * k], shp[3 * k + 1], shp[3 * k + 2] }; };
+			auto dsh = [dsh_row](int k, V3 v) {
+				dsh_row[3 * k] = v.x; dsh_row[3 * k + 1] = v.y; dsh_row[3 * k + 2] = v.z;
+			};
+			const float3 dm3 = sh_backward(a.D, mean, float3{ sCam[0], sCam[1], sCam[2] }, sh, dRGB, dsh);
+			dmean.x += dm3.x; dmean.y += dm3.y; dmean.z += dm3.z;
+			for (int k = (a.D + 1) * (a.D + 1) * 3; k < a.M * 3; k++) dsh_row[k] = 0.f;
+		}
+
+		// scale / rotation backward (backward.cu:489-552)
+		if (a.scales != nullptr) {
+			const float3 sc = { a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2] };
+			const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+			cov3d_backward(sc, a.scale_modifier, q, dcov6, dscale, drot);
+		}
+	} else if (dsh_row) {
+		for (int k = 0; k < a.M * 3; k++) dsh_row[k] = 0.f;
+	}
+
+	a.dL_dmean3D[3 * (size_t)idx + 0] = dmean.x;
+	a.dL_dmean3D[3 * (size_t)idx + 1] = dmean.y;
+	a.dL_dmean3D[3 * (size_t)idx + 2] = dmean.z;
+#pragma unroll
+	for (int i = 0; i < 6; i++) a.dL_dcov3D[6 * (size_t)idx + i] = dcov6[i];
+	a.dL_dscale[3 * (size_t)idx + 0] = dscale.x;
+	a.dL_dscale[3 * (size_t)idx + 1] = dscale.y;
+	a.dL_dscale[3 * (size_t)idx + 2] = dscale.z;
+	reinterpret_cast<float4*>(a.dL_drot)[idx] = drot;
+}
+
+int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st)
+{
+	preprocess_lonlat_bwd_kernel<<<ceil_div(a.P, kPreBwdThreads), kPreBwdThreads, 0, st>>>(a);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+} // namespace ogs

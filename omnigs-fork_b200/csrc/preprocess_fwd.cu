@@ -1,0 +1,156 @@
+// preprocess_fwd.cu — per-Gaussian forward preprocessing for the lonlat camera.
+//
+// One thread per Gaussian.  Follows the reference's preprocessLonlatCUDA step for step
+// (cuda_rasterizer/forward.cu:593-703) so that radii / tile rects / depth keys are bit-identical,
+// but writes our own packed, gather-friendly records instead of the reference's GeometryState and
+// fuses the bookkeeping the reference does in later kernels:
+//   * sum of tiles_touched (= num_rendered) via one 64-bit atomic per block (replaces the
+//     InclusiveSum + device->host read of its last element, rasterizer_impl.cu:622-628),
+//   * the 2-D tile-coverage difference array (4 atomics per visible Gaussian) from which the tile
+//     ranges and the radix digit histograms are derived without touching the R-sized key list,
+//   * the depth-sort key (float bits of r; 0xFFFFFFFF for Gaussians that emit nothing).
+#include "lonlat_math.cuh"
+#include "launchers.cuh"
+
+namespace ogs {
+
+constexpr int kPreThreads = 256;
+
+__global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(const PreprocessFwdArgs a)
+{
+	__shared__ float sV[16];
+	__shared__ float sCam[3];
+	__shared__ unsigned long long s_block_tiles;
+	if (threadIdx.x < 16) sV[threadIdx.x] = a.viewmatrix[threadIdx.x];
+	if (threadIdx.x < 3) sCam[threadIdx.x] = a.campos[threadIdx.x];
+	if (threadIdx.x == 0) s_block_tiles = 0ull;
+	__syncthreads();
+
+	const int idx = blockIdx.x * kPreThreads + threadIdx.x;
+	uint32_t my_tiles = 0;
+
+	if (idx < a.P) {
+		float V[16];
+#pragma unroll
+		for (int i = 0; i < 16; i++) V[i] = sV[i];
+
+		int out_radius = 0;
+		uint32_t key = 0xFFFFFFFFu;
+
+		// near cull (auxiliary.h:198-220): r^2 <= 0.04 drops the Gaussian
+		const float3 p_orig = { a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2] };
+		const float3 t = view_point(V, p_orig);
+		const float rr = t.x * t.x + t.y * t.y + t.z * t.z;
+		if (!(rr <= 0.04f)) {
+			const float r = sqrtf(rr);
+
+			// lon/lat screen coordinates (auxiliary.h:236-248)
+			const float inv_r = 1.0f / (r + kEps7);
+			const float lon = atan2f(t.x, t.z);
+			const float lat = asinf(t.y * inv_r);
+			const float2 p_proj = { lon * kPiInv, lat * kTwoPiInv };
+
+			// 3-D covariance (forward.cu:643-652)
+			float cov6[6];
+			if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+				for (int i = 0; i < 6; i++) cov6[i] = a.cov3D_precomp[6 * (size_t)idx + i];
+			} else {
+				const float3 sc = { a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2] };
+				const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+				cov3d_from_scale_rot(sc, a.scale_modifier, q, cov6);
+#pragma unroll
+				for (int i = 0; i < 6; i++) a.cov3D[6 * (size_t)idx + i] = cov6[i];
+			}
+
+			// 2-D covariance through the lonlat Jacobian + 0.3 px blur (forward.cu:130-189)
+			const float3 t2 = view_point(V, p_orig);
+			const LonlatJac J = lonlat_jacobian(t2, a.W, a.H);
+			M3 T, Vrk, cov2;
+			lonlat_T_cov(J, V, cov6, T, Vrk, cov2);
+			cov2.c[0][0] += 0.3f;
+			cov2.c[1][1] += 0.3f;
+			const float3 cov = { float(cov2.c[0][0]), float(cov2.c[0][1]), float(cov2.c[1][1]) };
+
+			// conic (forward.cu:660-664)
+			const float det = (cov.x * cov.z - cov.y * cov.y);
+			if (det != 0.0f) {
+				const float det_inv = 1.f / det;
+				const float3 conic = { cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv };
+
+				// screen-space extent (forward.cu:671-683)
+				const float mid = 0.5f * (cov.x + cov.z);
+				const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+				const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+				const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+				const float2 point_image = { ndc_to_pix(p_proj.x, a.W), ndc_to_pix(p_proj.y, a.H) };
+				int x0, y0, x1, y1;
+				tile_rect(point_image, (int)my_radius, a.gx, a.gy, x0, y0, x1, y1);
+				if ((x1 - x0) * (y1 - y0) != 0) {
+					out_radius = (int)my_radius;
+					// latitude-band clip (identity for the full image)
+					const int by0 = max(y0, a.band_y0), by1 = min(y1, a.band_y1);
+					if (by1 > by0) {
+						float3 rgb;
+						unsigned cmask = 0;
+						if (a.colors_precomp == nullptr) {
+							const float* shp = a.shs + (size_t)idx * a.M * 3;
+							auto sh = [shp](int k) { return V3{ shp[3 * k], shp[3 * k + 1], shp[3 * k + 2] }; };
+							const V3 c = sh_to_rgb(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
+							rgb = { c.x, c.y, c.z };
+						} else {
+							rgb = { a.colors_precomp[3 * (size_t)idx], a.colors_precomp[3 * (size_t)idx + 1],
+							        a.colors_precomp[3 * (size_t)idx + 2] };
+						}
+						a.clamped[idx] = (uint8_t)cmask;
+						a.depth[idx] = r;
+						a.g0[idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+						a.g1[idx] = make_float4(conic.z, a.opacities[idx], rgb.x, rgb.y);
+						a.gb[idx] = rgb.z;
+						a.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));
+						my_tiles = (uint32_t)((by1 - by0) * (x1 - x0));
+						key = __float_as_uint(r);
+						const int pitch = a.gx + 1;
+						atomicAdd(&a.tile_diff[by0 * pitch + x0], 1);
+						atomicAdd(&a.tile_diff[by0 * pitch + x1], -1);
+						atomicAdd(&a.tile_diff[by1 * pitch + x0], -1);
+						atomicAdd(&a.tile_diff[by1 * pitch + x1], 1);
+					}
+				}
+			}
+		}
+		a.radii[idx] = out_radius;
+		a.tiles_touched[idx] = my_tiles;
+		a.sort_key[idx] = key;
+	}
+
+	// block total of tiles_touched -> one 64-bit atomic
+	uint32_t wsum = my_tiles;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+	if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_block_tiles, (unsigned long long)wsum);
+	__syncthreads();
+	if (threadIdx.x == 0 && s_block_tiles) atomicAdd(a.total_tiles, s_block_tiles);
+}
+
+__global__ void mark_all_visible_kernel(int P, uint8_t* present)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < P) present[i] = 1;
+}
+
+int launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t st)
+{
+	preprocess_lonlat_fwd_kernel<<<ceil_div(a.P, kPreThreads), kPreThreads, 0, st>>>(a);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+int launch_mark_all_visible(int P, uint8_t* present, cudaStream_t st)
+{
+	mark_all_visible_kernel<<<ceil_div(P, 256), 256, 0, st>>>(P, present);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+} // namespace ogs

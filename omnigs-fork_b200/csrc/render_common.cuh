@@ -1,0 +1,80 @@
+// render_common.cuh — pieces shared by the forward and backward tile kernels.
+#pragma once
+#include "ogs_common.cuh"
+
+namespace ogs {
+
+constexpr int kRenderThreads = 256;   // one 16x16 tile per CTA, one pixel per thread
+constexpr int kBatch = 256;           // list entries staged per round (reference BLOCK_SIZE)
+// Each warp owns an 8x4 pixel sub-tile (instead of the reference's 16x2 strip): a compact
+// footprint makes the per-warp sub-tile cull below reject far more (warp, Gaussian) pairs.
+constexpr int kSubW = 8, kSubH = 4;
+
+// Safety margins for skipping work that provably cannot change the result.
+// A pair (pixel, Gaussian) contributes only if alpha = min(0.99, o*exp(power)) >= 1/255, i.e.
+// power >= tau := -ln(255*o).  `power` is a float32 quadratic form; its evaluation error is
+// bounded by a few ulps of its largest term, so conservative tests subtract
+//   kCullAbs + kCullRel * (|A|dx^2 + |C|dy^2 + 2|B||dx||dy|)   (evaluated at the farthest corner)
+// before declaring "cannot contribute".  The skipped pairs are exactly pairs the reference also
+// skips (forward.cu:428-438), so images, n_contrib and gradients are unchanged.
+constexpr float kCullAbs = 0.01f;
+constexpr float kCullRel = 8e-6f;
+
+// tau_safe for the per-pixel early-out: compares against the SAME float `power` the blend uses,
+// only expf's own error (<= 2 ulp) has to be covered.
+OGS_D float alpha_power_threshold(float opacity)
+{
+	// opacity <= 0 or NaN: never skip through this path (tau = -inf)
+	return (opacity > 0.f) ? (-logf(255.0f * opacity) - 1e-3f) : -INFINITY;
+}
+
+// Can the Gaussian (mean m, conic A,B,C, threshold tau) reach alpha >= 1/255 anywhere on the
+// pixel-centre box [x0,x1]x[y0,y1]?  Conservative: returns true when unsure.
+// The maximum of power(d) = -0.5*(A dx^2 + 2B dx dy + C dy^2) over the box of offsets
+// d = m - pix is 0 when the mean lies inside; otherwise (convex form, minimiser outside the box)
+// it is attained on a face that faces the mean, where the 1-D minimiser has a closed form.
+OGS_D bool gaussian_touches_box(float mx, float my, float A, float B, float C, float tau,
+                                float x0, float y0, float x1, float y1)
+{
+	const float dx_lo = mx - x1, dx_hi = mx - x0, dy_lo = my - y1, dy_hi = my - y0;
+	const bool in_x = (dx_lo <= 0.f) && (dx_hi >= 0.f);
+	const bool in_y = (dy_lo <= 0.f) && (dy_hi >= 0.f);
+	if (in_x && in_y) return true;
+	if (!(A > 0.f && C > 0.f && A * C - B * B > 0.f)) return true; // not provably positive definite
+	float qmin = INFINITY;
+	if (!in_x) {
+		const float dx = (dx_lo > 0.f) ? dx_lo : dx_hi;
+		const float dy = fminf(fmaxf(-B * dx / C, dy_lo), dy_hi);
+		qmin = fminf(qmin, A * dx * dx + 2.f * B * dx * dy + C * dy * dy);
+	}
+	if (!in_y) {
+		const float dy = (dy_lo > 0.f) ? dy_lo : dy_hi;
+		const float dx = fminf(fmaxf(-B * dy / A, dx_lo), dx_hi);
+		qmin = fminf(qmin, A * dx * dx + 2.f * B * dx * dy + C * dy * dy);
+	}
+	const float mdx = fmaxf(fabsf(dx_lo), fabsf(dx_hi)), mdy = fmaxf(fabsf(dy_lo), fabsf(dy_hi));
+	const float mag = A * mdx * mdx + C * mdy * mdy + 2.f * fabsf(B) * mdx * mdy;
+	return -0.5f * qmin >= tau - kCullAbs - kCullRel * mag;
+}
+
+// Stable block-wide compaction slot for `keep` flags (list order must be preserved: blending is
+// order dependent).  Returns this thread's slot (valid when keep) and the block total.
+// Uses one __syncthreads; s_warp_cnt must hold kRenderThreads/32 words.
+OGS_D int block_compact_slot(bool keep, uint32_t* s_warp_cnt, int& total)
+{
+	const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+	const int warp = threadIdx.x >> 5;
+	if ((threadIdx.x & 31) == 0) s_warp_cnt[warp] = __popc(ballot);
+	__syncthreads();
+	int off = 0, tot = 0;
+#pragma unroll
+	for (int w = 0; w < kRenderThreads / 32; w++) {
+		int c = (int)s_warp_cnt[w];
+		if (w < warp) off += c;
+		tot += c;
+	}
+	total = tot;
+	return off + __popc(ballot & lanemask_lt());
+}
+
+} // namespace ogs

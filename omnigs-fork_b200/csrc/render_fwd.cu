@@ -1,0 +1,144 @@
+// render_fwd.cu — 16x16-tile front-to-back alpha blending (forward).
+//
+// Same per-pixel arithmetic, guards and outputs as the reference's renderCUDA
+// (cuda_rasterizer/forward.cu:346-467): power, alpha = min(0.99, o*exp(power)), the 1/255 and
+// T < 1e-4 cut-offs, final_T, n_contrib (1-based list position of the last blended entry) and the
+// planar [3,H,W] image with background.  What differs is how the work is organised:
+//   * each 256-entry batch of the tile's list is gathered once per CTA, tested against the tile
+//     (exact conservative ellipse/box test) and stably compacted into shared memory together with
+//     its colour, list position and alpha threshold — the reference stages every entry and reads
+//     colours from global memory per contributing pixel (forward.cu:448);
+//   * each warp owns an 8x4 sub-tile and re-tests 32 staged entries at a time (one per lane),
+//     iterating only over the ballot of entries that can reach its 32 pixels;
+//   * pairs whose power is below the per-Gaussian threshold skip expf.
+// Skipped pairs are pairs the reference skips too, so results are unchanged.
+#include "render_common.cuh"
+#include "launchers.cuh"
+
+namespace ogs {
+
+__global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
+	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
+	const float4* __restrict__ g0, const float4* __restrict__ g1, const float* __restrict__ gb,
+	const float* __restrict__ bg_color,
+	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)
+{
+	__shared__ float4 s_a[kBatch];   // mean.x, mean.y, conic.x, conic.y
+	__shared__ float4 s_b[kBatch];   // conic.z, opacity, r, g
+	__shared__ float4 s_c[kBatch];   // b, list position (1-based, as bits), tau_safe, unused
+	__shared__ uint32_t s_warp_cnt[kRenderThreads / 32];
+
+	const int tile = blockIdx.x;
+	const int tile_x = tile % gx, tile_y = tile / gx;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int sub_x0 = tile_x * kTile + (warp & 1) * kSubW;
+	const int sub_y0 = tile_y * kTile + (warp >> 1) * kSubH;
+	const int px = sub_x0 + (lane & (kSubW - 1));
+	const int py = sub_y0 + (lane / kSubW);
+	const bool inside = px < W && py < H;
+	const float2 pixf = { (float)px, (float)py };
+
+	const float tx0 = (float)(tile_x * kTile), ty0 = (float)(tile_y * kTile);
+	const float tx1 = tx0 + (kTile - 1), ty1 = ty0 + (kTile - 1);
+	const float sx0 = (float)sub_x0, sy0 = (float)sub_y0;
+	const float sx1 = sx0 + (kSubW - 1), sy1 = sy0 + (kSubH - 1);
+
+	const uint2 range = ranges[tile];
+	const int n = (int)(range.y - range.x);
+	const int rounds = (n + kBatch - 1) / kBatch;
+
+	bool done = !inside;
+	float T = 1.0f;
+	uint32_t last_contributor = 0;
+	float C[3] = { 0.f, 0.f, 0.f };
+
+	for (int round = 0; round < rounds; round++) {
+		// all pixels of the tile saturated -> stop (forward.cu:399-401); also guards smem reuse
+		if (__syncthreads_count(done) == kRenderThreads) break;
+
+		// ---- gather one entry per thread, tile-level cull ----
+		const int i = round * kBatch + threadIdx.x;
+		bool keep = false;
+		float4 a = make_float4(0, 0, 0, 0), b = a;
+		float cb = 0.f, tau = 0.f;
+		if (i < n) {
+			const uint32_t id = point_list[range.x + i];
+			a = g0[id];
+			b = g1[id];
+			cb = gb[id];
+			tau = alpha_power_threshold(b.y);
+			keep = gaussian_touches_box(a.x, a.y, a.z, a.w, b.x, tau, tx0, ty0, tx1, ty1);
+		}
+		int total;
+		const int slot = block_compact_slot(keep, s_warp_cnt, total);
+		if (keep) {
+			s_a[slot] = a;
+			s_b[slot] = b;
+			s_c[slot] = make_float4(cb, __uint_as_float((uint32_t)(i + 1)), tau, 0.f);
+		}
+		__syncthreads();
+
+		// ---- per-warp: sub-tile cull of 32 staged entries at a time, blend the survivors ----
+		for (int base = 0; base < total; base += 32) {
+			const int s = base + lane;
+			bool hit = false;
+			if (s < total) {
+				const float4 ea = s_a[s];
+				const float4 eb = s_b[s];
+				hit = gaussian_touches_box(ea.x, ea.y, ea.z, ea.w, eb.x, s_c[s].z, sx0, sy0, sx1, sy1);
+			}
+			unsigned m = __ballot_sync(0xffffffffu, hit);
+			if (__all_sync(0xffffffffu, done)) break;
+			while (m) {
+				const int j = base + __ffs(m) - 1;
+				m &= m - 1;
+				if (done) continue;
+				const float4 ea = s_a[j];
+				const float4 eb = s_b[j];
+				const float4 ec = s_c[j];
+				// forward.cu:424-427
+				const float2 xy = { ea.x, ea.y };
+				const float2 d = { xy.x - pixf.x, xy.y - pixf.y };
+				const float4 con_o = { ea.z, ea.w, eb.x, eb.y };
+				const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+				if (power > 0.0f) continue;
+				if (power < ec.z) continue; // alpha would be < 1/255 (skips expf)
+				const float alpha = fminf(0.99f, con_o.w * expf(power));
+				if (alpha < kAlphaMin) continue;
+				const float test_T = T * (1 - alpha);
+				if (test_T < 0.0001f) {
+					done = true;
+					continue;
+				}
+				C[0] += eb.z * alpha * T;
+				C[1] += eb.w * alpha * T;
+				C[2] += ec.x * alpha * T;
+				T = test_T;
+				last_contributor = __float_as_uint(ec.y);
+			}
+		}
+	}
+
+	if (inside) {
+		const size_t pix_id = (size_t)W * py + px;
+		const size_t HW = (size_t)H * W;
+		final_T[pix_id] = T;
+		n_contrib[pix_id] = last_contributor;
+		out_color[0 * HW + pix_id] = C[0] + T * bg_color[0];
+		out_color[1 * HW + pix_id] = C[1] + T * bg_color[1];
+		out_color[2 * HW + pix_id] = C[2] + T * bg_color[2];
+	}
+}
+
+int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
+                      const float4* g0, const float4* g1, const float* gb, const float* bg,
+                      float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st)
+{
+	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
+	render_fwd_kernel<<<gx * gy, kRenderThreads, 0, st>>>(ranges, point_list, W, H, gx, g0, g1, gb, bg,
+	                                                     final_T, n_contrib, out_color);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+} // namespace ogs

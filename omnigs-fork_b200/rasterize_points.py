@@ -1,0 +1,196 @@
+"""Host-side mirror of the reference's LibTorch boundary for the lonlat path.
+
+Same names, argument order/meaning, return tuples and error behaviour as
+``RasterizeGaussiansCUDA`` / ``RasterizeGaussiansBackwardCUDA`` / ``markVisible`` in the reference's
+src/rasterize_points.cu:49-319 (declared in include/rasterize_points.h:29-80), implemented on the
+C ABI of libomnigs_b200.so.  ``camera_type == 3`` (LONLAT) is the hot path this package covers;
+``camera_type == 1`` (pinhole) is outside its scope and raises NotImplementedError; any other value
+raises the reference's RuntimeError.  The C++ twin of this file is csrc/rasterize_points.cpp.
+"""
+import ctypes
+
+import torch
+
+from ._lib import load_library, check
+
+PINHOLE = 1
+LONLAT = 3
+NUM_CHANNELS = 3  # reference cuda_rasterizer/config.h:25
+
+
+def _ptr(t):
+    """Device pointer of a tensor; an empty tensor is the reference's "None" (nullptr)."""
+    if t is None or t.numel() == 0:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.numel() and t.dtype != torch.float32:
+        raise RuntimeError("expected a float32 tensor")
+    return t.contiguous()
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (libomnigs_b200 has no CPU path)")
+
+
+def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                           cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                           image_height, image_width, sh, degree, campos, prefiltered,
+                           camera_type=PINHOLE, render_depth=False):
+    """reference src/rasterize_points.cu:49-164.
+
+    Returns (num_rendered, out_color[3,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer);
+    the three uint8 buffers are opaque and only meaningful to RasterizeGaussiansBackwardCUDA.
+    projmatrix, tan_fovx, tan_fovy, prefiltered and render_depth are ignored in lonlat mode, as in
+    the reference.
+    """
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    _require_cuda(means3D, "means3D")
+    lib = load_library()
+    device = means3D.device
+    P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+
+    byte_opts = dict(dtype=torch.uint8, device=device)
+    radii = torch.empty((P,), dtype=torch.int32, device=device)
+    geomBuffer = torch.empty((0,), **byte_opts)
+    binningBuffer = torch.empty((0,), **byte_opts)
+    imgBuffer = torch.empty((0,), **byte_opts)
+
+    rendered = 0
+    if P != 0:
+        if camera_type == PINHOLE:
+            raise NotImplementedError("camera_type=1 (pinhole) is outside this package's scope; use LONLAT (3)")
+        if camera_type != LONLAT:
+            raise RuntimeError("[CudaRasterizer]Invalid camera_type")
+        M = int(sh.size(1)) if sh.size(0) != 0 else 0
+        with torch.cuda.device(device):
+            out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
+            background, means3D_c, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix, sh, campos = (
+                _f32c(t) for t in (background, means3D, colors, opacity, scales, rotations, cov3D_precomp,
+                                   viewmatrix, sh, campos))
+            geomBuffer = torch.empty((lib.ogs_geom_bytes(P),), **byte_opts)
+            imgBuffer = torch.empty((lib.ogs_img_bytes(W, H),), **byte_opts)
+            n = ctypes.c_int64(0)
+            st = _stream(device)
+            check(lib.ogs_lonlat_forward_stage1(
+                P, int(degree), M, W, H,
+                _ptr(means3D_c), _ptr(sh), _ptr(colors), _ptr(opacity),
+                _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                _ptr(viewmatrix), _ptr(campos),
+                _ptr(radii), _ptr(geomBuffer), _ptr(imgBuffer), ctypes.byref(n), st))
+            rendered = int(n.value)
+            binningBuffer = torch.empty((lib.ogs_binning_bytes(rendered, W, H),), **byte_opts)
+            check(lib.ogs_lonlat_forward_stage2(
+                P, W, H, rendered, _ptr(background),
+                _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), _ptr(out_color), st))
+    else:
+        # reference: outputs are the zero-filled tensors, nothing is launched (:84-85,97)
+        out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
+    return rendered, out_color, radii, geomBuffer, binningBuffer, imgBuffer
+
+
+def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                   cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                   dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                   imageBuffer, camera_type=PINHOLE):
+    """reference src/rasterize_points.cu:166-285.
+
+    Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
+    dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4]).
+    """
+    _require_cuda(means3D, "means3D")
+    lib = load_library()
+    device = means3D.device
+    P = int(means3D.size(0))
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    M = int(sh.size(1)) if sh.size(0) != 0 else 0
+    opts = dict(dtype=torch.float32, device=device)
+    # the library writes every element (zeros for culled rows): no zero-fill needed
+    # (the reference zero-fills 81 floats per Gaussian here, :200-208,246-247)
+    alloc = torch.zeros if P == 0 else torch.empty
+    dL_dmeans3D = alloc((P, 3), **opts)
+    dL_dmeans2D = alloc((P, 3), **opts)
+    dL_dcolors = alloc((P, NUM_CHANNELS), **opts)
+    dL_dopacity = alloc((P, 1), **opts)
+    dL_dcov3D = alloc((P, 6), **opts)
+    dL_dsh = alloc((P, M, 3), **opts)
+    dL_dscales = alloc((P, 3), **opts)
+    dL_drotations = alloc((P, 4), **opts)
+    if P != 0:
+        if camera_type == PINHOLE:
+            raise NotImplementedError("camera_type=1 (pinhole) is outside this package's scope; use LONLAT (3)")
+        if camera_type != LONLAT:
+            raise RuntimeError("[CudaRasterizer]Invalid camera_type")
+        with torch.cuda.device(device):
+            background, means3D_c, colors, scales, rotations, cov3D_precomp, viewmatrix, sh, campos, dL = (
+                _f32c(t) for t in (background, means3D, colors, scales, rotations, cov3D_precomp, viewmatrix,
+                                   sh, campos, dL_dout_color))
+            radii_c = radii.contiguous()
+            check(lib.ogs_lonlat_backward(
+                P, int(degree), M, int(R), W, H,
+                _ptr(background), _ptr(means3D_c), _ptr(sh), _ptr(colors),
+                _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                _ptr(viewmatrix), _ptr(campos), _ptr(radii_c),
+                _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                _ptr(dL),
+                _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors),
+                _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations),
+                _stream(device)))
+            if M == 0:
+                dL_dsh = torch.zeros((P, 0, 3), **opts)
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def markVisible(means3D, viewmatrix, projmatrix, camera_type=PINHOLE):
+    """reference src/rasterize_points.cu:287-319 (lonlat: every Gaussian is marked visible)."""
+    _require_cuda(means3D, "means3D")
+    P = int(means3D.size(0))
+    present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
+    if P != 0:
+        if camera_type == PINHOLE:
+            raise NotImplementedError("camera_type=1 (pinhole) is outside this package's scope; use LONLAT (3)")
+        if camera_type != LONLAT:
+            raise RuntimeError("[CudaRasterizer]Invalid camera_type")
+        with torch.cuda.device(means3D.device):
+            check(load_library().ogs_mark_all_visible(P, _ptr(present), _stream(means3D.device)))
+    return present
+
+
+def export_forward_state(P, W, H, R, geomBuffer, binningBuffer, imgBuffer, want_keys=True):
+    """Test helper: our private buffers re-expressed as the reference's GeometryState /
+    BinningState / ImageState arrays (rasterizer_impl.cu:198-245).  Returns a dict of tensors."""
+    lib = load_library()
+    device = geomBuffer.device
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    f = dict(dtype=torch.float32, device=device)
+    out = {
+        "means2D": torch.zeros((P, 2), **f), "depths": torch.zeros((P,), **f),
+        "conic_opacity": torch.zeros((P, 4), **f), "rgb": torch.zeros((P, 3), **f),
+        "tiles_touched": torch.zeros((P,), dtype=torch.int32, device=device),
+        "clamped": torch.zeros((P, 3), dtype=torch.uint8, device=device),
+        "cov3D": torch.zeros((P, 6), **f),
+        "point_list": torch.zeros((R,), dtype=torch.int32, device=device),
+        "point_list_keys": torch.zeros((R if want_keys else 0,), dtype=torch.int64, device=device),
+        "ranges": torch.zeros((T, 2), dtype=torch.int32, device=device),
+        "accum_alpha": torch.zeros((H * W,), **f),
+        "n_contrib": torch.zeros((H * W,), dtype=torch.int32, device=device),
+    }
+    with torch.cuda.device(device):
+        st = _stream(device)
+        check(lib.ogs_export_geometry(P, _ptr(geomBuffer), _ptr(out["means2D"]), _ptr(out["depths"]),
+                                      _ptr(out["conic_opacity"]), _ptr(out["rgb"]), _ptr(out["tiles_touched"]),
+                                      _ptr(out["clamped"]), _ptr(out["cov3D"]), st))
+        check(lib.ogs_export_binning(P, W, H, R, _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer),
+                                     _ptr(out["point_list"]), _ptr(out["point_list_keys"]) if want_keys else None,
+                                     _ptr(out["ranges"]), _ptr(out["accum_alpha"]), _ptr(out["n_contrib"]), st))
+    return out

@@ -1,0 +1,106 @@
+"""Shared helpers for the parity tests, the golden-fixture generator and tools/parity_report.py."""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+pkg = importlib.import_module("omnigs-fork_b200")
+sys.modules.setdefault("omnigs_fork_b200", pkg)
+scene_mod = importlib.import_module("omnigs-fork_b200.scene")
+
+GRAD_NAMES = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales",
+              "dL_drotations"]
+
+
+def load_reference():
+    """The unmodified reference rasterizer (oracle/_ref/omnigs_ref.so) or None if it was not built."""
+    d = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(d, "omnigs_ref.so")):
+        return None
+    import torch  # noqa: F401  (libtorch must be loaded first)
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    return importlib.import_module("omnigs_ref")
+
+
+def torch_inputs(scene, view, device="cuda", mode="sh", bg=(0.0, 0.0, 0.0), degree=3):
+    """Tensors in the argument convention of RasterizeGaussiansCUDA.
+    mode: "sh" (SH + scale/rot, the live combination), "colors" (precomputed colours),
+          "cov" (SH + precomputed 3-D covariance)."""
+    import torch
+    V, campos = view
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    empty = torch.empty((0,), dtype=torch.float32, device=device)
+    d = dict(background=torch.tensor(bg, dtype=torch.float32, device=device), means3D=t(scene.means3D),
+             opacity=t(scene.opacities), viewmatrix=t(V), projmatrix=t(V), campos=t(campos),
+             colors=empty, sh=empty, scales=empty, rotations=empty, cov3D_precomp=empty,
+             scale_modifier=1.0, degree=degree, H=scene.H, W=scene.W)
+    if mode == "colors":
+        rng = np.random.Generator(np.random.PCG64(7))
+        d["colors"] = t(rng.uniform(0, 1, (scene.P, 3)).astype(np.float32))
+    else:
+        d["sh"] = t(scene.shs)
+    if mode == "cov":
+        d["cov3D_precomp"] = t(cov3d_numpy(scene.scales, scene.rotations))
+    else:
+        d["scales"] = t(scene.scales)
+        d["rotations"] = t(scene.rotations)
+    return d
+
+
+def cov3d_numpy(scales, rot):
+    """Sigma = R S S^T R^T upper triangle, float64 -> float32 (input generator for cov3D_precomp)."""
+    w, x, y, z = [rot[:, i].astype(np.float64) for i in range(4)]
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], -1),
+                  np.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)], -1),
+                  np.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1)], 1)
+    M = R * scales.astype(np.float64)[:, None, :]
+    S = M @ M.transpose(0, 2, 1)
+    return np.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], -1).astype(np.float32)
+
+
+def run_forward(mod, d):
+    return mod.RasterizeGaussiansCUDA(
+        d["background"], d["means3D"], d["colors"], d["opacity"], d["scales"], d["rotations"], d["scale_modifier"],
+        d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], 0.0, 0.0, d["H"], d["W"], d["sh"], d["degree"],
+        d["campos"], False, 3, False)
+
+
+def run_backward(mod, d, fwd, dL):
+    R, _, radii, geom, binning, img = fwd
+    return mod.RasterizeGaussiansBackwardCUDA(
+        d["background"], d["means3D"], radii, d["colors"], d["scales"], d["rotations"], d["scale_modifier"],
+        d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], 0.0, 0.0, dL, d["sh"], d["degree"], d["campos"],
+        geom, R, binning, img, 3)
+
+
+def ours_state(d, fwd):
+    R, _, _, geom, binning, img = fwd
+    return pkg.export_forward_state(int(d["means3D"].shape[0]), d["W"], d["H"], R, geom, binning, img)
+
+
+def ref_state(ref, d, fwd):
+    R, _, _, geom, binning, img = fwd
+    P, W, H = int(d["means3D"].shape[0]), d["W"], d["H"]
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    s = dict(ref.unpack_geom(geom, P))
+    s.update(ref.unpack_binning(binning, R))
+    s.update(ref.unpack_img(img, W * H, T))
+    return s
+
+
+def grad_error(a, b):
+    """(max-norm relative error, worst per-element excess over 1e-4*|b| + 1e-6*max|b|)."""
+    a = a.double().flatten(); b = b.double().flatten()
+    if b.numel() == 0:
+        return 0.0, 0.0
+    scale = float(b.abs().max()) + 1e-30
+    diff = (a - b).abs()
+    rel = float(diff.max()) / scale
+    excess = float((diff - (1e-4 * b.abs() + 1e-6 * scale)).max())
+    return rel, excess
