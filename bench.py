@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — lonlat rasterizer forward+backward on a 360Roam-shaped scene (BASELINE.json configs[1]:
+1M Gaussians, 2048x1024 equirect, SH degree 3), one view per rank per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` = whole-job training views/s with every input resident in HBM
+(fwd + bwd through the public RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA boundary, plus
+the NCCL gradient all-reduce when N > 1); `ms_per_step` is the BASELINE "fwd+bwd ms/frame".
+`e2e` adds, per step, the pinned host->device copy of the view (pose + target image) and the
+device->host read of the loss.  `--impl reference` times the reference's own rasterizer
+(oracle/_ref/omnigs_ref.so: its sources rebuilt for sm_100) through its own entry points on the same
+scene; if that library is absent it falls back to the CPU oracle port.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "lonlat_fwd_bwd_train_views_per_s"
+UNIT = "views/s"
+WORKLOAD = "C2"
+
+
+def alg_bytes(P, V, R, N, T, D, M, K):
+    """SURVEY.md §8(d) / BASELINE.md §4: algorithmic bytes per frame and per stage."""
+    return {
+        "preprocess_fwd": P * (52 + 12 * (D + 1) ** 2) + V * 67,
+        "binning": 8 * P + (8 * P + 12 * V + 12 * R) + R * (8 + 24 * K) + (8 * R + 8 * T),
+        "render_fwd": 40 * R + 20 * N + 8 * T,
+        "render_bwd": 40 * R + 20 * N + 80 * P,
+        "preprocess_bwd": 4 * P + V * (107 + 12 * (D + 1) ** 2) + P * (64 + 12 * M),
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, windows):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if not any(a <= t <= b for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_baseline(scene, view, dL_np, budget_s=45.0):
+    """The oracle port (plain C + OpenMP) on this box's host cores: one full frame when that fits the
+    budget, else BASELINE configs[0] (C1)."""
+    from oracle import oracle
+    import _harness as h
+    bg = np.zeros(3, np.float32)
+
+    def frame(sc, dl):
+        t0 = time.time()
+        f = oracle.forward(sc.means3D, sc.opacities, view[0], view[1], sc.W, sc.H, bg, shs=sc.shs, degree=3,
+                           scales=sc.scales, rotations=sc.rotations)
+        oracle.backward(f, dl, sc.means3D, view[0], view[1], sc.W, sc.H, bg, shs=sc.shs, degree=3,
+                        scales=sc.scales, rotations=sc.rotations)
+        return time.time() - t0
+
+    c1 = h.scene_mod.make_config_scene("C1")
+    t_c1 = frame(c1, h.scene_mod.make_grad_image(c1.W, c1.H, 99))
+    if t_c1 * 12 <= budget_s:
+        t = frame(scene, dL_np)
+        return {"value": 1.0 / t, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+                "sample": f"1 full {WORKLOAD} frame (fwd+bwd), {t:.1f} s"}
+    return {"value": 1.0 / t_c1, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+            "sample": f"1 frame of BASELINE configs[0] (C1: 100k Gaussians, 1024x512), {t_c1:.1f} s; a {WORKLOAD} frame "
+                      f"is ~11x larger"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    K, Wm = args.steps, max(3, args.warmup)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference" and rank != 0:
+        return 0  # the reference has no multi-GPU path: rank 0 alone runs it
+
+    import torch
+    import torch.distributed as dist
+    import _harness as h
+    sm = h.scene_mod
+    from importlib import import_module
+    par = import_module("omnigs-fork_b200.parallel")
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1 and args.impl == "ours"
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    scene = sm.make_config_scene(WORKLOAD)
+    P, W, H, D, M = scene.P, scene.W, scene.H, 3, 16
+    N, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
+    views = [sm.random_view(1000 + 97 * s + rank) for s in range(K + Wm)]
+    d = h.torch_inputs(scene, views[0], device=dev)
+    view_dev = [(torch.from_numpy(v).to(dev), torch.from_numpy(c).to(dev)) for v, c in views]
+    dL_np = sm.make_grad_image(W, H, 99)
+    dL = torch.from_numpy(dL_np).to(dev)
+
+    mod = h.pkg
+    impl_note = None
+    if args.impl == "reference":
+        mod = h.load_reference()
+        if mod is None:
+            # the reference rasterizer library did not travel: time the CPU oracle port instead
+            cb = cpu_port_baseline(scene, views[0], dL_np)
+            line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 0,
+                    "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": WORKLOAD, "gaussians": P, "image": [W, H], "sh_degree": D},
+                    "cpu_baseline": cb,
+                    "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+            return 0
+        impl_note = "reference CUDA rasterizer rebuilt for sm_100 (oracle/_ref), its own entry points"
+
+    names = h.GRAD_NAMES
+
+    def step(s):
+        d["viewmatrix"], d["campos"] = view_dev[s]
+        d["projmatrix"] = d["viewmatrix"]
+        fwd = h.run_forward(mod, d)
+        g = h.run_backward(mod, d, fwd, dL)
+        if distributed:
+            par.allreduce_gradients(dict(zip(names, g)), fwd[2])
+        return fwd, g
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if not distributed:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    vis_env = os.environ.get("CUDA_VISIBLE_DEVICES")
+    clocks = ClockSampler(vis_env.split(",")[local_rank] if vis_env else local_rank)
+    clocks.start()
+    windows = []
+
+    # ---------------- device-resident timed region ----------------
+    for s in range(Wm):
+        fwd, _ = step(s)
+    R = fwd[0]
+    V = int((fwd[2] > 0).sum())
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_a = time.time()
+    e0.record()
+    for s in range(K):
+        step(Wm + s)
+    e1.record()
+    sync_all()
+    windows.append((t_a, time.time()))
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms_total / K
+    value = world * K / (ms_total / 1000.0) if args.impl == "ours" else K / (ms_total / 1000.0)
+
+    # ---------------- end-to-end: pinned H2D of the view + target, loss read back ----------------
+    gt_host = torch.from_numpy(np.clip(dL_np * (W * H) * 0.1 + 0.5, 0, 1).astype(np.float32)).pin_memory()
+    view_host = [torch.from_numpy(np.concatenate([v.reshape(-1), c.reshape(-1)])).pin_memory() for v, c in views]
+    gt_dev = torch.empty_like(gt_host, device=dev)
+    vbuf = torch.empty(19, device=dev)
+    h2d = gt_host.numel() * 4 + 19 * 4
+
+    def e2e_step(s):
+        vbuf.copy_(view_host[s], non_blocking=True)
+        gt_dev.copy_(gt_host, non_blocking=True)
+        d["viewmatrix"], d["campos"] = vbuf[:16].view(4, 4), vbuf[16:19]
+        d["projmatrix"] = d["viewmatrix"]
+        fwd = h.run_forward(mod, d)
+        diff = fwd[1] - gt_dev
+        loss = diff.abs().mean()                       # L1 (the reference's main loss term)
+        g = h.run_backward(mod, d, fwd, torch.sign(diff) / diff.numel())
+        if distributed:
+            par.allreduce_gradients(dict(zip(names, g)), fwd[2])
+        return float(loss.item())                      # device->host read of the step's result
+
+    for s in range(Wm):
+        e2e_step(s)
+    sync_all()
+    t_a = time.time()
+    e0.record()
+    for s in range(K):
+        e2e_step(Wm + s)
+    e1.record()
+    sync_all()
+    windows.append((t_a, time.time()))
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = (world if args.impl == "ours" else 1) * K / (ms_e2e / 1000.0)
+
+    clocks.stop()
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return 0
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world if args.impl == "ours" else 1,
+        "steps": K, "warmup": Wm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "gaussians": P, "visible": V, "image": [W, H], "sh_degree": D,
+                   "num_rendered": R, "views_per_step_per_gpu": 1,
+                   "parallelism": f"dp{world}" if distributed else "single",
+                   "l2": "no flush: every step touches > 1 GB (params 236 MB, lists, accumulators), L2 is 126 MB; "
+                         "a different camera pose each step"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / K},
+        "clocks": clocks.summary(windows),
+    }
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["note"] = impl_note
+        line["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference", "device": "cuda",
+                                "sample": f"{K} full {WORKLOAD} frames; the reference ships no CPU rasterizer, its CUDA "
+                                          "kernels (rebuilt -arch=sm_100) are the reference implementation of the path"}
+        line["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- per-stage device times + roofline (ours) ----------------
+    lib = h.pkg.load_library()
+    stage_names = ["preprocess_fwd", "depth_order", "tile_ranges", "emit", "tile_sort", "render_fwd", "render_bwd",
+                   "preprocess_bwd"]
+    acc = np.zeros(8)
+    reps = min(K, 10)
+    lib.ogs_profile_enable(1)
+    buf = (ctypes.c_float * 8)()
+    for s in range(reps):
+        d["viewmatrix"], d["campos"] = view_dev[Wm + s]
+        fwd = h.run_forward(mod, d)
+        h.run_backward(mod, d, fwd, dL)
+        lib.ogs_profile_read(buf, 8)
+        acc += np.array(list(buf))
+    lib.ogs_profile_enable(0)
+    stage_ms = dict(zip(stage_names, (acc / reps).tolist()))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    Kpass = (32 + int(np.ceil(np.log2(T + 1))) + 7) // 8
+    B = alg_bytes(P, V, R, N, T, D, M, Kpass)
+    groups = {"preprocess_fwd": ["preprocess_fwd"], "binning": ["depth_order", "tile_ranges", "emit", "tile_sort"],
+              "render_fwd": ["render_fwd"], "render_bwd": ["render_bwd"], "preprocess_bwd": ["preprocess_bwd"]}
+    per_stage = {}
+    for gname, members in groups.items():
+        ms = sum(stage_ms[m] for m in members)
+        per_stage[gname] = {"ms": ms, "alg_bytes": B[gname], "gbs": B[gname] / ms / 1e6 if ms > 0 else None}
+    dominant = max(("render_fwd", "render_bwd", "preprocess_fwd", "preprocess_bwd"), key=lambda k: per_stage[k]["ms"])
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dominant)
+    except Exception:
+        pass
+    ach = per_stage[dominant]["gbs"]
+    line["roofline"] = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                        "note": "blend kernels are FP32-issue / L2-RED bound, not HBM bound (SURVEY 8d); HBM frac reported as the contract asks"}
+    total_alg = sum(B.values())
+    line["roofline_frame"] = {"alg_bytes": total_alg, "achieved": total_alg / ms_per_step / 1e6, "peak": peak,
+                              "unit": "GB/s", "frac": total_alg / ms_per_step / 1e6 / peak, "stages": per_stage,
+                              "stage_ms": stage_ms}
+    line["gpu_launches"] = K * (12 + 2)   # fwd: preprocess, hist, 4+2 onesweep, scan, ranges, emit, render; bwd: 2
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_port_baseline(scene, views[Wm], dL_np)
+    print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,6 +167,24 @@ OGS_API int ogs_lonlat_train_view_host(
 	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
 	int64_t* num_rendered_host, size_t* binning_needed, void* stream);
 
+/*
+ * Per-stage device timing (CUDA events on the launching stream), for bench.py's roofline block.
+ * Off by default; when enabled on the calling thread every stage of the next forward/backward is
+ * bracketed by events.  ogs_profile_read synchronises those events and writes milliseconds per stage
+ * (0 for stages that did not run); returns the number of stages (OGS_PROF_COUNT).
+ */
+#define OGS_PROF_PREPROCESS_FWD 0
+#define OGS_PROF_DEPTH_ORDER 1    /* depth-key histogram + 4 onesweep passes + emit-offset scan */
+#define OGS_PROF_TILE_RANGES 2
+#define OGS_PROF_EMIT 3           /* duplicateWithKeys equivalent */
+#define OGS_PROF_TILE_SORT 4      /* onesweep passes over the tile ids */
+#define OGS_PROF_RENDER_FWD 5
+#define OGS_PROF_RENDER_BWD 6
+#define OGS_PROF_PREPROCESS_BWD 7
+#define OGS_PROF_COUNT 8
+OGS_API int ogs_profile_enable(int on);
+OGS_API int ogs_profile_read(float* ms, int count);
+
 #ifdef __cplusplus
 }
 #endif

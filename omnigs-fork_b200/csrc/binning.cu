@@ -491,8 +491,11 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 	const int gx = ceil_div(W, kTile);
 	const TileSortPlan plan = make_tile_sort_plan(W, H);
 	const uint32_t n = (uint32_t)R;
+	prof_begin(OGS_PROF_EMIT, st);
 	emit_instances_kernel<<<(unsigned)((R + kEmitPerBlock - 1) / kEmitPerBlock), kEmitThreads, 0, st>>>(
 		g.emit_offset, g.sort_val[0], g.rect, (uint32_t)P, n, gx, b.key[0], b.val[0]);
+	prof_end(OGS_PROF_EMIT, st);
+	prof_begin(OGS_PROF_TILE_SORT, st);
 	const int tiles = (int)((R + kSortItemsPerBlock - 1) / kSortItemsPerBlock);
 	size_t status_off = 0;
 	for (int p = 0; p < plan.passes; p++) {
@@ -502,6 +505,7 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 			n, plan.shift[p], plan.bits[p], img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p);
 		status_off += (size_t)tiles << plan.bits[p];
 	}
+	prof_end(OGS_PROF_TILE_SORT, st);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }

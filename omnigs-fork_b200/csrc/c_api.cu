@@ -25,6 +25,29 @@ int fail_cuda(cudaError_t e)
 	return OGS_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------ per-stage profiling
+namespace {
+struct Profiler {
+	bool on = false;
+	bool created = false;
+	cudaEvent_t ev[2 * OGS_PROF_COUNT];
+	bool used[OGS_PROF_COUNT] = {};
+};
+thread_local Profiler g_prof;
+} // namespace
+
+void prof_begin(int stage, cudaStream_t st)
+{
+	if (!g_prof.on) return;
+	g_prof.used[stage] = true;
+	cudaEventRecord(g_prof.ev[2 * stage], st);
+}
+void prof_end(int stage, cudaStream_t st)
+{
+	if (!g_prof.on) return;
+	cudaEventRecord(g_prof.ev[2 * stage + 1], st);
+}
+
 // ------------------------------------------------------------------ layouts
 namespace {
 constexpr size_t kAlign = 256;
@@ -228,7 +251,9 @@ int forward_stage1_impl(
 	a.g0 = g.g0; a.g1 = g.g1; a.gb = g.gb; a.depth = g.depth; a.rect = g.rect;
 	a.tiles_touched = g.tiles_touched; a.cov3D = g.cov3D; a.clamped = g.clamped;
 	a.sort_key = g.sort_key[0]; a.tile_diff = img.tile_diff; a.total_tiles = g.scalars;
+	prof_begin(OGS_PROF_PREPROCESS_FWD, st);
 	if (int rc = launch_preprocess_fwd(a, st)) return rc;
+	prof_end(OGS_PROF_PREPROCESS_FWD, st);
 
 	// num_rendered read-back (the reference blocks here too, rasterizer_impl.cu:627-628); the
 	// R-independent kernels are queued behind the copy so they overlap the host round trip.
@@ -236,8 +261,12 @@ int forward_stage1_impl(
 	if (int rc = get_readback(&rb)) return rc;
 	OGS_CUDA_TRY(cudaMemcpyAsync(rb->pinned, g.scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	OGS_CUDA_TRY(cudaEventRecord(rb->event, st));
+	prof_begin(OGS_PROF_DEPTH_ORDER, st);
 	if (int rc = launch_depth_order(g, P, st)) return rc;
+	prof_end(OGS_PROF_DEPTH_ORDER, st);
+	prof_begin(OGS_PROF_TILE_RANGES, st);
 	if (int rc = launch_tile_ranges(img, W, H, st)) return rc;
+	prof_end(OGS_PROF_TILE_RANGES, st);
 	OGS_CUDA_TRY(cudaEventSynchronize(rb->event));
 	const unsigned long long total = *rb->pinned;
 	if (total >= (1ull << 30)) {
@@ -256,6 +285,31 @@ using namespace ogs;
 extern "C" {
 
 OGS_API int ogs_abi_version(void) { return OGS_ABI_VERSION; }
+
+OGS_API int ogs_profile_enable(int on)
+{
+	if (on && !g_prof.created) {
+		for (int i = 0; i < 2 * OGS_PROF_COUNT; i++) OGS_CUDA_TRY(cudaEventCreate(&g_prof.ev[i]));
+		g_prof.created = true;
+	}
+	g_prof.on = on != 0;
+	for (int i = 0; i < OGS_PROF_COUNT; i++) g_prof.used[i] = false;
+	return OGS_OK;
+}
+
+OGS_API int ogs_profile_read(float* ms, int count)
+{
+	if (!ms || count < OGS_PROF_COUNT) return fail(OGS_ERR_INVALID_ARG, "ogs_profile_read needs OGS_PROF_COUNT floats");
+	for (int i = 0; i < OGS_PROF_COUNT; i++) {
+		ms[i] = 0.f;
+		if (g_prof.created && g_prof.used[i]) {
+			OGS_CUDA_TRY(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+			OGS_CUDA_TRY(cudaEventElapsedTime(&ms[i], g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+		}
+		g_prof.used[i] = false;
+	}
+	return OGS_PROF_COUNT;
+}
 OGS_API const char* ogs_last_error(void) { return g_last_error.c_str(); }
 
 OGS_API size_t ogs_geom_bytes(int P) { return GeomState::bytes(P < 0 ? 0 : P); }
@@ -309,8 +363,11 @@ OGS_API int ogs_lonlat_forward_stage2(
 		OGS_CUDA_TRY(cudaMemsetAsync(b.zero_begin, 0, b.zero_bytes, st));
 		if (int rc = launch_emit_and_tile_sort(g, img, b, P, num_rendered, W, H, st)) return rc;
 	}
-	return launch_render_fwd(img.ranges, b.point_list, W, H, g.g0, g.g1, g.gb, background,
-	                         img.final_T, img.n_contrib, out_color, st);
+	prof_begin(OGS_PROF_RENDER_FWD, st);
+	const int rc = launch_render_fwd(img.ranges, b.point_list, W, H, g.g0, g.g1, g.gb, background,
+	                                 img.final_T, img.n_contrib, out_color, st);
+	prof_end(OGS_PROF_RENDER_FWD, st);
+	return rc;
 }
 
 OGS_API int ogs_lonlat_backward(
@@ -344,8 +401,10 @@ OGS_API int ogs_lonlat_backward(
 	if (num_rendered > 0) b = BinningState::carve(binning_buffer, num_rendered, W, H);
 
 	OGS_CUDA_TRY(cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * (size_t)P, st));
+	prof_begin(OGS_PROF_RENDER_BWD, st);
 	if (int rc = launch_render_bwd(img.ranges, b.point_list, W, H, background, g.g0, g.g1, g.gb,
 	                               img.final_T, img.n_contrib, dL_dpix, g.grad_acc, st)) return rc;
+	prof_end(OGS_PROF_RENDER_BWD, st);
 
 	PreprocessBwdArgs a{};
 	a.P = P; a.D = D; a.M = shs ? M : 0; a.W = W; a.H = H; a.scale_modifier = scale_modifier;
@@ -355,7 +414,10 @@ OGS_API int ogs_lonlat_backward(
 	a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
 	a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = shs ? dL_dsh : nullptr;
 	a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
-	return launch_preprocess_bwd(a, st);
+	prof_begin(OGS_PROF_PREPROCESS_BWD, st);
+	const int rc = launch_preprocess_bwd(a, st);
+	prof_end(OGS_PROF_PREPROCESS_BWD, st);
+	return rc;
 }
 
 OGS_API int ogs_mark_all_visible(int P, uint8_t* present, void* stream)

@@ -141,6 +141,108 @@ OGS_HD void lonlat_T_cov(const LonlatJac& Jv, const float* V, const float* cov6,
 	cov = m3_mul(m3_mul(m3_t(T), m3_t(Vrk)), T);
 }
 
+// ------------------------------------------------------------------ pinned forward chain
+// Everything that feeds an integer or bit-compared output of the forward (depth key, pixel
+// position, conic, radius, tile rect) is written with explicit round-to-nearest intrinsics in the
+// exact operation order of the reference's compiled kernel (read off its sm_100 SASS, see
+// DESIGN.md "Numeric pinning"), so the result cannot drift with compiler context:
+//   * a sum of three products is  fma(a2,b2, fma(a0,b0, mul(a1,b1)))   (NVVM's contraction of
+//     (a0*b0 + a1*b1) + a2*b2), including the products with literal zeros glm's generic mat3
+//     multiply carries along;
+//   * det = fma(cx, cz, -(cy*cy)) and mid*mid - det = fma(mid, mid, -det)  (fused by ptxas);
+//   * ndc->pixel runs in double: ((v + 1.0) * S - 1.0) * 0.5 with the middle step a DFMA.
+OGS_D float dot3p(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+	return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
+}
+OGS_D M3 m3_mul_p(const M3& A, const M3& B)
+{
+	M3 R;
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int r = 0; r < 3; r++)
+			R.c[c][r] = dot3p(A.c[0][r], B.c[c][0], A.c[1][r], B.c[c][1], A.c[2][r], B.c[c][2]);
+	return R;
+}
+OGS_D float3 view_point_p(const float* V, float3 p)
+{
+	float3 t;
+	t.x = __fadd_rn(dot3p(p.x, V[0], p.y, V[4], p.z, V[8]), V[12]);
+	t.y = __fadd_rn(dot3p(p.x, V[1], p.y, V[5], p.z, V[9]), V[13]);
+	t.z = __fadd_rn(dot3p(p.x, V[2], p.y, V[6], p.z, V[10]), V[14]);
+	return t;
+}
+OGS_D float ndc_to_pix_p(float v, int S)
+{
+	return (float)__dmul_rn(__fma_rn(__dadd_rn((double)v, 1.0), (double)S, -1.0), 0.5);
+}
+OGS_D void tile_rect_p(float2 p, int max_radius, int gx, int gy, int& x0, int& y0, int& x1, int& y1)
+{
+	const float R = (float)max_radius, inv = 1.0f / kTile; // division by 16 is an exact scaling
+	x0 = min(gx, max(0, (int)__fmul_rn(__fsub_rn(p.x, R), inv)));
+	y0 = min(gy, max(0, (int)__fmul_rn(__fsub_rn(p.y, R), inv)));
+	// (p + R + BLOCK) - 1, left to right as written in auxiliary.h:63-64
+	x1 = min(gx, max(0, (int)__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p.x, R), (float)kTile), -1.0f), inv)));
+	y1 = min(gy, max(0, (int)__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p.y, R), (float)kTile), -1.0f), inv)));
+}
+OGS_D void cov3d_from_scale_rot_p(float3 scale, float mod, float4 q, float* cov6)
+{
+	const float r = q.x, x = q.y, y = q.z, z = q.w;
+	// products kept as plain multiplies / fused into an fma exactly as ptxas scheduled them
+	const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z), xz = __fmul_rn(x, z), rz = __fmul_rn(r, z), rx = __fmul_rn(r, x);
+	M3 R = m3_cols(
+		__fsub_rn(1.f, __fmul_rn(2.f, __fadd_rn(yy, zz))), __fmul_rn(2.f, __fmaf_rn(x, y, -rz)), __fmul_rn(2.f, __fmaf_rn(r, y, xz)),
+		__fmul_rn(2.f, __fmaf_rn(x, y, rz)), __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, zz))), __fmul_rn(2.f, __fmaf_rn(y, z, -rx)),
+		__fmul_rn(2.f, __fmaf_rn(-r, y, xz)), __fmul_rn(2.f, __fmaf_rn(y, z, rx)), __fsub_rn(1.f, __fmul_rn(2.f, __fmaf_rn(x, x, yy))));
+	M3 S = m3_cols(__fmul_rn(mod, scale.x), 0.f, 0.f, 0.f, __fmul_rn(mod, scale.y), 0.f, 0.f, 0.f, __fmul_rn(mod, scale.z));
+	M3 Mm = m3_mul_p(S, R);
+	M3 Sigma = m3_mul_p(m3_t(Mm), Mm);
+	cov6[0] = Sigma.c[0][0];
+	cov6[1] = Sigma.c[0][1];
+	cov6[2] = Sigma.c[0][2];
+	cov6[3] = Sigma.c[1][1];
+	cov6[4] = Sigma.c[1][2];
+	cov6[5] = Sigma.c[2][2];
+}
+// 2-D covariance (with the 0.3 blur) of a Gaussian whose camera-space mean is t.
+OGS_D float3 cov2d_lonlat_p(float3 t, const float* V, const float* c6, int W, int H)
+{
+	const float a = __fmaf_rn(t.x, t.x, __fmul_rn(t.z, t.z));
+	const float a_inv = __frcp_rn(__fadd_rn(a, kEps7));
+	const float rho = __fsqrt_rn(a);
+	const float rho_inv = __frcp_rn(__fadd_rn(rho, kEps7));
+	const float rr = __fmaf_rn(t.y, t.y, a);
+	const float rr_inv = __frcp_rn(__fadd_rn(rr, kEps7));
+	const float Wd = __fmul_rn(__fmul_rn((float)W, 0.5f), kPiInv);
+	const float Hd = __fmul_rn((float)H, kPiInv);
+	const float j00 = __fmul_rn(__fmul_rn(Wd, t.z), a_inv);
+	const float j02 = __fmul_rn(__fmul_rn(t.x, -Wd), a_inv);
+	const float j10 = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(t.x, -Hd), t.y), rho_inv), rr_inv);
+	const float j11 = __fmul_rn(__fmul_rn(Hd, rho), rr_inv);
+	const float j12 = __fmul_rn(__fmul_rn(__fmul_rn(t.y, __fmul_rn(t.z, -Hd)), rho_inv), rr_inv);
+	// T = W*J: rows 0 and 1 of (J R); the third is identically unused
+	float T0[3], T1[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		T0[k] = dot3p(V[4 * k + 0], j00, V[4 * k + 1], 0.0f, V[4 * k + 2], j02);
+		T1[k] = dot3p(V[4 * k + 0], j10, V[4 * k + 1], j11, V[4 * k + 2], j12);
+	}
+	// (T^T Vrk^T)[k][r] = T_r . Vrk[:,k]
+	const float v0[3] = { c6[0], c6[1], c6[2] }, v1[3] = { c6[1], c6[3], c6[4] }, v2[3] = { c6[2], c6[4], c6[5] };
+	const float p00 = dot3p(T0[0], v0[0], T0[1], v0[1], T0[2], v0[2]);
+	const float p01 = dot3p(T1[0], v0[0], T1[1], v0[1], T1[2], v0[2]);
+	const float p10 = dot3p(T0[0], v1[0], T0[1], v1[1], T0[2], v1[2]);
+	const float p11 = dot3p(T1[0], v1[0], T1[1], v1[1], T1[2], v1[2]);
+	const float p20 = dot3p(T0[0], v2[0], T0[1], v2[1], T0[2], v2[2]);
+	const float p21 = dot3p(T1[0], v2[0], T1[1], v2[1], T1[2], v2[2]);
+	float3 cov;
+	cov.x = __fadd_rn(dot3p(p00, T0[0], p10, T0[1], p20, T0[2]), 0.3f);
+	cov.y = dot3p(p01, T0[0], p11, T0[1], p21, T0[2]);
+	cov.z = __fadd_rn(dot3p(p01, T1[0], p11, T1[1], p21, T1[2]), 0.3f);
+	return cov;
+}
+
 // ------------------------------------------------------------------ spherical harmonics
 __device__ const float kSH_C0 = 0.28209479177387814f;
 __device__ const float kSH_C1 = 0.4886025119029199f;

@@ -26,6 +26,8 @@ constexpr float kAlphaMin = 1.0f / 255.0f;
 		if (_e != cudaSuccess) return ogs::fail_cuda(_e);   \
 	} while (0)
 
+void prof_begin(int stage, cudaStream_t st);   // no-ops unless ogs_profile_enable(1)
+void prof_end(int stage, cudaStream_t st);
 int fail_cuda(cudaError_t e);   // records the message, returns OGS_ERR_CUDA
 int fail(int code, const char* msg);
 

@@ -39,16 +39,16 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 
 		// near cull (auxiliary.h:198-220): r^2 <= 0.04 drops the Gaussian
 		const float3 p_orig = { a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2] };
-		const float3 t = view_point(V, p_orig);
-		const float rr = t.x * t.x + t.y * t.y + t.z * t.z;
+		const float3 t = view_point_p(V, p_orig);
+		const float rr = dot3p(t.x, t.x, t.y, t.y, t.z, t.z);
 		if (!(rr <= 0.04f)) {
-			const float r = sqrtf(rr);
+			const float r = __fsqrt_rn(rr);
 
 			// lon/lat screen coordinates (auxiliary.h:236-248)
-			const float inv_r = 1.0f / (r + kEps7);
+			const float inv_r = __frcp_rn(__fadd_rn(r, kEps7));
 			const float lon = atan2f(t.x, t.z);
-			const float lat = asinf(t.y * inv_r);
-			const float2 p_proj = { lon * kPiInv, lat * kTwoPiInv };
+			const float lat = asinf(__fmul_rn(t.y, inv_r));
+			const float2 p_proj = { __fmul_rn(lon, kPiInv), __fmul_rn(lat, kTwoPiInv) };
 
 			// 3-D covariance (forward.cu:643-652)
 			float cov6[6];
@@ -58,34 +58,29 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 			} else {
 				const float3 sc = { a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2] };
 				const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
-				cov3d_from_scale_rot(sc, a.scale_modifier, q, cov6);
+				cov3d_from_scale_rot_p(sc, a.scale_modifier, q, cov6);
 #pragma unroll
 				for (int i = 0; i < 6; i++) a.cov3D[6 * (size_t)idx + i] = cov6[i];
 			}
 
 			// 2-D covariance through the lonlat Jacobian + 0.3 px blur (forward.cu:130-189)
-			const float3 t2 = view_point(V, p_orig);
-			const LonlatJac J = lonlat_jacobian(t2, a.W, a.H);
-			M3 T, Vrk, cov2;
-			lonlat_T_cov(J, V, cov6, T, Vrk, cov2);
-			cov2.c[0][0] += 0.3f;
-			cov2.c[1][1] += 0.3f;
-			const float3 cov = { float(cov2.c[0][0]), float(cov2.c[0][1]), float(cov2.c[1][1]) };
+			const float3 cov = cov2d_lonlat_p(t, V, cov6, a.W, a.H);
 
 			// conic (forward.cu:660-664)
-			const float det = (cov.x * cov.z - cov.y * cov.y);
+			const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
 			if (det != 0.0f) {
-				const float det_inv = 1.f / det;
-				const float3 conic = { cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv };
+				const float det_inv = __frcp_rn(det);
+				const float3 conic = { __fmul_rn(cov.z, det_inv), __fmul_rn(cov.y, -det_inv), __fmul_rn(cov.x, det_inv) };
 
 				// screen-space extent (forward.cu:671-683)
-				const float mid = 0.5f * (cov.x + cov.z);
-				const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
-				const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
-				const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
-				const float2 point_image = { ndc_to_pix(p_proj.x, a.W), ndc_to_pix(p_proj.y, a.H) };
+				const float mid = __fmul_rn(__fadd_rn(cov.x, cov.z), 0.5f);
+				const float sq = __fsqrt_rn(fmaxf(__fmaf_rn(mid, mid, -det), 0.1f));
+				const float lambda1 = __fadd_rn(mid, sq);
+				const float lambda2 = __fsub_rn(mid, sq);
+				const float my_radius = ceilf(__fmul_rn(__fsqrt_rn(fmaxf(lambda1, lambda2)), 3.f));
+				const float2 point_image = { ndc_to_pix_p(p_proj.x, a.W), ndc_to_pix_p(p_proj.y, a.H) };
 				int x0, y0, x1, y1;
-				tile_rect(point_image, (int)my_radius, a.gx, a.gy, x0, y0, x1, y1);
+				tile_rect_p(point_image, (int)my_radius, a.gx, a.gy, x0, y0, x1, y1);
 				if ((x1 - x0) * (y1 - y0) != 0) {
 					out_radius = (int)my_radius;
 					// latitude-band clip (identity for the full image)

@@ -156,15 +156,14 @@ __global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
 				const float4 ec = s_c[j];
 
 				// backward.cu:766-782: same guards as the forward
-				const float2 xy = { ea.x, ea.y };
-				const float2 d = { xy.x - pixf.x, xy.y - pixf.y };
 				const float4 con_o = { ea.z, ea.w, eb.x, eb.y };
-				const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+				float2 d;
+				const float power = pair_power(ea.x, ea.y, con_o.x, con_o.y, con_o.z, pixf, d.x, d.y);
 				bool valid = inside && (__float_as_int(ec.y) < last_contributor) && !(power > 0.0f) && !(power < ec.z);
 				float G = 0.f, alpha = 0.f;
 				if (valid) {
 					G = expf(power);
-					alpha = fminf(0.99f, con_o.w * G);
+					alpha = fminf(0.99f, __fmul_rn(con_o.w, G));
 					valid = !(alpha < kAlphaMin);
 				}
 				if (!__any_sync(0xffffffffu, valid)) continue;

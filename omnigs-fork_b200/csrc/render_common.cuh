@@ -57,6 +57,19 @@ OGS_D bool gaussian_touches_box(float mx, float my, float A, float B, float C, f
 	return -0.5f * qmin >= tau - kCullAbs - kCullRel * mag;
 }
 
+// power(d) of a (pixel, Gaussian) pair in the reference's compiled operation order
+// (forward.cu:424-427 / backward.cu:772-775 as scheduled in its sm_100 SASS):
+//   q = fma(A*dx, dx, (C*dy)*dy);  power = fma(q, -0.5, -((B*dx)*dy))
+// Pinned with .rn intrinsics so the skip decisions (power > 0, alpha < 1/255, T < 1e-4) are
+// bit-identical to the reference's.
+OGS_D float pair_power(float mx, float my, float A, float B, float C, float2 pixf, float& dx, float& dy)
+{
+	dx = __fsub_rn(mx, pixf.x);
+	dy = __fsub_rn(my, pixf.y);
+	const float q = __fmaf_rn(__fmul_rn(A, dx), dx, __fmul_rn(__fmul_rn(C, dy), dy));
+	return __fmaf_rn(q, -0.5f, -__fmul_rn(__fmul_rn(B, dx), dy));
+}
+
 // Stable block-wide compaction slot for `keep` flags (list order must be preserved: blending is
 // order dependent).  Returns this thread's slot (valid when keep) and the block total.
 // Uses one __syncthreads; s_warp_cnt must hold kRenderThreads/32 words.

@@ -96,23 +96,21 @@ __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 				const float4 ea = s_a[j];
 				const float4 eb = s_b[j];
 				const float4 ec = s_c[j];
-				// forward.cu:424-427
-				const float2 xy = { ea.x, ea.y };
-				const float2 d = { xy.x - pixf.x, xy.y - pixf.y };
-				const float4 con_o = { ea.z, ea.w, eb.x, eb.y };
-				const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+				// forward.cu:424-455, arithmetic pinned to the reference's compiled order
+				float dx, dy;
+				const float power = pair_power(ea.x, ea.y, ea.z, ea.w, eb.x, pixf, dx, dy);
 				if (power > 0.0f) continue;
 				if (power < ec.z) continue; // alpha would be < 1/255 (skips expf)
-				const float alpha = fminf(0.99f, con_o.w * expf(power));
+				const float alpha = fminf(0.99f, __fmul_rn(eb.y, expf(power)));
 				if (alpha < kAlphaMin) continue;
-				const float test_T = T * (1 - alpha);
+				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
 				if (test_T < 0.0001f) {
 					done = true;
 					continue;
 				}
-				C[0] += eb.z * alpha * T;
-				C[1] += eb.w * alpha * T;
-				C[2] += ec.x * alpha * T;
+				C[0] = __fmaf_rn(T, __fmul_rn(alpha, eb.z), C[0]);
+				C[1] = __fmaf_rn(T, __fmul_rn(alpha, eb.w), C[1]);
+				C[2] = __fmaf_rn(T, __fmul_rn(alpha, ec.x), C[2]);
 				T = test_T;
 				last_contributor = __float_as_uint(ec.y);
 			}
@@ -124,9 +122,9 @@ __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 		const size_t HW = (size_t)H * W;
 		final_T[pix_id] = T;
 		n_contrib[pix_id] = last_contributor;
-		out_color[0 * HW + pix_id] = C[0] + T * bg_color[0];
-		out_color[1 * HW + pix_id] = C[1] + T * bg_color[1];
-		out_color[2 * HW + pix_id] = C[2] + T * bg_color[2];
+		out_color[0 * HW + pix_id] = __fmaf_rn(bg_color[0], T, C[0]);
+		out_color[1 * HW + pix_id] = __fmaf_rn(bg_color[1], T, C[1]);
+		out_color[2 * HW + pix_id] = __fmaf_rn(bg_color[2], T, C[2]);
 	}
 }
 

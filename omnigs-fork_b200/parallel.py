@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing for the two ways the lonlat path shards.
+
+(a) Data parallel over camera views: every rank holds all Gaussians, renders its own view(s) and the
+    per-Gaussian gradients are summed with one all-reduce per tensor (NCCL over NVLink on GPUs, gloo in
+    the CPU tests).  The reference itself has no multi-GPU code; the single-GPU equivalent is "sum of the
+    per-view gradients computed serially", which is what the tests compare against.
+(b) Latitude bands of one panorama: `band_rows` splits the tile rows so that every rank gets about
+    the same number of tile instances (pole rows are heavier); each rank then runs
+    ogs_lonlat_forward_stage1_band on its rows.
+"""
+import torch
+import torch.distributed as dist
+
+# tensors of the backward 8-tuple the optimiser consumes (236 B per Gaussian at SH degree 3)
+OPTIMISED = ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations")
+
+
+def is_distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def allreduce_gradients(grads, radii=None, group=None):
+    """Sum the optimiser-facing gradients over ranks, in place.  `grads` maps the names of
+    RasterizeGaussiansBackwardCUDA's outputs to tensors.  With `radii`, also reduces the densification
+    statistics the trainer derives per view (reference src/gaussian_mapper.cpp:427-434,
+    src/gaussian_model.cpp:839-853): sum of |dL_dmeans2D.xy|, visibility count, max radius.
+    Returns (grads, stats-or-None).  A no-op on a single rank."""
+    stats = None
+    if radii is not None:
+        vis = radii > 0
+        stats = {
+            "xyz_gradient_accum": torch.where(vis, grads["dL_dmeans2D"][:, :2].norm(dim=-1), torch.zeros_like(radii, dtype=torch.float32)),
+            "denom": vis.to(torch.float32),
+            "max_radii2D": radii.to(torch.float32),
+        }
+    if not is_distributed():
+        return grads, stats
+    work = [dist.all_reduce(grads[n], op=dist.ReduceOp.SUM, group=group, async_op=True) for n in OPTIMISED if grads[n].numel()]
+    if stats is not None:
+        work.append(dist.all_reduce(stats["xyz_gradient_accum"], op=dist.ReduceOp.SUM, group=group, async_op=True))
+        work.append(dist.all_reduce(stats["denom"], op=dist.ReduceOp.SUM, group=group, async_op=True))
+        work.append(dist.all_reduce(stats["max_radii2D"], op=dist.ReduceOp.MAX, group=group, async_op=True))
+    for w in work:
+        w.wait()
+    return grads, stats
+
+
+def views_for_rank(num_views, rank, world):
+    """Round-robin assignment of a step's views: rank g renders views g, g+G, ..."""
+    return list(range(rank, num_views, world))
+
+
+def band_rows(row_instance_counts, world):
+    """Split tile rows [0, gy) into `world` contiguous bands with balanced instance counts.
+    row_instance_counts[y] = number of tile instances in tile row y.  Returns [(y0, y1)] * world;
+    bands may be empty when world > gy."""
+    counts = [int(c) for c in row_instance_counts]
+    gy, total = len(counts), sum(counts)
+    bands, y, acc = [], 0, 0
+    for g in range(world):
+        target = total * (g + 1) / world
+        y0 = y
+        while y < gy and (acc + counts[y] <= target or y == y0) and (gy - y) > (world - g - 1):
+            acc += counts[y]
+            y += 1
+        if g == world - 1:
+            y = gy
+        bands.append((y0, y))
+    return bands

@@ -1,0 +1,57 @@
+"""CPU: host-side logic — scene generator, argument checks of the boundary mirror, band planner."""
+import numpy as np
+import pytest
+import torch
+
+import _harness as h
+
+sm = h.scene_mod
+
+
+def test_scene_generator_is_deterministic_and_well_formed():
+    a = sm.make_scene(500, 64, 32, 0.02, 3, pole_frac=0.1, seam_frac=0.1)
+    b = sm.make_scene(500, 64, 32, 0.02, 3, pole_frac=0.1, seam_frac=0.1)
+    for f in ("means3D", "scales", "rotations", "opacities", "shs"):
+        assert np.array_equal(getattr(a, f), getattr(b, f))
+        assert getattr(a, f).dtype == np.float32
+    assert np.allclose(np.linalg.norm(a.rotations, axis=1), 1.0, atol=1e-5)
+    assert (a.opacities >= 0.05).all() and (a.opacities < 1.0).all()
+    assert (a.scales > 0).all()
+    r = np.linalg.norm(a.means3D, axis=1)
+    assert (r < 0.2).sum() >= 0 and r.max() <= 20.5
+
+
+def test_view_convention():
+    V, c = sm.random_view(9)
+    Tcw = V.T.astype(np.float64)            # viewmatrix is Tcw transposed
+    R, t = Tcw[:3, :3], Tcw[:3, 3]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-6)
+    assert np.allclose(-R.T @ t, c, atol=1e-6)   # campos = camera centre
+    assert np.linalg.norm(c) <= 0.3 + 1e-6
+
+
+def test_boundary_argument_checks_without_gpu():
+    bad = torch.zeros((4, 2))
+    e = torch.empty((0,))
+    with pytest.raises(RuntimeError, match="means3D must have dimensions"):
+        h.pkg.RasterizeGaussiansCUDA(e, bad, e, e, e, e, 1.0, e, e, e, 0.0, 0.0, 8, 8, e, 0, e, False, 3, False)
+    ok = torch.zeros((4, 3))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):   # no CPU path, fails loudly
+        h.pkg.RasterizeGaussiansCUDA(e, ok, e, e, e, e, 1.0, e, e, e, 0.0, 0.0, 8, 8, e, 0, e, False, 3, False)
+
+
+def test_rasterizer_module_argument_rules():
+    rs = h.pkg.GaussianRasterizationSettings(8, 8, 0.0, 0.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0,
+                                             torch.zeros(3))
+    r = h.pkg.GaussianRasterizer(rs)
+    m = torch.zeros((2, 3))
+    with pytest.raises(RuntimeError, match="excatly one of either SHs or precomputed colors"):
+        r(m, m, torch.ones(2, 1), shs=None, colors_precomp=None, scales=m, rotations=torch.zeros(2, 4))
+    with pytest.raises(RuntimeError, match="scale/rotation pair or precomputed 3D covariance"):
+        r(m, m, torch.ones(2, 1), shs=torch.zeros(2, 1, 3), scales=m, rotations=torch.zeros(2, 4),
+          cov3D_precomp=torch.zeros(2, 6))
+
+
+def test_config_table_matches_baseline():
+    assert sm.CONFIGS["C2"]["P"] == 1_000_000 and (sm.CONFIGS["C2"]["W"], sm.CONFIGS["C2"]["H"]) == (2048, 1024)
+    assert sm.CONFIGS["C1"]["P"] == 100_000 and (sm.CONFIGS["C1"]["W"], sm.CONFIGS["C1"]["H"]) == (1024, 512)

@@ -1,0 +1,334 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libomnigs_b200.so) against
+  (1) the committed golden fixtures = outputs of the unmodified reference rasterizer,
+  (2) the CPU oracle on seeded inputs,
+  (3) the reference rasterizer itself (oracle/_ref/omnigs_ref.so) when it travelled to the box,
+  (4) size-independent properties at BASELINE.json's full size (C2: 1M Gaussians, 2048x1024).
+
+Parity bar (BASELINE.json north_star): num_rendered, radii, tile ranges, sorted point list and keys
+bit-exact; image <= 1e-5 max-abs; gradients <= 1e-4 relative (max-norm per tensor; per-element
+|a-b| <= 1e-4|b| + 1e-5*max|b| allows for the reference's own atomic-order noise, measured at
+~1e-5 by running the reference twice)."""
+import numpy as np
+import pytest
+import torch
+
+import _harness as h
+import cases
+
+pytestmark = pytest.mark.gpu
+sm = h.scene_mod
+
+IMG_TOL = 1e-5
+GRAD_REL = 1e-4
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def assert_grads_close(ours, ref, names=h.GRAD_NAMES):
+    for n, a, b in zip(names, ours, ref):
+        a = torch.as_tensor(a).double().cpu().flatten()
+        b = torch.as_tensor(b).double().cpu().flatten()
+        assert a.shape == b.shape, n
+        if b.numel() == 0:
+            continue
+        scale = float(b.abs().max())
+        if scale < 1e-9:
+            assert float(a.abs().max()) < 1e-8, n
+            continue
+        diff = (a - b).abs()
+        assert float(diff.max()) / scale <= GRAD_REL, (n, float(diff.max()) / scale)
+        assert bool((diff <= 1e-4 * b.abs() + 1e-5 * scale).all()), n
+
+
+def bits(t):
+    return t.contiguous().view(torch.int32)
+
+
+# ------------------------------------------------------------------ (1) golden fixtures
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_against_golden_reference_outputs(name):
+    gold = np.load(f"{h.ROOT}/tests/golden/{name}.npz")
+    scene, view, dL_np, c = cases.build(name)
+    assert bytes(gold["input_sha256"]).decode() == cases.input_hash(scene, view, dL_np)
+    d = h.torch_inputs(scene, view, mode=c["mode"], bg=c["bg"], degree=c["degree"])
+    fwd = h.run_forward(h.pkg, d)
+    grads = h.run_backward(h.pkg, d, fwd, torch.from_numpy(dL_np).cuda())
+    st = h.ours_state(d, fwd)
+    torch.cuda.synchronize()
+
+    assert fwd[0] == int(gold["num_rendered"])
+    assert np.array_equal(_np(fwd[2]), gold["radii"])
+    assert np.array_equal(_np(st["tiles_touched"]), gold["tiles_touched"])
+    vis = gold["radii"] > 0
+    for k in ("means2D", "depths", "conic_opacity"):
+        assert np.array_equal(_np(st[k])[vis].view(np.int32), gold[k][vis].view(np.int32)), k
+    assert np.array_equal(_np(st["ranges"]), gold["ranges"])
+    assert np.array_equal(_np(st["point_list"]), gold["point_list"])
+    assert np.array_equal(_np(st["point_list_keys"]), gold["point_list_keys"])
+    if "rgb" in gold:
+        assert np.abs(_np(st["rgb"])[vis] - gold["rgb"][vis]).max() <= 1e-6
+        assert np.array_equal(_np(st["clamped"])[vis], gold["clamped"][vis])
+    assert np.abs(_np(fwd[1]) - gold["out_color"]).max() <= IMG_TOL
+    assert np.abs(_np(st["accum_alpha"]) - gold["accum_alpha"]).max() <= IMG_TOL
+    assert np.array_equal(_np(st["n_contrib"]), gold["n_contrib"])
+    assert_grads_close(grads, [gold[n] for n in h.GRAD_NAMES])
+
+
+# ------------------------------------------------------------------ (2) CPU oracle
+@pytest.mark.parametrize("seed,W,H,degree,bg", [(1, 177, 93, 3, (0, 0, 0)), (2, 64, 48, 0, (1, 0.5, 0.25))])
+def test_against_cpu_oracle(seed, W, H, degree, bg):
+    from oracle import oracle
+    scene = sm.make_scene(2500, W, H, 0.04, 40 + seed, pole_frac=0.1, seam_frac=0.05, near_frac=0.01)
+    view = sm.random_view(50 + seed)
+    dL_np = sm.make_grad_image(W, H, 60 + seed)
+    d = h.torch_inputs(scene, view, bg=bg, degree=degree)
+    fwd = h.run_forward(h.pkg, d)
+    grads = h.run_backward(h.pkg, d, fwd, torch.from_numpy(dL_np).cuda())
+    bgn = np.array(bg, np.float32)
+    of = oracle.forward(scene.means3D, scene.opacities, view[0], view[1], W, H, bgn, shs=scene.shs, degree=degree,
+                        scales=scene.scales, rotations=scene.rotations)
+    og = oracle.backward(of, dL_np, scene.means3D, view[0], view[1], W, H, bgn, shs=scene.shs, degree=degree,
+                         scales=scene.scales, rotations=scene.rotations)
+    # CPU libm vs CUDA libdevice: allow isolated threshold flips, nothing systematic
+    assert abs(fwd[0] - of["num_rendered"]) <= max(4, of["num_rendered"] // 500)
+    assert int((_np(fwd[2]) != of["radii"]).sum()) <= 2
+    diff = np.abs(_np(fwd[1]) - of["out_color"]).max(axis=0)
+    assert (diff > 1e-4).mean() <= 2e-3 and diff.max() < 0.1
+    for n, g in zip(h.GRAD_NAMES, grads):
+        ref = og[n].reshape(tuple(g.shape))
+        scale = np.abs(ref).max() + 1e-30
+        assert np.abs(_np(g) - ref).max() / scale < 1e-2, n
+
+
+# ------------------------------------------------------------------ (3) the reference itself
+REF_CASES = {
+    "C1": lambda: (sm.make_config_scene("C1"), sm.identity_view(), "sh", (0, 0, 0), 3),
+    "C1_view": lambda: (sm.make_config_scene("C1"), sm.random_view(71), "sh", (1, 1, 1), 3),
+    "odd_deg2": lambda: (sm.make_scene(30000, 517, 263, 0.03, 72, pole_frac=0.1, seam_frac=0.05), sm.random_view(73), "sh", (0, 0, 0), 2),
+    "colors": lambda: (sm.make_scene(30000, 400, 200, 0.03, 74), sm.random_view(75), "colors", (0.1, 0.2, 0.3), 0),
+    "cov_deg1": lambda: (sm.make_scene(30000, 400, 200, 0.03, 76), sm.random_view(77), "cov", (0, 0, 0), 1),
+    "long_lists": lambda: (sm.make_scene(40000, 256, 128, 0.15, 78), sm.identity_view(), "sh", (0, 0, 0), 3),
+}
+
+
+@pytest.mark.parametrize("case", list(REF_CASES))
+def test_against_reference_rasterizer(case):
+    ref = h.load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref/omnigs_ref.so not present on this box")
+    scene, view, mode, bg, degree = REF_CASES[case]()
+    d = h.torch_inputs(scene, view, mode=mode, bg=bg, degree=degree)
+    dL = torch.from_numpy(sm.make_grad_image(scene.W, scene.H, 99)).cuda()
+    fo, fr = h.run_forward(h.pkg, d), h.run_forward(ref, d)
+    go, gr = h.run_backward(h.pkg, d, fo, dL), h.run_backward(ref, d, fr, dL)
+    so, sr = h.ours_state(d, fo), h.ref_state(ref, d, fr)
+    torch.cuda.synchronize()
+    assert fo[0] == fr[0]
+    assert torch.equal(fo[2], fr[2])
+    vis = fr[2] > 0
+    assert torch.equal(so["tiles_touched"], sr["tiles_touched"])
+    for k in ("means2D", "depths", "conic_opacity"):
+        assert torch.equal(bits(so[k][vis]), bits(sr[k][vis])), k
+    assert torch.equal(so["ranges"], sr["ranges"])
+    assert torch.equal(so["point_list"], sr["point_list"])
+    assert torch.equal(so["point_list_keys"], sr["point_list_keys"])
+    assert float((fo[1] - fr[1]).abs().max()) <= IMG_TOL
+    assert float((so["accum_alpha"] - sr["accum_alpha"]).abs().max()) <= IMG_TOL
+    assert torch.equal(so["n_contrib"], sr["n_contrib"])
+    assert_grads_close(go, gr)
+
+
+# ------------------------------------------------------------------ (4) full-size properties (C2)
+@pytest.fixture(scope="module")
+def c2():
+    scene = sm.make_config_scene("C2")
+    d = h.torch_inputs(scene, sm.random_view(21))
+    fwd = h.run_forward(h.pkg, d)
+    return scene, d, fwd
+
+
+def test_c2_binning_invariants(c2):
+    scene, d, fwd = c2
+    R = fwd[0]
+    st = h.ours_state(d, fwd)
+    keys = st["point_list_keys"]
+    assert int(st["tiles_touched"].long().sum()) == R
+    assert bool((keys[1:] >= keys[:-1]).all()), "keys not sorted"
+    # equal keys keep ascending Gaussian index (stability of the reference's radix sort)
+    same = keys[1:] == keys[:-1]
+    pl = st["point_list"].long()
+    assert bool((pl[1:][same] > pl[:-1][same]).all())
+    ranges = st["ranges"].long()
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert int(lens.sum()) == R and bool((lens >= 0).all())
+    nz = lens > 0
+    tiles = (keys >> 32)
+    assert torch.equal(torch.unique(tiles), torch.nonzero(nz).flatten())
+    assert torch.equal(tiles[ranges[nz, 0]], torch.nonzero(nz).flatten())
+    # every list entry is a visible Gaussian whose depth bits are the low key word
+    depth_bits = bits(st["depths"]).long() & 0xFFFFFFFF
+    assert torch.equal(keys & 0xFFFFFFFF, depth_bits[pl])
+    assert bool((fwd[2][pl] > 0).all())
+    # a checksum of checksums: per-Gaussian multiplicity in the list == tiles_touched
+    mult = torch.bincount(pl, minlength=scene.P)
+    assert torch.equal(mult, st["tiles_touched"].long())
+
+
+def test_c2_forward_is_deterministic(c2):
+    scene, d, fwd = c2
+    again = h.run_forward(h.pkg, d)
+    assert again[0] == fwd[0]
+    assert torch.equal(bits(again[1]), bits(fwd[1]))
+    assert torch.equal(again[2], fwd[2])
+    img = fwd[1]
+    assert bool(torch.isfinite(img).all()) and float(img.min()) >= 0.0
+
+
+def test_c2_backward_is_linear_in_upstream_gradient(c2):
+    scene, d, fwd = c2
+    g1 = torch.from_numpy(sm.make_grad_image(scene.W, scene.H, 1)).cuda()
+    g2 = torch.from_numpy(sm.make_grad_image(scene.W, scene.H, 2)).cuda()
+    a = h.run_backward(h.pkg, d, fwd, g1)
+    b = h.run_backward(h.pkg, d, fwd, g2)
+    c = h.run_backward(h.pkg, d, fwd, 2.0 * g1 - 3.0 * g2)
+    for n, x, y, z in zip(h.GRAD_NAMES, a, b, c):
+        lin = 2.0 * x - 3.0 * y
+        scale = float(lin.abs().max()) + 1e-30
+        assert float((z - lin).abs().max()) / scale < 2e-4, n
+    culled = fwd[2] == 0
+    for n, x in zip(h.GRAD_NAMES, a):
+        assert not bool(x[culled].any()), n     # culled Gaussians get exact zeros
+    assert not bool(a[0][:, 2].any())           # dL_dmeans2D.z is never written
+    assert bool(all(torch.isfinite(x).all() for x in a))
+
+
+def test_c2_against_reference_if_present(c2):
+    ref = h.load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref/omnigs_ref.so not present on this box")
+    scene, d, fo = c2
+    dL = torch.from_numpy(sm.make_grad_image(scene.W, scene.H, 99)).cuda()
+    fr = h.run_forward(ref, d)
+    assert fo[0] == fr[0] and torch.equal(fo[2], fr[2])
+    so, sr = h.ours_state(d, fo), h.ref_state(ref, d, fr)
+    assert torch.equal(so["point_list"], sr["point_list"])
+    assert torch.equal(so["point_list_keys"], sr["point_list_keys"])
+    assert torch.equal(so["ranges"], sr["ranges"])
+    assert float((fo[1] - fr[1]).abs().max()) <= IMG_TOL
+    assert torch.equal(so["n_contrib"], sr["n_contrib"])
+    assert_grads_close(h.run_backward(h.pkg, d, fo, dL), h.run_backward(ref, d, fr, dL))
+
+
+# ------------------------------------------------------------------ edge cases
+def test_empty_scene_returns_zero_outputs():
+    e = torch.empty((0,), device="cuda")
+    m = torch.empty((0, 3), device="cuda")
+    out = h.pkg.RasterizeGaussiansCUDA(torch.ones(3, device="cuda"), m, e, e, e, e, 1.0, e, torch.eye(4, device="cuda"),
+                                       torch.eye(4, device="cuda"), 0.0, 0.0, 20, 30, e, 0, torch.zeros(3, device="cuda"),
+                                       False, 3, False)
+    assert out[0] == 0 and out[1].shape == (3, 20, 30) and not bool(out[1].any())   # rasterize_points.cu:84,97
+    assert out[2].numel() == 0
+    g = h.pkg.RasterizeGaussiansBackwardCUDA(torch.ones(3, device="cuda"), m, out[2], e, e, e, 1.0, e,
+                                             torch.eye(4, device="cuda"), torch.eye(4, device="cuda"), 0.0, 0.0,
+                                             torch.zeros(3, 20, 30, device="cuda"), e, 0, torch.zeros(3, device="cuda"),
+                                             out[3], 0, out[4], out[5], 3)
+    assert [tuple(x.shape) for x in g] == [(0, 3), (0, 3), (0, 1), (0, 3), (0, 6), (0, 0, 3), (0, 3), (0, 4)]
+
+
+def test_all_culled_renders_background():
+    scene = sm.make_scene(300, 50, 30, 0.02, 5)
+    scene.means3D[:] *= 0.005                      # everything inside the r <= 0.2 cull sphere
+    d = h.torch_inputs(scene, sm.identity_view(), bg=(0.25, 0.5, 0.75))
+    fwd = h.run_forward(h.pkg, d)
+    assert fwd[0] == 0 and not bool(fwd[2].any())
+    exp = torch.tensor([0.25, 0.5, 0.75], device="cuda")[:, None, None].expand(3, 30, 50)
+    assert torch.equal(fwd[1], exp)
+    g = h.run_backward(h.pkg, d, fwd, torch.ones(3, 30, 50, device="cuda"))
+    assert not any(bool(x.any()) for x in g)
+
+
+def test_invalid_camera_type_raises_like_the_reference():
+    scene = sm.make_scene(10, 32, 16, 0.02, 6)
+    d = h.torch_inputs(scene, sm.identity_view())
+    args = [d["background"], d["means3D"], d["colors"], d["opacity"], d["scales"], d["rotations"], 1.0,
+            d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], 0.0, 0.0, 16, 32, d["sh"], 3, d["campos"], False]
+    with pytest.raises(RuntimeError, match=r"\[CudaRasterizer\]Invalid camera_type"):
+        h.pkg.RasterizeGaussiansCUDA(*args, 2, False)
+    with pytest.raises(NotImplementedError):
+        h.pkg.RasterizeGaussiansCUDA(*args, 1, False)
+
+
+def test_mark_visible_marks_everything():
+    m = torch.randn(1000, 3, device="cuda")
+    v = h.pkg.markVisible(m, torch.eye(4, device="cuda"), torch.eye(4, device="cuda"), 3)
+    assert v.dtype == torch.bool and bool(v.all())
+
+
+@pytest.mark.parametrize("W,H", [(1, 1), (16, 16), (17, 15), (33, 65)])
+def test_tiny_and_ragged_images_match_oracle(W, H):
+    from oracle import oracle
+    scene = sm.make_scene(200, W, H, 0.2, 8)
+    view = sm.identity_view()
+    d = h.torch_inputs(scene, view)
+    fwd = h.run_forward(h.pkg, d)
+    of = oracle.forward(scene.means3D, scene.opacities, view[0], view[1], W, H, np.zeros(3, np.float32), shs=scene.shs,
+                        degree=3, scales=scene.scales, rotations=scene.rotations)
+    assert abs(fwd[0] - of["num_rendered"]) <= 2
+    diff = np.abs(_np(fwd[1]) - of["out_color"])
+    assert np.median(diff) < 1e-5 and (diff > 1e-3).mean() < 0.02
+
+
+def test_single_huge_gaussian_fans_out_over_every_tile():
+    # one Gaussian whose square rect covers the whole 2048x1024 grid: exercises the load-balanced
+    # emission (one source -> 8192 slots) and a polar position
+    scene = sm.make_scene(1, 2048, 1024, 0.02, 9)
+    scene.means3D[0] = (0.01, -3.0, 0.02)          # almost at the pole (lat ~ -90 deg, +y is down)
+    scene.scales[0] = (2.0, 2.0, 2.0)
+    d = h.torch_inputs(scene, sm.identity_view())
+    fwd = h.run_forward(h.pkg, d)
+    st = h.ours_state(d, fwd)
+    assert fwd[0] == int(st["tiles_touched"][0]) == 128 * 64
+    assert bool((st["point_list"] == 0).all())
+    assert torch.equal(st["ranges"][:, 0].long(), torch.arange(8192, device="cuda"))
+
+
+def test_latitude_bands_partition_the_frame():
+    """Stage 1 with a tile-row band: the union of the bands' lists is the full frame's list."""
+    import ctypes
+    lib = h.pkg.load_library()
+    scene = sm.make_scene(20000, 512, 256, 0.03, 10, pole_frac=0.2)
+    d = h.torch_inputs(scene, sm.random_view(11))
+    full = h.run_forward(h.pkg, d)
+    st_full = h.ours_state(d, full)
+    P, W, H = scene.P, scene.W, scene.H
+    gy = (H + 15) // 16
+    total, img = 0, torch.zeros_like(full[1])
+    for (b0, b1) in [(0, 5), (5, 11), (11, gy)]:
+        radii = torch.empty(P, dtype=torch.int32, device="cuda")
+        geom = torch.empty(lib.ogs_geom_bytes(P), dtype=torch.uint8, device="cuda")
+        imgb = torch.empty(lib.ogs_img_bytes(W, H), dtype=torch.uint8, device="cuda")
+        n = ctypes.c_int64(0)
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else None
+        rc = lib.ogs_lonlat_forward_stage1_band(P, 3, 16, W, H, b0, b1, p(d["means3D"]), p(d["sh"]), None, p(d["opacity"]),
+                                               p(d["scales"]), 1.0, p(d["rotations"]), None, p(d["viewmatrix"]),
+                                               p(d["campos"]), p(radii), p(geom), p(imgb), ctypes.byref(n), None)
+        assert rc == 0
+        R = n.value
+        binb = torch.empty(lib.ogs_binning_bytes(R, W, H), dtype=torch.uint8, device="cuda")
+        out = torch.empty(3, H, W, device="cuda")
+        assert lib.ogs_lonlat_forward_stage2(P, W, H, R, p(d["background"]), p(geom), p(binb), p(imgb), p(out), None) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(radii, full[2])          # radii are the unclipped reference radii
+        st = h.pkg.export_forward_state(P, W, H, R, geom, binb, imgb)
+        rows = slice(b0 * (W // 16), b1 * (W // 16))
+        lens_band = (st["ranges"][:, 1] - st["ranges"][:, 0]).long()
+        lens_full = (st_full["ranges"][:, 1] - st_full["ranges"][:, 0]).long()
+        assert torch.equal(lens_band[rows], lens_full[rows]) and int(lens_band.sum()) == R == int(lens_full[rows].sum())
+        start = int(st_full["ranges"][rows][lens_full[rows] > 0][0, 0]) if R else 0
+        assert torch.equal(st["point_list"], st_full["point_list"][start:start + R])
+        img[:, b0 * 16:min(H, b1 * 16)] = out[:, b0 * 16:min(H, b1 * 16)]
+        total += R
+    assert total == full[0]
+    assert torch.equal(bits(img), bits(full[1]))

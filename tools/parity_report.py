@@ -46,11 +46,13 @@ def report(name, scene, view, mode="sh", bg=(0, 0, 0), degree=3, time_it=True):
         vis = fr[2] > 0
         print("radii mismatches", int((fo[2] != fr[2]).sum()), "/", scene.P, " visible", int(vis.sum()))
         print("tiles_touched mismatches", int((so["tiles_touched"] != sr["tiles_touched"]).sum()))
-        for k in ["means2D", "depths", "conic_opacity", "rgb", "cov3D"]:
+        keys = ["means2D", "depths", "conic_opacity"] + ([] if mode == "colors" else ["rgb"]) + ([] if mode == "cov" else ["cov3D"])
+        for k in keys:
             a, b = so[k][vis], sr[k][vis]
             bits = int((a.view(torch.int32) != b.view(torch.int32)).sum())
             print(f"  {k}: bit mismatches {bits} / {a.numel()}  max abs diff {float((a - b).abs().max()) if a.numel() else 0:.3e}")
-        print("  clamped mismatches", int((so["clamped"][vis] != sr["clamped"][vis].to(torch.uint8)).sum()))
+        if mode != "colors":
+            print("  clamped mismatches", int((so["clamped"][vis] != sr["clamped"][vis].to(torch.uint8)).sum()))
         if fo[0] == fr[0]:
             print("ranges mismatches", int((so["ranges"] != sr["ranges"]).sum()),
                   " point_list mismatches", int((so["point_list"] != sr["point_list"]).sum()),
