@@ -1,0 +1,87 @@
+"""CPU: the multi-GPU plumbing on the gloo backend (world_size 2) and the latitude-band planner."""
+import importlib
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import _harness as h  # noqa: F401  (registers the package)
+
+par = importlib.import_module("omnigs-fork_b200.parallel")
+NAMES = h.GRAD_NAMES
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make(rank, P=257, M=16):
+    g = torch.Generator().manual_seed(100 + rank)
+    shapes = {"dL_dmeans2D": (P, 3), "dL_dcolors": (P, 3), "dL_dopacity": (P, 1), "dL_dmeans3D": (P, 3),
+              "dL_dcov3D": (P, 6), "dL_dsh": (P, M, 3), "dL_dscales": (P, 3), "dL_drotations": (P, 4)}
+    grads = {n: torch.randn(s, generator=g) for n, s in shapes.items()}
+    radii = torch.randint(0, 40, (P,), generator=g, dtype=torch.int32)
+    return grads, radii
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grads, radii = _make(rank)
+    grads, stats = par.allreduce_gradients(grads, radii)
+    if rank == 0:
+        torch.save({"grads": grads, "stats": stats}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_world2_gloo(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    (g0, r0), (g1, r1) = _make(0), _make(1)
+    for n in NAMES:
+        if n in par.OPTIMISED:      # summed: what the optimiser consumes
+            assert torch.allclose(got["grads"][n], g0[n] + g1[n], atol=1e-6), n
+        else:                        # per-view quantities stay local
+            assert torch.equal(got["grads"][n], g0[n]), n
+    acc = sum(torch.where(r > 0, g["dL_dmeans2D"][:, :2].norm(dim=-1), torch.zeros(r.shape)) for g, r in ((g0, r0), (g1, r1)))
+    assert torch.allclose(got["stats"]["xyz_gradient_accum"], acc, atol=1e-6)
+    assert torch.equal(got["stats"]["denom"], (r0 > 0).float() + (r1 > 0).float())
+    assert torch.equal(got["stats"]["max_radii2D"], torch.maximum(r0, r1).float())
+
+
+def test_allreduce_is_identity_on_one_rank():
+    grads, radii = _make(0)
+    ref = {k: v.clone() for k, v in grads.items()}
+    out, stats = par.allreduce_gradients(grads, radii)
+    for n in NAMES:
+        assert torch.equal(out[n], ref[n])
+    assert stats["denom"].sum() == (radii > 0).sum()
+
+
+def test_views_round_robin():
+    assert par.views_for_rank(8, 1, 4) == [1, 5]
+    assert sorted(sum((par.views_for_rank(8, r, 3) for r in range(3)), [])) == list(range(8))
+
+
+def test_band_rows_balances_instances_and_covers_all_rows():
+    rng = np.random.default_rng(0)
+    counts = rng.integers(100, 1000, 64)
+    counts[:6] *= 8      # heavy polar rows
+    counts[-6:] *= 8
+    for world in (1, 2, 3, 4, 8):
+        bands = par.band_rows(counts, world)
+        assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == 64
+        assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        loads = [int(counts[a:b].sum()) for a, b in bands]
+        assert max(loads) <= 1.6 * sum(loads) / world + counts.max()
+    assert par.band_rows([5, 5], 4)[-1][1] == 2   # more ranks than rows: trailing bands may be empty
