@@ -77,37 +77,79 @@ __global__ void __launch_bounds__(256) depth_histogram_kernel(const uint32_t* __
 
 // ------------------------------------------------------------------ onesweep radix pass
 // One stable LSD pass over (key,value) pairs on digit (key >> shift) & (2^bits - 1), bits <= 9.
-// Chained-scan ("onesweep") formulation: every block takes a dynamic tile id, ranks its 4096
+// Chained-scan ("onesweep") formulation: every block takes a dynamic tile id, ranks its 2048
 // keys locally, publishes its per-digit counts and resolves its global offsets by decoupled
 // look-back over the predecessors' status words; digit totals come from `digit_counts`.
 // vals_in == nullptr means value i = i (first depth pass); keys_out == nullptr skips the key
-// write (last tile pass).
+// write (last tile pass).  Sized for occupancy: 256 threads x 8 keys, values are only loaded when
+// they are staged.  Throughput of a chained scan is bounded by (look-back batch x tile size) / L2
+// latency, and the look-back window grows with the number of CTAs in flight, hence 4096-key tiles,
+// 16 status words per round trip and 3 CTAs per SM.
 struct OnesweepSmem {
 	uint32_t warp_hist[kSortThreads / 32][kMaxBins]; // per-warp digit counters -> warp offsets
 	uint32_t bin_start[kMaxBins];                    // exclusive prefix of the tile's digit totals
 	uint32_t global_base[kMaxBins];                  // global offset of digit run minus bin_start
 	uint32_t keys[kSortItemsPerBlock];
 	uint32_t vals[kSortItemsPerBlock];
+	uint32_t tile_hist[kMaxBins];                    // digit counts of this tile (published early)
 	uint32_t warp_tmp[8];
 	uint32_t tile;
 };
 
-__global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
+constexpr int kLookbackBatch = 16;
+
+// Decoupled look-back for one counter: sum the predecessors' published values back to the nearest
+// inclusive one.  Status words of kLookbackBatch predecessors are fetched together, so the walk
+// costs one L2 round trip per batch instead of one per tile (with several hundred CTAs in flight
+// the not-yet-inclusive window is hundreds of tiles long).
+OGS_D uint32_t lookback_sum(const uint32_t* __restrict__ status, int tile, size_t stride, size_t offset)
+{
+	uint32_t excl = 0;
+	int t = tile - 1;
+	while (true) {
+		uint32_t s[kLookbackBatch];
+#pragma unroll
+		for (int i = 0; i < kLookbackBatch; i++)
+			s[i] = (t - i >= 0) ? ld_acquire(&status[(size_t)(t - i) * stride + offset]) : kFlagInclusive;
+		bool done = false;
+		int consumed = kLookbackBatch;
+#pragma unroll
+		for (int i = 0; i < kLookbackBatch; i++) {
+			if (!done && consumed == kLookbackBatch) {
+				const uint32_t flag = s[i] & ~kValueMask;
+				if (flag == 0) {
+					consumed = i;            // not published yet: poll again from this tile
+				} else {
+					excl += s[i] & kValueMask;
+					if (flag == kFlagInclusive) done = true;
+				}
+			}
+		}
+		if (done) break;
+		t -= consumed;
+	}
+	return excl;
+}
+
+__global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
 	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
 	uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
 	uint32_t n, int shift, int bits,
 	const uint32_t* __restrict__ digit_counts, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
+	__shared__ OnesweepSmem sm;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nbins = 1 << bits;
 	const uint32_t mask = (uint32_t)nbins - 1u;
 
 	if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-	for (int i = tid; i < (kSortThreads / 32) * kMaxBins; i += kSortThreads) (&sm.warp_hist[0][0])[i] = 0;
+	for (int w = 0; w < kSortThreads / 32; w++)
+		for (int b = tid; b < nbins; b += kSortThreads) sm.warp_hist[w][b] = 0;
 	// global digit starts: exclusive scan of the pass histogram
-	for (int b = tid; b < nbins; b += kSortThreads) sm.global_base[b] = digit_counts[b];
+	for (int b = tid; b < nbins; b += kSortThreads) {
+		sm.global_base[b] = digit_counts[b];
+		sm.tile_hist[b] = 0;
+	}
 	__syncthreads();
 	block_exclusive_scan_512(sm.global_base, nbins, sm.warp_tmp);
 
@@ -115,16 +157,23 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
 	const uint32_t tile_base = tile * (uint32_t)kSortItemsPerBlock;
 	const uint32_t tile_count = min((uint32_t)kSortItemsPerBlock, n - tile_base);
 
-	// ---- load (warp-striped) and rank ----
-	uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+	// ---- load (warp-striped); count digits and publish the tile's counts before the (slow) ranking ----
+	uint32_t key[kSortItems];
+	uint32_t rank[kSortItems];
 	const uint32_t warp_base = tile_base + warp * (32 * kSortItems);
 #pragma unroll
 	for (int k = 0; k < kSortItems; k++) {
 		uint32_t idx = warp_base + k * 32 + lane;
-		bool valid = idx < n;
-		key[k] = valid ? keys_in[idx] : 0xFFFFFFFFu;
-		val[k] = valid ? (vals_in ? vals_in[idx] : idx) : 0u;
+		key[k] = (idx < n) ? keys_in[idx] : 0xFFFFFFFFu;
 	}
+#pragma unroll
+	for (int k = 0; k < kSortItems; k++) {
+		uint32_t idx = warp_base + k * 32 + lane;
+		if (idx < n) atomicAdd(&sm.tile_hist[(key[k] >> shift) & mask], 1u);
+	}
+	__syncthreads();
+	for (int b = tid; b < nbins; b += kSortThreads)
+		st_release(&status[(size_t)tile * nbins + b], (tile == 0 ? kFlagInclusive : kFlagPartial) | sm.tile_hist[b]);
 #pragma unroll
 	for (int k = 0; k < kSortItems; k++) {
 		uint32_t idx = warp_base + k * 32 + lane;
@@ -156,33 +205,19 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
 	}
 	__syncthreads();
 
-	// ---- decoupled look-back (one thread per digit) ----
+	// ---- decoupled look-back (one thread per digit, batched status loads) ----
 	for (int b = tid; b < nbins; b += kSortThreads) {
-		const uint32_t total = sm.bin_start[b];
-		uint32_t excl = 0;
-		if (tile == 0) {
-			st_release(&status[b], kFlagInclusive | total);
-		} else {
-			st_release(&status[(size_t)tile * nbins + b], kFlagPartial | total);
-			int t = (int)tile - 1;
-			while (true) {
-				uint32_t s = ld_acquire(&status[(size_t)t * nbins + b]);
-				uint32_t flag = s & ~kValueMask;
-				if (flag == 0) continue; // predecessor has not published yet
-				excl += s & kValueMask;
-				if (flag == kFlagInclusive) break;
-				t--;
-			}
-			st_release(&status[(size_t)tile * nbins + b], kFlagInclusive | (excl + total));
+		if (tile != 0) {
+			const uint32_t excl = lookback_sum(status, (int)tile, (size_t)nbins, (size_t)b);
+			st_release(&status[(size_t)tile * nbins + b], kFlagInclusive | (excl + sm.bin_start[b]));
+			sm.global_base[b] += excl; // digit start + keys of this digit in earlier tiles
 		}
-		sm.global_base[b] += excl; // digit start + keys of this digit in earlier tiles
 	}
 	__syncthreads();
 	block_exclusive_scan_512(sm.bin_start, nbins, sm.warp_tmp); // totals -> tile-local starts
 	for (int b = tid; b < nbins; b += kSortThreads) sm.global_base[b] -= sm.bin_start[b];
-	__syncthreads();
 
-	// ---- stage into digit order, then coalesced scatter ----
+	// ---- stage into digit order (values are fetched only now), then coalesced scatter ----
 #pragma unroll
 	for (int k = 0; k < kSortItems; k++) {
 		uint32_t idx = warp_base + k * 32 + lane;
@@ -190,7 +225,7 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
 			uint32_t d = (key[k] >> shift) & mask;
 			uint32_t pos = sm.bin_start[d] + sm.warp_hist[warp][d] + rank[k];
 			sm.keys[pos] = key[k];
-			sm.vals[pos] = val[k];
+			sm.vals[pos] = vals_in ? vals_in[idx] : idx;
 		}
 	}
 	__syncthreads();
@@ -205,6 +240,10 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
 
 // ------------------------------------------------------------------ exclusive scan (look-back)
 // out[i] = sum_{j<i} counts[order[j]] for i in [0, n]; out has n+1 entries.
+// Also fills first_src[b] = index i of the source that owns output slot min(b*kEmitPerBlock, R-1)
+// for b in [0, ceil(R/kEmitPerBlock)], so the emission needs no search (R = *total).
+constexpr int kEmitPerBlock = 2048;
+
 struct ScanSmem {
 	uint32_t warp_tmp[8];
 	uint32_t tile;
@@ -212,7 +251,8 @@ struct ScanSmem {
 };
 __global__ void __launch_bounds__(kSortThreads) gather_scan_kernel(
 	const uint32_t* __restrict__ counts, const uint32_t* __restrict__ order, uint32_t n,
-	uint32_t* __restrict__ out, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket)
+	uint32_t* __restrict__ out, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket,
+	uint32_t* __restrict__ first_src, const unsigned long long* __restrict__ total)
 {
 	__shared__ ScanSmem sm;
 	const int tid = threadIdx.x;
@@ -250,25 +290,27 @@ __global__ void __launch_bounds__(kSortThreads) gather_scan_kernel(
 			st_release(&status[0], kFlagInclusive | tile_total);
 		} else {
 			st_release(&status[tile], kFlagPartial | tile_total);
-			int t = (int)tile - 1;
-			while (true) {
-				uint32_t s = ld_acquire(&status[t]);
-				uint32_t flag = s & ~kValueMask;
-				if (flag == 0) continue;
-				excl += s & kValueMask;
-				if (flag == kFlagInclusive) break;
-				t--;
-			}
+			excl = lookback_sum(status, (int)tile, 1, 0);
 			st_release(&status[tile], kFlagInclusive | (excl + tile_total));
 		}
 		sm.tile_excl = excl;
 	}
 	__syncthreads();
+	const uint32_t R = (uint32_t)*total;
 	uint32_t run = sm.tile_excl + warp_off + incl - sum;
 #pragma unroll
 	for (int k = 0; k < kSortItems; k++) {
 		uint32_t i = base + k;
-		if (i < n) out[i] = run;
+		if (i < n) {
+			out[i] = run;
+			if (v[k]) {
+				// block boundaries b*kEmitPerBlock (and the last slot R-1) that fall inside [run, run + v[k])
+				const uint32_t lo = run, hi = run + v[k];
+				for (uint32_t b = (lo + kEmitPerBlock - 1) / kEmitPerBlock; (uint64_t)b * kEmitPerBlock < hi; b++)
+					first_src[b] = i;
+				if (hi == R) first_src[(R + kEmitPerBlock - 1) / kEmitPerBlock] = i;
+			}
+		}
 		run += v[k];
 		if (i == n - 1) out[n] = run;
 	}
@@ -352,58 +394,77 @@ __global__ void __launch_bounds__(1024) tile_ranges_kernel(
 // slots, so work is even no matter how many tiles a single (e.g. polar) Gaussian covers, and all
 // stores are fully coalesced.
 constexpr int kEmitThreads = 256;
-constexpr int kEmitPerBlock = 2048;
+constexpr int kEmitPerThread = kEmitPerBlock / kEmitThreads;
 
 __global__ void __launch_bounds__(kEmitThreads) emit_instances_kernel(
 	const uint32_t* __restrict__ emit_offset /*P+1*/, const uint32_t* __restrict__ order /*P*/,
-	const uint2* __restrict__ rect, uint32_t P, uint32_t R, int gx,
+	const uint2* __restrict__ rect, const uint32_t* __restrict__ first_src, uint32_t R, int gx,
 	uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ values)
 {
 	__shared__ uint32_t s_off[kEmitPerBlock + 2];
 	__shared__ uint32_t s_gid[kEmitPerBlock + 1];
 	__shared__ uint2 s_rect[kEmitPerBlock + 1];
+	__shared__ uint32_t s_src[kEmitPerBlock];      // slot -> local source index (after the max-scan)
+	__shared__ uint32_t s_warp_max[kEmitThreads / 32];
 	__shared__ uint32_t s_first, s_last;
 
 	const uint32_t o0 = blockIdx.x * (uint32_t)kEmitPerBlock;
 	if (o0 >= R) return;
 	const uint32_t o1 = min(R, o0 + (uint32_t)kEmitPerBlock);
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-	if (tid < 2) {
-		// largest i with emit_offset[i] <= target (upper_bound - 1) over i in [0, P)
-		uint32_t target = tid == 0 ? o0 : o1 - 1;
-		uint32_t lo = 0, hi = P; // invariant: emit_offset[lo] <= target, answer in [lo, hi)
-		while (hi - lo > 1) {
-			uint32_t mid = (lo + hi) >> 1;
-			if (emit_offset[mid] <= target) lo = mid; else hi = mid;
-		}
-		if (tid == 0) s_first = lo; else s_last = lo;
-	}
+	// sources owning the first and the last slot of this block (table written by gather_scan_kernel)
+	if (tid == 0) s_first = first_src[blockIdx.x];
+	if (tid == 1) s_last = first_src[blockIdx.x + 1];   // owner of slot min(o1, R-1): may start exactly at o1
+#pragma unroll
+	for (int k = 0; k < kEmitPerThread; k++) s_src[tid + k * kEmitThreads] = 0u;
 	__syncthreads();
 	const uint32_t first = s_first, last = s_last;
-	const uint32_t ns = last - first + 1; // <= kEmitPerBlock + 1: every source in range owns >= 1 slot here
+	// every source in [first, last) owns >= 1 slot of this block (zero-count Gaussians sort to the end
+	// of the depth order), so ns <= kEmitPerBlock + 1 and the head marks below never collide
+	const uint32_t ns = last - first + 1;
 	for (uint32_t i = tid; i < ns; i += kEmitThreads) {
-		uint32_t g = order[first + i];
-		s_off[i] = emit_offset[first + i];
+		const uint32_t g = order[first + i];
+		const uint32_t off = emit_offset[first + i];
+		s_off[i] = off;
 		s_gid[i] = g;
 		s_rect[i] = rect[g];
+		if (i > 0 && off < o1) s_src[off - o0] = i;   // head of source i (source 0 starts at or before slot 0)
 	}
-	if (tid == 0) s_off[ns] = 0xFFFFFFFFu;
+	__syncthreads();
+
+	// inclusive max-scan of the head marks: slot -> source index
+	uint32_t v[kEmitPerThread];
+	uint32_t run = 0;
+#pragma unroll
+	for (int k = 0; k < kEmitPerThread; k++) {
+		run = max(run, s_src[tid * kEmitPerThread + k]);
+		v[k] = run;
+	}
+	uint32_t incl = run;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl = max(incl, u);
+	}
+	if (lane == 31) s_warp_max[warp] = incl;
+	const uint32_t prev_lane = __shfl_up_sync(0xffffffffu, incl, 1);
+	__syncthreads();
+	uint32_t carry = (lane > 0) ? prev_lane : 0u;
+	for (int w = 0; w < warp; w++) carry = max(carry, s_warp_max[w]);
+#pragma unroll
+	for (int k = 0; k < kEmitPerThread; k++) s_src[tid * kEmitPerThread + k] = max(v[k], carry);
 	__syncthreads();
 
 	for (uint32_t o = o0 + tid; o < o1; o += kEmitThreads) {
-		uint32_t lo = 0, hi = ns;
-		while (hi - lo > 1) {
-			uint32_t mid = (lo + hi) >> 1;
-			if (s_off[mid] <= o) lo = mid; else hi = mid;
-		}
-		uint2 rc = s_rect[lo];
-		uint32_t x0 = rc.x & 0xFFFFu, x1 = rc.x >> 16, y0 = rc.y & 0xFFFFu;
-		uint32_t w = x1 - x0;
-		uint32_t local = o - s_off[lo];
-		uint32_t y = y0 + local / w, x = x0 + local % w;
-		tile_keys[o] = y * (uint32_t)gx + x;
-		values[o] = s_gid[lo];
+		const uint32_t src = s_src[o - o0];
+		const uint2 rc = s_rect[src];
+		const uint32_t x0 = rc.x & 0xFFFFu, x1 = rc.x >> 16, y0 = rc.y & 0xFFFFu;
+		const uint32_t w = x1 - x0;
+		const uint32_t local = o - s_off[src];
+		const uint32_t q = local / w;
+		tile_keys[o] = (y0 + q) * (uint32_t)gx + x0 + (local - q * w);
+		values[o] = s_gid[src];
 	}
 }
 
@@ -436,21 +497,10 @@ TileSortPlan make_tile_sort_plan(int W, int H)
 	return p;
 }
 
-static cudaError_t ensure_onesweep_smem()
-{
-	static bool done = false;
-	if (done) return cudaSuccess;
-	cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                                     (int)sizeof(OnesweepSmem));
-	if (e == cudaSuccess) done = true;
-	return e;
-}
-
 // Depth ordering of the P Gaussians (stage 1).  Keys: g.sort_key[0]; result order in g.sort_val[0];
 // then emit_offset (P+1) in that order.
 int launch_depth_order(const GeomState& g, int P, cudaStream_t st)
 {
-	OGS_CUDA_TRY(ensure_onesweep_smem());
 	const uint32_t n = (uint32_t)P;
 	const int tiles = ceil_div(P, kSortItemsPerBlock);
 	int hist_blocks = min(ceil_div(P, 256 * 8), kNumSMs * 4);
@@ -462,13 +512,11 @@ int launch_depth_order(const GeomState& g, int P, cudaStream_t st)
 		const uint32_t* vin = p == 0 ? nullptr : g.sort_val[p & 1];
 		uint32_t* kout = g.sort_key[(p + 1) & 1];
 		uint32_t* vout = g.sort_val[(p + 1) & 1];
-		onesweep_pass_kernel<<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(
+		onesweep_pass_kernel<<<tiles, kSortThreads, 0, st>>>(
 			kin, vin, kout, vout, n, 8 * p, 8, g.depth_hist + 256 * p,
 			g.depth_status + (size_t)p * tiles * 256, tickets + p);
 	}
 	// 4 passes: result back in buffer 0
-	gather_scan_kernel<<<tiles, kSortThreads, 0, st>>>(g.tiles_touched, g.sort_val[0], n, g.emit_offset,
-	                                                  g.scan_status, tickets + 4);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }
@@ -487,20 +535,22 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
                               int P, int64_t R, int W, int H, cudaStream_t st)
 {
 	if (R <= 0) return OGS_OK;
-	OGS_CUDA_TRY(ensure_onesweep_smem());
 	const int gx = ceil_div(W, kTile);
 	const TileSortPlan plan = make_tile_sort_plan(W, H);
 	const uint32_t n = (uint32_t)R;
 	prof_begin(OGS_PROF_EMIT, st);
+	unsigned int* scan_ticket = reinterpret_cast<unsigned int*>(g.scalars + 2) + 4;
+	gather_scan_kernel<<<ceil_div(P, kSortItemsPerBlock), kSortThreads, 0, st>>>(
+		g.tiles_touched, g.sort_val[0], (uint32_t)P, g.emit_offset, g.scan_status, scan_ticket, b.first_src, g.scalars);
 	emit_instances_kernel<<<(unsigned)((R + kEmitPerBlock - 1) / kEmitPerBlock), kEmitThreads, 0, st>>>(
-		g.emit_offset, g.sort_val[0], g.rect, (uint32_t)P, n, gx, b.key[0], b.val[0]);
+		g.emit_offset, g.sort_val[0], g.rect, b.first_src, n, gx, b.key[0], b.val[0]);
 	prof_end(OGS_PROF_EMIT, st);
 	prof_begin(OGS_PROF_TILE_SORT, st);
 	const int tiles = (int)((R + kSortItemsPerBlock - 1) / kSortItemsPerBlock);
 	size_t status_off = 0;
 	for (int p = 0; p < plan.passes; p++) {
 		const bool last = (p == plan.passes - 1);
-		onesweep_pass_kernel<<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(
+		onesweep_pass_kernel<<<tiles, kSortThreads, 0, st>>>(
 			b.key[p & 1], b.val[p & 1], last ? nullptr : b.key[(p + 1) & 1], b.val[(p + 1) & 1],
 			n, plan.shift[p], plan.bits[p], img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p);
 		status_off += (size_t)tiles << plan.bits[p];

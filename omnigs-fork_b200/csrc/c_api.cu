@@ -128,6 +128,7 @@ BinningState carve_binning(char* base, int64_t R, int W, int H, size_t* total)
 	b.val[0] = c.take<uint32_t>(r);
 	b.val[1] = c.take<uint32_t>(r);
 	b.point_list = b.val[plan.passes & 1];
+	b.first_src = c.take<uint32_t>(r / 2048 + 3);
 	size_t status_words = 0;
 	const int tiles = sort_tiles(R);
 	for (int p = 0; p < plan.passes; p++) status_words += (size_t)tiles << plan.bits[p];

@@ -102,6 +102,7 @@ struct BinningState {            // per tile instance, R-sized
 	uint32_t* key[2];            // tile id ping-pong
 	uint32_t* val[2];            // Gaussian idx ping-pong
 	uint32_t* point_list;        // alias of val[passes & 1]: the sorted list
+	uint32_t* first_src;         // R/2048 + 2: depth-ordered source owning the first slot of each emit block
 	uint32_t* status;            // look-back status, passes x tiles x bins
 	unsigned int* tickets;       // one dynamic-tile-id counter per pass
 	char* zero_begin;
@@ -146,16 +147,18 @@ OGS_D void red_add(float* addr, float a)
 	asm volatile("red.global.add.f32 [%0], %1;" :: "l"(addr), "f"(a) : "memory");
 }
 
-// acquire / release accesses for decoupled look-back status words
+// Decoupled look-back status words carry flag and value in ONE 32-bit word, so no ordering with any
+// other location is needed: relaxed gpu-scope accesses (L2-coherent, no fence, no L1 invalidate) suffice.
+// (acquire/release here costs a MEMBAR.GPU + CCTL.IVALL per access and serialises the key loads.)
 OGS_D uint32_t ld_acquire(const uint32_t* p)
 {
 	uint32_t v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
 OGS_D void st_release(uint32_t* p, uint32_t v)
 {
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
 } // namespace ogs

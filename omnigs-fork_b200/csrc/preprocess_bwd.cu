@@ -10,22 +10,41 @@
 //   SH backward -> dL/dsh, dL/dmean;  scale/rotation backward -> dL/dscale, dL/drot.
 // Every output element is written, exact zeros for culled Gaussians, so callers may pass
 // uninitialised memory.
+// With M == 16 the SH rows come in and the dL/dsh rows go out through the bulk-copy engine
+// (cp.async.bulk, 192 bytes per Gaussian, 208-byte shared-memory pitch; async_copy.cuh): the thread
+// loads its row with conflict-free 128-bit shared loads, overwrites it in place with the gradient row and
+// hands it back to the copy engine, so neither direction issues 192-byte-strided global accesses.
 #include "lonlat_math.cuh"
 #include "launchers.cuh"
+#include "async_copy.cuh"
 
 namespace ogs {
 
-constexpr int kPreBwdThreads = 256;
+constexpr int kPreBwdThreads = 128;
 
+template <bool kBulkSH>
 __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(const PreprocessBwdArgs a)
 {
 	__shared__ float sV[16];
 	__shared__ float sCam[3];
-	if (threadIdx.x < 16) sV[threadIdx.x] = a.viewmatrix[threadIdx.x];
-	if (threadIdx.x < 3) sCam[threadIdx.x] = a.campos[threadIdx.x];
+	__shared__ __align__(16) float s_sh[kBulkSH ? kPreBwdThreads * kShPitchFloats : 4];
+	__shared__ __align__(8) uint64_t s_bar;
+	const int tid = threadIdx.x;
+	const int idx = blockIdx.x * kPreBwdThreads + tid;
+	if (tid < 16) sV[tid] = a.viewmatrix[tid];
+	if (tid < 3) sCam[tid] = a.campos[tid];
+	if (kBulkSH && tid == 0) {
+		const int rows = min(kPreBwdThreads, a.P - (int)blockIdx.x * kPreBwdThreads);
+		mbar_init(&s_bar, 1);
+		mbar_arrive_expect_tx(&s_bar, (uint32_t)rows * kShRowFloats * 4u);
+	}
 	__syncthreads();
-	const int idx = blockIdx.x * kPreBwdThreads + threadIdx.x;
-	if (idx >= a.P) return;
+	if (kBulkSH && idx < a.P)
+		bulk_load(&s_sh[tid * kShPitchFloats], a.shs + (size_t)idx * kShRowFloats, kShRowFloats * 4u, &s_bar);
+	if (idx >= a.P) {
+		if (kBulkSH) mbar_wait(&s_bar, 0);   // do not retire while the CTA's copies are in flight
+		return;
+	}
 
 	const bool visible = a.radii[idx] > 0;
 
@@ -56,6 +75,7 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 	float3 dscale = { 0.f, 0.f, 0.f };
 	float4 drot = { 0.f, 0.f, 0.f, 0.f };
 	float* dsh_row = a.dL_dsh ? a.dL_dsh + (size_t)idx * a.M * 3 : nullptr;
+	bool sh_waited = false, sh_row_ready = false;
 
 	if (visible) {
 		float V[16];
@@ -88,14 +108,36 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 			dRGB.x *= (cm & 1u) ? 0 : 1;
 			dRGB.y *= (cm & 2u) ? 0 : 1;
 			dRGB.z *= (cm & 4u) ? 0 : 1;
-			const float* shp = a.shs + (size_t)idx * a.M * 3;
-			auto sh = [shp](int k) { return V3{ shp[3 * k], shp[3 * k + 1], shp[3 * k + 2] }; };
-			auto dsh = [dsh_row](int k, V3 v) {
-				dsh_row[3 * k] = v.x; dsh_row[3 * k + 1] = v.y; dsh_row[3 * k + 2] = v.z;
-			};
-			const float3 dm3 = sh_backward(a.D, mean, float3{ sCam[0], sCam[1], sCam[2] }, sh, dRGB, dsh);
+			float3 dm3;
+			if (kBulkSH) {
+				mbar_wait(&s_bar, 0);
+				sh_waited = true;
+				float shr[kShRowFloats], dshr[kShRowFloats];
+				float4* row = reinterpret_cast<float4*>(&s_sh[tid * kShPitchFloats]);
+#pragma unroll
+				for (int k = 0; k < kShRowFloats / 4; k++) {
+					const float4 q = row[k];
+					shr[4 * k] = q.x; shr[4 * k + 1] = q.y; shr[4 * k + 2] = q.z; shr[4 * k + 3] = q.w;
+				}
+#pragma unroll
+				for (int k = 0; k < kShRowFloats; k++) dshr[k] = 0.f;   // rows beyond (D+1)^2 stay zero
+				auto sh = [&shr](int k) { return V3{ shr[3 * k], shr[3 * k + 1], shr[3 * k + 2] }; };
+				auto dsh = [&dshr](int k, V3 v) { dshr[3 * k] = v.x; dshr[3 * k + 1] = v.y; dshr[3 * k + 2] = v.z; };
+				dm3 = sh_backward(a.D, mean, float3{ sCam[0], sCam[1], sCam[2] }, sh, dRGB, dsh);
+#pragma unroll
+				for (int k = 0; k < kShRowFloats / 4; k++)
+					row[k] = make_float4(dshr[4 * k], dshr[4 * k + 1], dshr[4 * k + 2], dshr[4 * k + 3]);
+				sh_row_ready = true;
+			} else {
+				const float* shp = a.shs + (size_t)idx * a.M * 3;
+				auto sh = [shp](int k) { return V3{ shp[3 * k], shp[3 * k + 1], shp[3 * k + 2] }; };
+				auto dsh = [dsh_row](int k, V3 v) {
+					dsh_row[3 * k] = v.x; dsh_row[3 * k + 1] = v.y; dsh_row[3 * k + 2] = v.z;
+				};
+				dm3 = sh_backward(a.D, mean, float3{ sCam[0], sCam[1], sCam[2] }, sh, dRGB, dsh);
+				for (int k = (a.D + 1) * (a.D + 1) * 3; k < a.M * 3; k++) dsh_row[k] = 0.f;
+			}
 			dmean.x += dm3.x; dmean.y += dm3.y; dmean.z += dm3.z;
-			for (int k = (a.D + 1) * (a.D + 1) * 3; k < a.M * 3; k++) dsh_row[k] = 0.f;
 		}
 
 		// scale / rotation backward (backward.cu:489-552)
@@ -104,8 +146,20 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 			const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
 			cov3d_backward(sc, a.scale_modifier, q, dcov6, dscale, drot);
 		}
-	} else if (dsh_row) {
+	} else if (dsh_row && !kBulkSH) {
 		for (int k = 0; k < a.M * 3; k++) dsh_row[k] = 0.f;
+	}
+	if (kBulkSH) {
+		// hand the gradient row (zeros for culled Gaussians) to the copy engine
+		if (!sh_waited) mbar_wait(&s_bar, 0);
+		float4* row = reinterpret_cast<float4*>(&s_sh[tid * kShPitchFloats]);
+		if (!sh_row_ready) {
+#pragma unroll
+			for (int k = 0; k < kShRowFloats / 4; k++) row[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+		fence_async_smem();
+		bulk_store(dsh_row, row, kShRowFloats * 4u);
+		bulk_commit();
 	}
 
 	a.dL_dmean3D[3 * (size_t)idx + 0] = dmean.x;
@@ -117,11 +171,16 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 	a.dL_dscale[3 * (size_t)idx + 1] = dscale.y;
 	a.dL_dscale[3 * (size_t)idx + 2] = dscale.z;
 	reinterpret_cast<float4*>(a.dL_drot)[idx] = drot;
+	if (kBulkSH) bulk_wait_read_all();   // shared memory must outlive the outgoing copy
 }
 
 int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st)
 {
-	preprocess_lonlat_bwd_kernel<<<ceil_div(a.P, kPreBwdThreads), kPreBwdThreads, 0, st>>>(a);
+	const int blocks = ceil_div(a.P, kPreBwdThreads);
+	if (a.shs != nullptr && a.dL_dsh != nullptr && sh_rows_bulk_capable(a.shs, a.M) && sh_rows_bulk_capable(a.dL_dsh, a.M))
+		preprocess_lonlat_bwd_kernel<true><<<blocks, kPreBwdThreads, 0, st>>>(a);
+	else
+		preprocess_lonlat_bwd_kernel<false><<<blocks, kPreBwdThreads, 0, st>>>(a);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }

@@ -9,40 +9,61 @@
 //   * the 2-D tile-coverage difference array (4 atomics per visible Gaussian) from which the tile
 //     ranges and the radix digit histograms are derived without touching the R-sized key list,
 //   * the depth-sort key (float bits of r; 0xFFFFFFFF for Gaussians that emit nothing).
+// The 192-byte SH rows of the CTA are fetched by the bulk-copy engine (cp.async.bulk + mbarrier) while
+// the threads do the projection math; see async_copy.cuh.
 #include "lonlat_math.cuh"
 #include "launchers.cuh"
+#include "async_copy.cuh"
 
 namespace ogs {
 
-constexpr int kPreThreads = 256;
+constexpr int kPreThreads = 128;
 
+template <bool kBulkSH>
 __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(const PreprocessFwdArgs a)
 {
 	__shared__ float sV[16];
 	__shared__ float sCam[3];
 	__shared__ unsigned long long s_block_tiles;
-	if (threadIdx.x < 16) sV[threadIdx.x] = a.viewmatrix[threadIdx.x];
-	if (threadIdx.x < 3) sCam[threadIdx.x] = a.campos[threadIdx.x];
-	if (threadIdx.x == 0) s_block_tiles = 0ull;
-	__syncthreads();
+	__shared__ __align__(16) float s_sh[kBulkSH ? kPreThreads * kShPitchFloats : 4];
+	__shared__ __align__(8) uint64_t s_bar;
 
-	const int idx = blockIdx.x * kPreThreads + threadIdx.x;
+	const int tid = threadIdx.x;
+	const int idx = blockIdx.x * kPreThreads + tid;
+	if (tid < 16) sV[tid] = a.viewmatrix[tid];
+	if (tid < 3) sCam[tid] = a.campos[tid];
+	if (tid == 0) {
+		s_block_tiles = 0ull;
+		if (kBulkSH) {
+			const int rows = min(kPreThreads, a.P - (int)blockIdx.x * kPreThreads);
+			mbar_init(&s_bar, 1);
+			mbar_arrive_expect_tx(&s_bar, (uint32_t)rows * kShRowFloats * 4u);
+		}
+	}
+	__syncthreads();
+	if (kBulkSH && idx < a.P)
+		bulk_load(&s_sh[tid * kShPitchFloats], a.shs + (size_t)idx * kShRowFloats, kShRowFloats * 4u, &s_bar);
+
 	uint32_t my_tiles = 0;
+	int out_radius = 0;
+	uint32_t key = 0xFFFFFFFFu;
+	bool emits = false;           // visible inside this band: needs a colour and a packed record
+	float3 p_orig = { 0.f, 0.f, 0.f }, conic = { 0.f, 0.f, 0.f };
+	float2 point_image = { 0.f, 0.f };
+	float r = 0.f;
+	int x0 = 0, x1 = 0, by0 = 0, by1 = 0;
 
 	if (idx < a.P) {
 		float V[16];
 #pragma unroll
 		for (int i = 0; i < 16; i++) V[i] = sV[i];
 
-		int out_radius = 0;
-		uint32_t key = 0xFFFFFFFFu;
-
 		// near cull (auxiliary.h:198-220): r^2 <= 0.04 drops the Gaussian
-		const float3 p_orig = { a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2] };
+		p_orig = { a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2] };
 		const float3 t = view_point_p(V, p_orig);
 		const float rr = dot3p(t.x, t.x, t.y, t.y, t.z, t.z);
 		if (!(rr <= 0.04f)) {
-			const float r = __fsqrt_rn(rr);
+			r = __fsqrt_rn(rr);
 
 			// lon/lat screen coordinates (auxiliary.h:236-248)
 			const float inv_r = __frcp_rn(__fadd_rn(r, kEps7));
@@ -70,7 +91,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 			const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
 			if (det != 0.0f) {
 				const float det_inv = __frcp_rn(det);
-				const float3 conic = { __fmul_rn(cov.z, det_inv), __fmul_rn(cov.y, -det_inv), __fmul_rn(cov.x, det_inv) };
+				conic = { __fmul_rn(cov.z, det_inv), __fmul_rn(cov.y, -det_inv), __fmul_rn(cov.x, det_inv) };
 
 				// screen-space extent (forward.cu:671-683)
 				const float mid = __fmul_rn(__fadd_rn(cov.x, cov.z), 0.5f);
@@ -78,42 +99,63 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 				const float lambda1 = __fadd_rn(mid, sq);
 				const float lambda2 = __fsub_rn(mid, sq);
 				const float my_radius = ceilf(__fmul_rn(__fsqrt_rn(fmaxf(lambda1, lambda2)), 3.f));
-				const float2 point_image = { ndc_to_pix_p(p_proj.x, a.W), ndc_to_pix_p(p_proj.y, a.H) };
-				int x0, y0, x1, y1;
+				point_image = { ndc_to_pix_p(p_proj.x, a.W), ndc_to_pix_p(p_proj.y, a.H) };
+				int y0, y1;
 				tile_rect_p(point_image, (int)my_radius, a.gx, a.gy, x0, y0, x1, y1);
 				if ((x1 - x0) * (y1 - y0) != 0) {
 					out_radius = (int)my_radius;
 					// latitude-band clip (identity for the full image)
-					const int by0 = max(y0, a.band_y0), by1 = min(y1, a.band_y1);
-					if (by1 > by0) {
-						float3 rgb;
-						unsigned cmask = 0;
-						if (a.colors_precomp == nullptr) {
-							const float* shp = a.shs + (size_t)idx * a.M * 3;
-							auto sh = [shp](int k) { return V3{ shp[3 * k], shp[3 * k + 1], shp[3 * k + 2] }; };
-							const V3 c = sh_to_rgb(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
-							rgb = { c.x, c.y, c.z };
-						} else {
-							rgb = { a.colors_precomp[3 * (size_t)idx], a.colors_precomp[3 * (size_t)idx + 1],
-							        a.colors_precomp[3 * (size_t)idx + 2] };
-						}
-						a.clamped[idx] = (uint8_t)cmask;
-						a.depth[idx] = r;
-						a.g0[idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-						a.g1[idx] = make_float4(conic.z, a.opacities[idx], rgb.x, rgb.y);
-						a.gb[idx] = rgb.z;
-						a.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));
-						my_tiles = (uint32_t)((by1 - by0) * (x1 - x0));
-						key = __float_as_uint(r);
-						const int pitch = a.gx + 1;
-						atomicAdd(&a.tile_diff[by0 * pitch + x0], 1);
-						atomicAdd(&a.tile_diff[by0 * pitch + x1], -1);
-						atomicAdd(&a.tile_diff[by1 * pitch + x0], -1);
-						atomicAdd(&a.tile_diff[by1 * pitch + x1], 1);
-					}
+					by0 = max(y0, a.band_y0);
+					by1 = min(y1, a.band_y1);
+					emits = by1 > by0;
 				}
 			}
 		}
+	}
+
+	// every thread waits for the CTA's SH rows (a CTA must not retire with bulk copies in flight)
+	if (kBulkSH) mbar_wait(&s_bar, 0);
+
+	if (emits) {
+		float3 rgb;
+		unsigned cmask = 0;
+		if (a.colors_precomp == nullptr) {
+			V3 c;
+			if (kBulkSH) {
+				float shr[kShRowFloats];
+				const float4* row = reinterpret_cast<const float4*>(&s_sh[tid * kShPitchFloats]);
+#pragma unroll
+				for (int k = 0; k < kShRowFloats / 4; k++) {
+					const float4 q = row[k];
+					shr[4 * k] = q.x; shr[4 * k + 1] = q.y; shr[4 * k + 2] = q.z; shr[4 * k + 3] = q.w;
+				}
+				auto sh = [&shr](int k) { return V3{ shr[3 * k], shr[3 * k + 1], shr[3 * k + 2] }; };
+				c = sh_to_rgb(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
+			} else {
+				const float* shp = a.shs + (size_t)idx * a.M * 3;
+				auto sh = [shp](int k) { return V3{ shp[3 * k], shp[3 * k + 1], shp[3 * k + 2] }; };
+				c = sh_to_rgb(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
+			}
+			rgb = { c.x, c.y, c.z };
+		} else {
+			rgb = { a.colors_precomp[3 * (size_t)idx], a.colors_precomp[3 * (size_t)idx + 1],
+			        a.colors_precomp[3 * (size_t)idx + 2] };
+		}
+		a.clamped[idx] = (uint8_t)cmask;
+		a.depth[idx] = r;
+		a.g0[idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+		a.g1[idx] = make_float4(conic.z, a.opacities[idx], rgb.x, rgb.y);
+		a.gb[idx] = rgb.z;
+		a.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));
+		my_tiles = (uint32_t)((by1 - by0) * (x1 - x0));
+		key = __float_as_uint(r);
+		const int pitch = a.gx + 1;
+		atomicAdd(&a.tile_diff[by0 * pitch + x0], 1);
+		atomicAdd(&a.tile_diff[by0 * pitch + x1], -1);
+		atomicAdd(&a.tile_diff[by1 * pitch + x0], -1);
+		atomicAdd(&a.tile_diff[by1 * pitch + x1], 1);
+	}
+	if (idx < a.P) {
 		a.radii[idx] = out_radius;
 		a.tiles_touched[idx] = my_tiles;
 		a.sort_key[idx] = key;
@@ -123,9 +165,9 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 	uint32_t wsum = my_tiles;
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-	if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_block_tiles, (unsigned long long)wsum);
+	if ((tid & 31) == 0 && wsum) atomicAdd(&s_block_tiles, (unsigned long long)wsum);
 	__syncthreads();
-	if (threadIdx.x == 0 && s_block_tiles) atomicAdd(a.total_tiles, s_block_tiles);
+	if (tid == 0 && s_block_tiles) atomicAdd(a.total_tiles, s_block_tiles);
 }
 
 __global__ void mark_all_visible_kernel(int P, uint8_t* present)
@@ -136,7 +178,11 @@ __global__ void mark_all_visible_kernel(int P, uint8_t* present)
 
 int launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t st)
 {
-	preprocess_lonlat_fwd_kernel<<<ceil_div(a.P, kPreThreads), kPreThreads, 0, st>>>(a);
+	const int blocks = ceil_div(a.P, kPreThreads);
+	if (a.shs != nullptr && sh_rows_bulk_capable(a.shs, a.M))
+		preprocess_lonlat_fwd_kernel<true><<<blocks, kPreThreads, 0, st>>>(a);
+	else
+		preprocess_lonlat_fwd_kernel<false><<<blocks, kPreThreads, 0, st>>>(a);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }

@@ -61,9 +61,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
 	const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
 	const float* __restrict__ dL_dpixels, float* __restrict__ grad_acc /*[P,12]*/)
 {
-	__shared__ float4 s_a[kBatch];   // mean.x, mean.y, conic.x, conic.y
-	__shared__ float4 s_b[kBatch];   // conic.z, opacity, r, g
-	__shared__ float4 s_c[kBatch];   // b, list position (0-based, bits), tau_safe, Gaussian id (bits)
+	__shared__ StagedEntry s_e[kBatch];
 	__shared__ float s_acc[kBatch * kAccStride];
 	__shared__ uint32_t s_warp_cnt[kRenderThreads / 32];
 	__shared__ int s_max_contrib;
@@ -104,6 +102,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
 	float bg_dot_dpixel = 0.f;
 #pragma unroll
 	for (int ch = 0; ch < 3; ch++) bg_dot_dpixel += bg_color[ch] * dL_dpixel[ch];
+	const float neg_Tfinal_bg = -T_final * bg_dot_dpixel;   // (-T_final / (1 - alpha)) * bg_dot = this * 1/(1 - alpha)
 
 	// entries at list positions >= max(n_contrib) of the tile were blended by no pixel
 	if (threadIdx.x == 0) s_max_contrib = 0;
@@ -131,9 +130,9 @@ __global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
 		int total;
 		const int slot = block_compact_slot(keep, s_warp_cnt, total); // contains a __syncthreads
 		if (keep) {
-			s_a[slot] = a;
-			s_b[slot] = b;
-			s_c[slot] = make_float4(cb, __int_as_float(i), tau, __uint_as_float(id));
+			s_e[slot].a = a;
+			s_e[slot].b = make_float4(b.x, tau, b.y, __int_as_float(i));   // 0-based list position
+			s_e[slot].c = make_float4(b.z, b.w, cb, __uint_as_float(id));
 		}
 		for (int k = threadIdx.x; k < total * kAccStride; k += kRenderThreads) s_acc[k] = 0.f;
 		__syncthreads();
@@ -143,27 +142,26 @@ __global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
 			const int s = base + lane;
 			bool hit = false;
 			if (s < total) {
-				const float4 ea = s_a[s];
-				const float4 eb = s_b[s];
-				hit = gaussian_touches_box(ea.x, ea.y, ea.z, ea.w, eb.x, s_c[s].z, sx0, sy0, sx1, sy1);
+				const float4 ea = s_e[s].a;
+				const float4 eb = s_e[s].b;
+				hit = gaussian_touches_box(ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, sx0, sy0, sx1, sy1);
 			}
 			unsigned m = __ballot_sync(0xffffffffu, hit);
 			while (m) {
 				const int j = base + __ffs(m) - 1;
 				m &= m - 1;
-				const float4 ea = s_a[j];
-				const float4 eb = s_b[j];
-				const float4 ec = s_c[j];
+				const StagedEntry* e = &s_e[j];
+				const float4 ea = e->a;
+				const float4 eb = e->b;
 
-				// backward.cu:766-782: same guards as the forward
-				const float4 con_o = { ea.z, ea.w, eb.x, eb.y };
+				// backward.cu:766-782: same guards (and the same pinned arithmetic) as the forward
 				float2 d;
-				const float power = pair_power(ea.x, ea.y, con_o.x, con_o.y, con_o.z, pixf, d.x, d.y);
-				bool valid = inside && (__float_as_int(ec.y) < last_contributor) && !(power > 0.0f) && !(power < ec.z);
+				const float power = pair_power(ea.x, ea.y, ea.z, ea.w, eb.x, pixf, d.x, d.y);
+				bool valid = inside && (__float_as_int(eb.w) < last_contributor) && !(power > 0.0f) && !(power < eb.y);
 				float G = 0.f, alpha = 0.f;
 				if (valid) {
 					G = expf(power);
-					alpha = fminf(0.99f, __fmul_rn(con_o.w, G));
+					alpha = fminf(0.99f, __fmul_rn(eb.z, G));
 					valid = !(alpha < kAlphaMin);
 				}
 				if (!__any_sync(0xffffffffu, valid)) continue;
@@ -171,31 +169,34 @@ __global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
 				float v[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
 				float v8 = 0.f;
 				if (valid) {
-					// backward.cu:784-840
-					T = T / (1.f - alpha);
+					// backward.cu:784-840.  One correctly rounded reciprocal replaces the reference's two
+					// divisions by (1 - alpha): T/(1-a) and -T_final/(1-a) (difference <= 1 ulp, inside the
+					// 1e-4 gradient tolerance).
+					const float4 ec = e->c;
+					const float inv = __frcp_rn(1.f - alpha);
+					T = T * inv;
 					const float dchannel_dcolor = alpha * T;
 					float dL_dalpha = 0.0f;
-					const float col[3] = { eb.z, eb.w, ec.x };
+					const float col[3] = { ec.x, ec.y, ec.z };
 #pragma unroll
 					for (int ch = 0; ch < 3; ch++) {
 						const float c = col[ch];
 						accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
 						last_color[ch] = c;
-						const float dL_dchannel = dL_dpixel[ch];
-						dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
+						dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
 					}
 					v[6] = dchannel_dcolor * dL_dpixel[0];
 					v[7] = dchannel_dcolor * dL_dpixel[1];
 					v8 = dchannel_dcolor * dL_dpixel[2];
 					dL_dalpha *= T;
 					last_alpha = alpha;
-					dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+					dL_dalpha += neg_Tfinal_bg * inv;
 
-					const float dL_dG = con_o.w * dL_dalpha;
+					const float dL_dG = eb.z * dL_dalpha;
 					const float gdx = G * d.x;
 					const float gdy = G * d.y;
-					const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-					const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+					const float dG_ddelx = -gdx * ea.z - gdy * ea.w;
+					const float dG_ddely = -gdy * eb.x - gdx * ea.w;
 					v[0] = dL_dG * dG_ddelx * ddelx_dx;
 					v[1] = dL_dG * dG_ddely * ddely_dy;
 					v[2] = -0.5f * gdx * d.x * dL_dG;
@@ -205,8 +206,10 @@ __global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
 				}
 				float z, z8;
 				warp_transpose_reduce9(v, v8, z, z8);
-				if ((lane & 3) == 0) atomicAdd(&s_acc[j * kAccStride + (lane >> 2)], z);
-				if (lane == 1) atomicAdd(&s_acc[j * kAccStride + 8], z8);
+				// lanes 0,4,..,28 hold sums 0..7, lane 1 takes the ninth: one shared-memory atomic pass
+				const bool ninth = (lane == 1);
+				if ((lane & 3) == 0 || ninth)
+					atomicAdd(&s_acc[j * kAccStride + (ninth ? 8 : (lane >> 2))], ninth ? z8 : z);
 			}
 		}
 		__syncthreads();
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
 				nz |= (r[k] != 0.f);
 			}
 			if (nz) {
-				float* dst = grad_acc + (size_t)__float_as_uint(s_c[threadIdx.x].w) * 12;
+				float* dst = grad_acc + (size_t)__float_as_uint(s_e[threadIdx.x].c.w) * 12;
 				red_add_v4(dst, r[0], r[1], r[2], r[3]);
 				red_add_v4(dst + 4, r[4], r[5], r[6], r[7]);
 				red_add(dst + 8, r[8]);

@@ -70,6 +70,14 @@ OGS_D float pair_power(float mx, float my, float A, float B, float C, float2 pix
 	return __fmaf_rn(q, -0.5f, -__fmul_rn(__fmul_rn(B, dx), dy));
 }
 
+// One staged list entry in shared memory (48 bytes, a single base address per inner-loop iteration):
+//   a = (mean.x, mean.y, conic.x, conic.y)
+//   b = (conic.z, tau_safe, opacity, list position as bits)
+//   c = (colour.r, colour.g, colour.b, Gaussian id as bits)
+struct __align__(16) StagedEntry {
+	float4 a, b, c;
+};
+
 // Stable block-wide compaction slot for `keep` flags (list order must be preserved: blending is
 // order dependent).  Returns this thread's slot (valid when keep) and the block total.
 // Uses one __syncthreads; s_warp_cnt must hold kRenderThreads/32 words.

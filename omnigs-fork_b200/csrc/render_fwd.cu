@@ -23,9 +23,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 	const float* __restrict__ bg_color,
 	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)
 {
-	__shared__ float4 s_a[kBatch];   // mean.x, mean.y, conic.x, conic.y
-	__shared__ float4 s_b[kBatch];   // conic.z, opacity, r, g
-	__shared__ float4 s_c[kBatch];   // b, list position (1-based, as bits), tau_safe, unused
+	__shared__ StagedEntry s_e[kBatch];
 	__shared__ uint32_t s_warp_cnt[kRenderThreads / 32];
 
 	const int tile = blockIdx.x;
@@ -72,9 +70,9 @@ __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 		int total;
 		const int slot = block_compact_slot(keep, s_warp_cnt, total);
 		if (keep) {
-			s_a[slot] = a;
-			s_b[slot] = b;
-			s_c[slot] = make_float4(cb, __uint_as_float((uint32_t)(i + 1)), tau, 0.f);
+			s_e[slot].a = a;
+			s_e[slot].b = make_float4(b.x, tau, b.y, __uint_as_float((uint32_t)(i + 1))); // 1-based list position
+			s_e[slot].c = make_float4(b.z, b.w, cb, 0.f);
 		}
 		__syncthreads();
 
@@ -83,36 +81,36 @@ __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 			const int s = base + lane;
 			bool hit = false;
 			if (s < total) {
-				const float4 ea = s_a[s];
-				const float4 eb = s_b[s];
-				hit = gaussian_touches_box(ea.x, ea.y, ea.z, ea.w, eb.x, s_c[s].z, sx0, sy0, sx1, sy1);
+				const float4 ea = s_e[s].a;
+				const float4 eb = s_e[s].b;
+				hit = gaussian_touches_box(ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, sx0, sy0, sx1, sy1);
 			}
 			unsigned m = __ballot_sync(0xffffffffu, hit);
 			if (__all_sync(0xffffffffu, done)) break;
 			while (m) {
-				const int j = base + __ffs(m) - 1;
+				const StagedEntry* e = &s_e[base + __ffs(m) - 1];
 				m &= m - 1;
 				if (done) continue;
-				const float4 ea = s_a[j];
-				const float4 eb = s_b[j];
-				const float4 ec = s_c[j];
+				const float4 ea = e->a;
+				const float4 eb = e->b;
 				// forward.cu:424-455, arithmetic pinned to the reference's compiled order
 				float dx, dy;
 				const float power = pair_power(ea.x, ea.y, ea.z, ea.w, eb.x, pixf, dx, dy);
 				if (power > 0.0f) continue;
-				if (power < ec.z) continue; // alpha would be < 1/255 (skips expf)
-				const float alpha = fminf(0.99f, __fmul_rn(eb.y, expf(power)));
+				if (power < eb.y) continue; // alpha would be < 1/255 (skips expf)
+				const float alpha = fminf(0.99f, __fmul_rn(eb.z, expf(power)));
 				if (alpha < kAlphaMin) continue;
 				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
 				if (test_T < 0.0001f) {
 					done = true;
 					continue;
 				}
-				C[0] = __fmaf_rn(T, __fmul_rn(alpha, eb.z), C[0]);
-				C[1] = __fmaf_rn(T, __fmul_rn(alpha, eb.w), C[1]);
-				C[2] = __fmaf_rn(T, __fmul_rn(alpha, ec.x), C[2]);
+				const float4 ec = e->c;
+				C[0] = __fmaf_rn(T, __fmul_rn(alpha, ec.x), C[0]);
+				C[1] = __fmaf_rn(T, __fmul_rn(alpha, ec.y), C[1]);
+				C[2] = __fmaf_rn(T, __fmul_rn(alpha, ec.z), C[2]);
 				T = test_T;
-				last_contributor = __float_as_uint(ec.y);
+				last_contributor = __float_as_uint(eb.w);
 			}
 		}
 	}

@@ -16,6 +16,7 @@ from ._lib import load_library, check
 PINHOLE = 1
 LONLAT = 3
 NUM_CHANNELS = 3  # reference cuda_rasterizer/config.h:25
+_BINNING_GRANULE = 64 << 20
 
 
 def _ptr(t):
@@ -89,7 +90,10 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
                 _ptr(viewmatrix), _ptr(campos),
                 _ptr(radii), _ptr(geomBuffer), _ptr(imgBuffer), ctypes.byref(n), st))
             rendered = int(n.value)
-            binningBuffer = torch.empty((lib.ogs_binning_bytes(rendered, W, H),), **byte_opts)
+            # num_rendered changes from view to view: round the request to a 64 MiB size class so the
+            # caching allocator can hand back last frame's block instead of calling cudaMalloc
+            need = lib.ogs_binning_bytes(rendered, W, H)
+            binningBuffer = torch.empty((-(-need // _BINNING_GRANULE) * _BINNING_GRANULE,), **byte_opts)
             check(lib.ogs_lonlat_forward_stage2(
                 P, W, H, rendered, _ptr(background),
                 _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), _ptr(out_color), st))
