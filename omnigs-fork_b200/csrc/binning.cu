@@ -23,7 +23,7 @@
 namespace ogs {
 
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = kSortItemsPerBlock / kSortThreads;   // 16 keys per thread
+constexpr int kSortItems = kSortItemsPerBlock / kSortThreads;   // 8 keys per thread
 constexpr uint32_t kFlagPartial = 1u << 30;
 constexpr uint32_t kFlagInclusive = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1;
@@ -82,9 +82,9 @@ __global__ void __launch_bounds__(256) depth_histogram_kernel(const uint32_t* __
 // look-back over the predecessors' status words; digit totals come from `digit_counts`.
 // vals_in == nullptr means value i = i (first depth pass); keys_out == nullptr skips the key
 // write (last tile pass).  Sized for occupancy: 256 threads x 8 keys, values are only loaded when
-// they are staged.  Throughput of a chained scan is bounded by (look-back batch x tile size) / L2
-// latency, and the look-back window grows with the number of CTAs in flight, hence 4096-key tiles,
-// 16 status words per round trip and 3 CTAs per SM.
+// in flight while the keys are ranked.  Ranking uses one ballot per digit bit (peers = AND of the
+// matching ballots): MATCH.ANY costs ~46 cycles per SM per warp-instruction on B200 and dominated the
+// first version of this kernel (ncu stall sampling, profiles/), 7-9 VOTEs are several times cheaper.
 struct OnesweepSmem {
 	uint32_t warp_hist[kSortThreads / 32][kMaxBins]; // per-warp digit counters -> warp offsets
 	uint32_t bin_start[kMaxBins];                    // exclusive prefix of the tile's digit totals
@@ -96,7 +96,7 @@ struct OnesweepSmem {
 	uint32_t tile;
 };
 
-constexpr int kLookbackBatch = 16;
+constexpr int kLookbackBatch = 8;
 
 // Decoupled look-back for one counter: sum the predecessors' published values back to the nearest
 // inclusive one.  Status words of kLookbackBatch predecessors are fetched together, so the walk
@@ -131,13 +131,14 @@ OGS_D uint32_t lookback_sum(const uint32_t* __restrict__ status, int tile, size_
 	return excl;
 }
 
-__global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
+__global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
 	uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
 	uint32_t n, int shift, int bits,
 	const uint32_t* __restrict__ digit_counts, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket)
 {
-	__shared__ OnesweepSmem sm;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nbins = 1 << bits;
 	const uint32_t mask = (uint32_t)nbins - 1u;
@@ -174,13 +175,25 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
 	__syncthreads();
 	for (int b = tid; b < nbins; b += kSortThreads)
 		st_release(&status[(size_t)tile * nbins + b], (tile == 0 ? kFlagInclusive : kFlagPartial) | sm.tile_hist[b]);
+	// values travel with the keys: issue their loads now, they are consumed after the look-back
+	uint32_t val[kSortItems];
 #pragma unroll
 	for (int k = 0; k < kSortItems; k++) {
 		uint32_t idx = warp_base + k * 32 + lane;
-		bool valid = idx < n;
-		uint32_t d = valid ? ((key[k] >> shift) & mask) : 0xFFFFFFFFu;
-		unsigned peers = __match_any_sync(0xffffffffu, d);
-		int rank_in = __popc(peers & lanemask_lt());
+		val[k] = (idx < n) ? (vals_in ? vals_in[idx] : idx) : 0u;
+	}
+#pragma unroll
+	for (int k = 0; k < kSortItems; k++) {
+		const uint32_t idx = warp_base + k * 32 + lane;
+		const bool valid = idx < n;
+		const uint32_t d = (key[k] >> shift) & mask;
+		unsigned peers = __ballot_sync(0xffffffffu, valid);
+		for (int bit = 0; bit < bits; bit++) {
+			const bool one = (d >> bit) & 1u;
+			const unsigned b = __ballot_sync(0xffffffffu, one);
+			peers &= one ? b : ~b;
+		}
+		const int rank_in = __popc(peers & lanemask_lt());
 		uint32_t prev = 0;
 		if (valid && rank_in == 0) {
 			prev = sm.warp_hist[warp][d];
@@ -217,7 +230,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
 	block_exclusive_scan_512(sm.bin_start, nbins, sm.warp_tmp); // totals -> tile-local starts
 	for (int b = tid; b < nbins; b += kSortThreads) sm.global_base[b] -= sm.bin_start[b];
 
-	// ---- stage into digit order (values are fetched only now), then coalesced scatter ----
+	// ---- stage into digit order, then coalesced scatter ----
 #pragma unroll
 	for (int k = 0; k < kSortItems; k++) {
 		uint32_t idx = warp_base + k * 32 + lane;
@@ -225,7 +238,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) onesweep_pass_kernel(
 			uint32_t d = (key[k] >> shift) & mask;
 			uint32_t pos = sm.bin_start[d] + sm.warp_hist[warp][d] + rank[k];
 			sm.keys[pos] = key[k];
-			sm.vals[pos] = vals_in ? vals_in[idx] : idx;
+			sm.vals[pos] = val[k];
 		}
 	}
 	__syncthreads();
@@ -497,10 +510,18 @@ TileSortPlan make_tile_sort_plan(int W, int H)
 	return p;
 }
 
+static cudaError_t ensure_onesweep_smem()
+{
+	// per device/context attribute, cheap host call: set on every use (several devices per process)
+	return cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                            (int)sizeof(OnesweepSmem));
+}
+
 // Depth ordering of the P Gaussians (stage 1).  Keys: g.sort_key[0]; result order in g.sort_val[0];
 // then emit_offset (P+1) in that order.
 int launch_depth_order(const GeomState& g, int P, cudaStream_t st)
 {
+	OGS_CUDA_TRY(ensure_onesweep_smem());
 	const uint32_t n = (uint32_t)P;
 	const int tiles = ceil_div(P, kSortItemsPerBlock);
 	int hist_blocks = min(ceil_div(P, 256 * 8), kNumSMs * 4);
@@ -512,7 +533,7 @@ int launch_depth_order(const GeomState& g, int P, cudaStream_t st)
 		const uint32_t* vin = p == 0 ? nullptr : g.sort_val[p & 1];
 		uint32_t* kout = g.sort_key[(p + 1) & 1];
 		uint32_t* vout = g.sort_val[(p + 1) & 1];
-		onesweep_pass_kernel<<<tiles, kSortThreads, 0, st>>>(
+		onesweep_pass_kernel<<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(
 			kin, vin, kout, vout, n, 8 * p, 8, g.depth_hist + 256 * p,
 			g.depth_status + (size_t)p * tiles * 256, tickets + p);
 	}
@@ -535,6 +556,7 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
                               int P, int64_t R, int W, int H, cudaStream_t st)
 {
 	if (R <= 0) return OGS_OK;
+	OGS_CUDA_TRY(ensure_onesweep_smem());
 	const int gx = ceil_div(W, kTile);
 	const TileSortPlan plan = make_tile_sort_plan(W, H);
 	const uint32_t n = (uint32_t)R;
@@ -550,7 +572,7 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 	size_t status_off = 0;
 	for (int p = 0; p < plan.passes; p++) {
 		const bool last = (p == plan.passes - 1);
-		onesweep_pass_kernel<<<tiles, kSortThreads, 0, st>>>(
+		onesweep_pass_kernel<<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(
 			b.key[p & 1], b.val[p & 1], last ? nullptr : b.key[(p + 1) & 1], b.val[(p + 1) & 1],
 			n, plan.shift[p], plan.bits[p], img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p);
 		status_off += (size_t)tiles << plan.bits[p];

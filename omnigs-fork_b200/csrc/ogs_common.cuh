@@ -86,7 +86,7 @@ struct ImageState {              // per pixel / per tile
 	static ImageState carve(char* base, int W, int H);
 };
 
-constexpr int kSortItemsPerBlock = 4096; // onesweep tile size (256 threads x 16 keys)
+constexpr int kSortItemsPerBlock = 2048; // onesweep tile size (256 threads x 8 keys)
 constexpr int kMaxBins = 512;            // <= 9-bit digits
 constexpr int kMaxTilePasses = 4;
 
