@@ -45,6 +45,38 @@ def allreduce_gradients(grads, radii=None, group=None):
     return grads, stats
 
 
+def tile_row_counts(ranges, W, H):
+    """Instances per tile row from a frame's `ranges` [T,2] (e.g. of the previous frame of a sequence)."""
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    lens = (ranges[:, 1] - ranges[:, 0]).to(torch.int64).view(gy, gx)
+    return lens.sum(dim=1).tolist()
+
+
+def render_band_forward(rasterize, band, H, group=None):
+    """Latitude-band forward for this rank.  `rasterize(band)` must call RasterizeGaussiansCUDA(...,
+    band=band) and return its 6-tuple.  Pixel rows outside the band are zeroed and the per-rank images
+    are summed, so every rank ends with the full frame (the loss of the trainer needs it whole; a band-
+    wise loss would only need an 11x11-SSIM halo of 5 rows).  Returns (image, forward_tuple)."""
+    fwd = rasterize(band)
+    img = fwd[1]
+    y0, y1 = min(H, band[0] * 16), min(H, band[1] * 16)
+    full = torch.zeros_like(img)
+    full[:, y0:y1] = img[:, y0:y1]
+    if is_distributed():
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+    return full, fwd
+
+
+def reduce_band_gradients(grads, group=None):
+    """Sum every rank's band share of the backward 8-tuple (all of them are per-band partial sums,
+    including dL_dmeans2D / dL_dcolors that the data-parallel path keeps local)."""
+    if is_distributed():
+        work = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in grads if g.numel()]
+        for w in work:
+            w.wait()
+    return grads
+
+
 def views_for_rank(num_views, rank, world):
     """Round-robin assignment of a step's views: rank g renders views g, g+G, ..."""
     return list(range(rank, num_views, world))

@@ -46,13 +46,18 @@ def _require_cuda(t, name):
 def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                            cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                            image_height, image_width, sh, degree, campos, prefiltered,
-                           camera_type=PINHOLE, render_depth=False):
+                           camera_type=PINHOLE, render_depth=False, band=None):
     """reference src/rasterize_points.cu:49-164.
 
     Returns (num_rendered, out_color[3,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer);
     the three uint8 buffers are opaque and only meaningful to RasterizeGaussiansBackwardCUDA.
     projmatrix, tan_fovx, tan_fovy, prefiltered and render_depth are ignored in lonlat mode, as in
     the reference.
+
+    ``band=(ty0, ty1)`` (extension) restricts binning and blending to tile rows
+    [ty0, ty1): pixels outside the band come back as background, ``radii`` stay the full-frame radii, and
+    the returned buffers feed RasterizeGaussiansBackwardCUDA unchanged (it then yields this band's
+    share of every gradient; shares of disjoint bands add up to the full-frame gradient).
     """
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -83,12 +88,14 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
             imgBuffer = torch.empty((lib.ogs_img_bytes(W, H),), **byte_opts)
             n = ctypes.c_int64(0)
             st = _stream(device)
-            check(lib.ogs_lonlat_forward_stage1(
-                P, int(degree), M, W, H,
-                _ptr(means3D_c), _ptr(sh), _ptr(colors), _ptr(opacity),
-                _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
-                _ptr(viewmatrix), _ptr(campos),
-                _ptr(radii), _ptr(geomBuffer), _ptr(imgBuffer), ctypes.byref(n), st))
+            common = (_ptr(means3D_c), _ptr(sh), _ptr(colors), _ptr(opacity),
+                      _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                      _ptr(viewmatrix), _ptr(campos),
+                      _ptr(radii), _ptr(geomBuffer), _ptr(imgBuffer), ctypes.byref(n), st)
+            if band is None:
+                check(lib.ogs_lonlat_forward_stage1(P, int(degree), M, W, H, *common))
+            else:
+                check(lib.ogs_lonlat_forward_stage1_band(P, int(degree), M, W, H, int(band[0]), int(band[1]), *common))
             rendered = int(n.value)
             # num_rendered changes from view to view: round the request to a 64 MiB size class so the
             # caching allocator can hand back last frame's block instead of calling cudaMalloc

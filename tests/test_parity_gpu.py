@@ -385,3 +385,39 @@ def test_cpp_dropin_matches_python_mirror_bit_for_bit():
     with pytest.raises(RuntimeError, match="means3D must have dimensions"):
         bad = list(args); bad[1] = torch.zeros(5, 2, device="cuda")
         shim.RasterizeGaussiansCUDA(*bad, 3, False)
+
+
+def test_band_gradients_sum_to_full_frame_gradients():
+    """SURVEY 8(e-b): render + backward per latitude band (what each GPU of a band-parallel job does);
+    the bands' images tile the full image bit for bit and their gradient shares add up to the full-frame
+    gradients.  Bands are balanced with parallel.band_rows on the per-row instance counts."""
+    import importlib
+    par = importlib.import_module("omnigs-fork_b200.parallel")
+    scene = sm.make_scene(60000, 1024, 512, 0.02, 15, pole_frac=0.15, seam_frac=0.05)
+    d = h.torch_inputs(scene, sm.random_view(16), bg=(0.1, 0.2, 0.3))
+    dL = torch.from_numpy(sm.make_grad_image(scene.W, scene.H, 17)).cuda()
+    full = h.run_forward(h.pkg, d)
+    g_full = h.run_backward(h.pkg, d, full, dL)
+    rows = par.tile_row_counts(h.ours_state(d, full)["ranges"], scene.W, scene.H)
+    for world in (2, 4):
+        bands = par.band_rows(rows, world)
+        assert bands[0][0] == 0 and bands[-1][1] == len(rows)
+        loads = [sum(rows[a:b]) for a, b in bands]
+        assert max(loads) < 1.35 * sum(loads) / world
+        img = torch.zeros_like(full[1])
+        acc = None
+        for band in bands:
+            def rasterize(b):
+                return h.pkg.RasterizeGaussiansCUDA(
+                    d["background"], d["means3D"], d["colors"], d["opacity"], d["scales"], d["rotations"], 1.0,
+                    d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], 0.0, 0.0, d["H"], d["W"], d["sh"], 3,
+                    d["campos"], False, 3, False, band=b)
+            part, fwd = par.render_band_forward(rasterize, band, scene.H)   # single process: no all-reduce
+            img += part
+            assert torch.equal(fwd[2], full[2])
+            g = h.run_backward(h.pkg, d, fwd, dL)
+            acc = [x.clone() for x in g] if acc is None else [a + x for a, x in zip(acc, g)]
+        assert torch.equal(bits(img), bits(full[1]))
+        for n, a, b in zip(h.GRAD_NAMES, acc, g_full):
+            scale = float(b.abs().max()) + 1e-30
+            assert float((a - b).abs().max()) / scale < (3e-4 if n in ILL_CONDITIONED else 2e-5), n
