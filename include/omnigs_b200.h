@@ -114,6 +114,25 @@ OGS_API int ogs_lonlat_backward(
 	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
 	void* stream);
 
+/*
+ * The two halves of ogs_lonlat_backward, for callers that exchange data between them (latitude bands,
+ * SURVEY.md §8(e-b)): ..._render zero-fills the packed accumulators ([P,12] float at byte
+ * ogs_grad_acc_offset(P) of the 256-byte-aligned geometry buffer: dL_dmean2D.xy, dL_dconic.x.y.w,
+ * dL_dopacity, dL_dcolour.rgb, 3 pad) and replays the blend of this rank's tiles into them
+ * (backward.cu:672-843); the caller may sum them over ranks (48 B/Gaussian instead of 324);
+ * ..._finish runs the fused per-Gaussian backward (backward.cu:297-485, :613-669) from them.
+ */
+OGS_API int ogs_lonlat_backward_render(
+	int P, int64_t num_rendered, int W, int H, const float* background,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, const float* dL_dpix, void* stream);
+OGS_API int ogs_lonlat_backward_finish(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* campos, const int* radii, char* geom_buffer,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream);
+OGS_API size_t ogs_grad_acc_offset(int P);
+
 /* markAllVisible (rasterizer_impl.cu:82-90): present[i] = true for i < P (1 byte per flag). */
 OGS_API int ogs_mark_all_visible(int P, uint8_t* present, void* stream);
 

@@ -31,6 +31,9 @@ SYMBOLS = {
     "ogs_lonlat_forward_stage1_band": (_c_int, [_c_int] * 7 + [_p] * 5 + [_c_f] + [_p] * 4 + [_p] * 3 + [ctypes.POINTER(_c_i64), _p]),
     "ogs_lonlat_forward_stage2": (_c_int, [_c_int] * 3 + [_c_i64] + [_p] * 6),
     "ogs_lonlat_backward": (_c_int, [_c_int] * 3 + [_c_i64, _c_int, _c_int] + [_p] * 5 + [_c_f] + [_p] * 5 + [_p] * 3 + [_p] + [_p] * 9 + [_p]),
+    "ogs_lonlat_backward_render": (_c_int, [_c_int, _c_i64, _c_int, _c_int] + [_p] * 5 + [_p]),
+    "ogs_lonlat_backward_finish": (_c_int, [_c_int] * 5 + [_p] * 3 + [_c_f] + [_p] * 6 + [_p] * 9 + [_p]),
+    "ogs_grad_acc_offset": (_c_sz, [_c_int]),
     "ogs_mark_all_visible": (_c_int, [_c_int, _p, _p]),
     "ogs_export_geometry": (_c_int, [_c_int, _p] + [_p] * 7 + [_p]),
     "ogs_export_binning": (_c_int, [_c_int] * 3 + [_c_i64] + [_p] * 3 + [_p] * 5 + [_p]),

@@ -371,42 +371,48 @@ OGS_API int ogs_lonlat_forward_stage2(
 	return rc;
 }
 
-OGS_API int ogs_lonlat_backward(
-	int P, int D, int M, int64_t num_rendered, int W, int H,
-	const float* background,
-	const float* means3D, const float* shs, const float* colors_precomp,
-	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
-	const float* viewmatrix, const float* campos, const int* radii,
-	char* geom_buffer, char* binning_buffer, char* img_buffer,
-	const float* dL_dpix,
-	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
-	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
-	void* stream)
+// Backward, part 1: zero the packed accumulators and replay the blend (render backward).
+OGS_API int ogs_lonlat_backward_render(
+	int P, int64_t num_rendered, int W, int H, const float* background,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, const float* dL_dpix, void* stream)
 {
 	cudaStream_t st = (cudaStream_t)stream;
-	(void)colors_precomp;
 	if (P < 0 || num_rendered < 0) return fail(OGS_ERR_INVALID_ARG, "bad P / num_rendered");
 	if (P == 0) return OGS_OK;
 	if (int rc = check_image(W, H)) return rc;
-	if (!background || !means3D || !viewmatrix || !campos || !radii || !geom_buffer || !img_buffer || !dL_dpix ||
-	    !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot)
-		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
-	if (shs && M > 0 && !dL_dsh) return fail(OGS_ERR_INVALID_ARG, "dL_dsh is NULL");
+	if (!background || !geom_buffer || !img_buffer || !dL_dpix) return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
 	if (num_rendered > 0 && !binning_buffer) return fail(OGS_ERR_INVALID_ARG, "binning_buffer is NULL");
-	if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
-		return fail(OGS_ERR_INVALID_ARG, "exactly one of (scales, rotations) / cov3D_precomp must be given");
-
 	GeomState g = GeomState::carve(geom_buffer, P);
 	ImageState img = ImageState::carve(img_buffer, W, H);
 	BinningState b{};
 	if (num_rendered > 0) b = BinningState::carve(binning_buffer, num_rendered, W, H);
-
 	OGS_CUDA_TRY(cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * (size_t)P, st));
 	prof_begin(OGS_PROF_RENDER_BWD, st);
 	if (int rc = launch_render_bwd(img.ranges, b.point_list, W, H, background, g.g0, g.g1, g.gb,
 	                               img.final_T, img.n_contrib, dL_dpix, g.grad_acc, st)) return rc;
 	prof_end(OGS_PROF_RENDER_BWD, st);
+	return OGS_OK;
+}
 
+// Backward, part 2: the fused per-Gaussian backward from the (possibly all-reduced) accumulators.
+OGS_API int ogs_lonlat_backward_finish(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* campos, const int* radii, char* geom_buffer,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (P < 0) return fail(OGS_ERR_INVALID_ARG, "bad P");
+	if (P == 0) return OGS_OK;
+	if (int rc = check_image(W, H)) return rc;
+	if (!means3D || !viewmatrix || !campos || !radii || !geom_buffer ||
+	    !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot)
+		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	if (shs && M > 0 && !dL_dsh) return fail(OGS_ERR_INVALID_ARG, "dL_dsh is NULL");
+	if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+		return fail(OGS_ERR_INVALID_ARG, "exactly one of (scales, rotations) / cov3D_precomp must be given");
+	GeomState g = GeomState::carve(geom_buffer, P);
 	PreprocessBwdArgs a{};
 	a.P = P; a.D = D; a.M = shs ? M : 0; a.W = W; a.H = H; a.scale_modifier = scale_modifier;
 	a.means3D = means3D; a.shs = shs; a.scales = scales; a.rotations = rotations;
@@ -419,6 +425,35 @@ OGS_API int ogs_lonlat_backward(
 	const int rc = launch_preprocess_bwd(a, st);
 	prof_end(OGS_PROF_PREPROCESS_BWD, st);
 	return rc;
+}
+
+// Byte offset of the packed render-backward accumulators ([P,12] float: dL_dmean2D.xy, dL_dconic.x.y.w,
+// dL_dopacity, dL_dcolour.rgb, 3 pad) inside a 256-byte aligned geometry buffer.
+OGS_API size_t ogs_grad_acc_offset(int P)
+{
+	if (P <= 0) return 0;
+	GeomState g = carve_geom(nullptr, P, nullptr);
+	return (size_t)reinterpret_cast<char*>(g.grad_acc);
+}
+
+OGS_API int ogs_lonlat_backward(
+	int P, int D, int M, int64_t num_rendered, int W, int H,
+	const float* background,
+	const float* means3D, const float* shs, const float* colors_precomp,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* campos, const int* radii,
+	char* geom_buffer, char* binning_buffer, char* img_buffer,
+	const float* dL_dpix,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+	void* stream)
+{
+	(void)colors_precomp;
+	if (int rc = ogs_lonlat_backward_render(P, num_rendered, W, H, background, geom_buffer, binning_buffer,
+	                                        img_buffer, dL_dpix, stream)) return rc;
+	return ogs_lonlat_backward_finish(P, D, M, W, H, means3D, shs, scales, scale_modifier, rotations, cov3D_precomp,
+	                                  viewmatrix, campos, radii, geom_buffer, dL_dmean2D, dL_dconic, dL_dopacity,
+	                                  dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, stream);
 }
 
 OGS_API int ogs_mark_all_visible(int P, uint8_t* present, void* stream)

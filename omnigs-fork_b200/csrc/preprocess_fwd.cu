@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 	uint32_t my_tiles = 0;
 	int out_radius = 0;
 	uint32_t key = 0xFFFFFFFFu;
-	bool emits = false;           // visible inside this band: needs a colour and a packed record
+	bool emits = false;           // visible inside this band: needs a packed record and tile instances
+	bool visible = false;         // visible in the full frame (radii > 0): needs its SH clamp mask
 	float3 p_orig = { 0.f, 0.f, 0.f }, conic = { 0.f, 0.f, 0.f };
 	float2 point_image = { 0.f, 0.f };
 	float r = 0.f;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 				tile_rect_p(point_image, (int)my_radius, a.gx, a.gy, x0, y0, x1, y1);
 				if ((x1 - x0) * (y1 - y0) != 0) {
 					out_radius = (int)my_radius;
+					visible = true;
 					// latitude-band clip (identity for the full image)
 					by0 = max(y0, a.band_y0);
 					by1 = min(y1, a.band_y1);
@@ -116,7 +118,9 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 	// every thread waits for the CTA's SH rows (a CTA must not retire with bulk copies in flight)
 	if (kBulkSH) mbar_wait(&s_bar, 0);
 
-	if (emits) {
+	// The clamp mask is per-Gaussian forward state the per-Gaussian backward needs for EVERY visible
+	// Gaussian, also when this rank's band does not contain it (accumulators may arrive from other ranks).
+	if (visible) {
 		float3 rgb;
 		unsigned cmask = 0;
 		if (a.colors_precomp == nullptr) {
@@ -142,18 +146,20 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 			        a.colors_precomp[3 * (size_t)idx + 2] };
 		}
 		a.clamped[idx] = (uint8_t)cmask;
-		a.depth[idx] = r;
-		a.g0[idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-		a.g1[idx] = make_float4(conic.z, a.opacities[idx], rgb.x, rgb.y);
-		a.gb[idx] = rgb.z;
-		a.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));
-		my_tiles = (uint32_t)((by1 - by0) * (x1 - x0));
-		key = __float_as_uint(r);
-		const int pitch = a.gx + 1;
-		atomicAdd(&a.tile_diff[by0 * pitch + x0], 1);
-		atomicAdd(&a.tile_diff[by0 * pitch + x1], -1);
-		atomicAdd(&a.tile_diff[by1 * pitch + x0], -1);
-		atomicAdd(&a.tile_diff[by1 * pitch + x1], 1);
+		if (emits) {
+			a.depth[idx] = r;
+			a.g0[idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+			a.g1[idx] = make_float4(conic.z, a.opacities[idx], rgb.x, rgb.y);
+			a.gb[idx] = rgb.z;
+			a.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));
+			my_tiles = (uint32_t)((by1 - by0) * (x1 - x0));
+			key = __float_as_uint(r);
+			const int pitch = a.gx + 1;
+			atomicAdd(&a.tile_diff[by0 * pitch + x0], 1);
+			atomicAdd(&a.tile_diff[by0 * pitch + x1], -1);
+			atomicAdd(&a.tile_diff[by1 * pitch + x0], -1);
+			atomicAdd(&a.tile_diff[by1 * pitch + x1], 1);
+		}
 	}
 	if (idx < a.P) {
 		a.radii[idx] = out_radius;

@@ -113,11 +113,16 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
 def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                    cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                    dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                   imageBuffer, camera_type=PINHOLE):
+                                   imageBuffer, camera_type=PINHOLE, reduce_accumulators=None):
     """reference src/rasterize_points.cu:166-285.
 
     Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
     dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4]).
+
+    ``reduce_accumulators`` (extension for latitude bands): a callable that receives the packed
+    [P,12] float32 render-backward accumulators of this rank (a view into geomBuffer) between the two
+    backward kernels, e.g. ``lambda t: dist.all_reduce(t)``; the per-Gaussian backward then runs on the
+    sums, so every rank ends with the full-frame gradients after exchanging 48 B/Gaussian.
     """
     _require_cuda(means3D, "means3D")
     lib = load_library()
@@ -147,16 +152,25 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                 _f32c(t) for t in (background, means3D, colors, scales, rotations, cov3D_precomp, viewmatrix,
                                    sh, campos, dL_dout_color))
             radii_c = radii.contiguous()
-            check(lib.ogs_lonlat_backward(
-                P, int(degree), M, int(R), W, H,
-                _ptr(background), _ptr(means3D_c), _ptr(sh), _ptr(colors),
-                _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
-                _ptr(viewmatrix), _ptr(campos), _ptr(radii_c),
-                _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
-                _ptr(dL),
-                _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors),
-                _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations),
-                _stream(device)))
+            outs = (_ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors),
+                    _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
+            if reduce_accumulators is None:
+                check(lib.ogs_lonlat_backward(
+                    P, int(degree), M, int(R), W, H,
+                    _ptr(background), _ptr(means3D_c), _ptr(sh), _ptr(colors),
+                    _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                    _ptr(viewmatrix), _ptr(campos), _ptr(radii_c),
+                    _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer), _ptr(dL), *outs, _stream(device)))
+            else:
+                check(lib.ogs_lonlat_backward_render(
+                    P, int(R), W, H, _ptr(background), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                    _ptr(dL), _stream(device)))
+                base = (-geomBuffer.data_ptr()) % 256 + lib.ogs_grad_acc_offset(P)   # carving starts 256-B aligned
+                reduce_accumulators(geomBuffer[base:base + 48 * P].view(torch.float32).view(P, 12))
+                check(lib.ogs_lonlat_backward_finish(
+                    P, int(degree), M, W, H, _ptr(means3D_c), _ptr(sh), _ptr(scales), float(scale_modifier),
+                    _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(campos), _ptr(radii_c),
+                    _ptr(geomBuffer), *outs, _stream(device)))
             if M == 0:
                 dL_dsh = torch.zeros((P, 0, 3), **opts)
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations

@@ -71,12 +71,12 @@ def run_forward(mod, d):
         d["campos"], False, 3, False)
 
 
-def run_backward(mod, d, fwd, dL):
+def run_backward(mod, d, fwd, dL, **kw):
     R, _, radii, geom, binning, img = fwd
     return mod.RasterizeGaussiansBackwardCUDA(
         d["background"], d["means3D"], radii, d["colors"], d["scales"], d["rotations"], d["scale_modifier"],
         d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], 0.0, 0.0, dL, d["sh"], d["degree"], d["campos"],
-        geom, R, binning, img, 3)
+        geom, R, binning, img, 3, **kw)
 
 
 def ours_state(d, fwd):

@@ -39,8 +39,8 @@ band = bands[rank]
 
 def step():
     img, fwd = par.render_band_forward(rasterize, band, scene.H)
-    g = h.run_backward(h.pkg, d, fwd, dL)
-    par.reduce_band_gradients(list(g))
+    # exchange the 48 B/Gaussian accumulators between the two backward kernels, not the 324 B of final gradients
+    g = h.run_backward(h.pkg, d, fwd, dL, reduce_accumulators=(lambda t: dist.all_reduce(t)) if world > 1 else (lambda t: None))
     return fwd[0]
 
 for _ in range(args.warmup): Rb = step()
