@@ -1,26 +1,33 @@
 // render_bwd.cu — 16x16-tile back-to-front replay of the blend (backward).
 //
 // Per-pixel arithmetic follows the reference's backward renderCUDA
-// (cuda_rasterizer/backward.cu:672-843): T is un-multiplied by division, accum_rec / last_alpha /
-// last_color carry the colour behind the current Gaussian, and the nine partial derivatives
-// (dL/dmean2D.xy in NDC units, dL/dconic .x .y .w, dL/dopacity, dL/dcolour rgb) use the same
-// expressions.  The reference then issues 9 global float atomics per (pixel, Gaussian) pair
-// (backward.cu:805,829-840).  Here instead:
-//   * the tile list is cut at the tile's largest n_contrib (nothing behind it was blended),
-//   * entries are tile-culled and compacted like in the forward, each warp handles an 8x4 sub-tile
-//     and iterates only over entries that can reach it,
-//   * the nine partials are summed over the warp's 32 pixels with a transposing butterfly
-//     (14 shuffles for 9 values instead of 45), accumulated across the CTA's 8 warps in shared
-//     memory, and flushed with ONE vectorised L2 reduction set per (tile, Gaussian):
-//     2 x red.global.add.v4.f32 + 1 x red.global.add.f32 into a packed 12-float accumulator row.
-// Summation order differs from the reference's atomics (which are unordered anyway); parity is
-// within the stated 1e-4 relative tolerance.
+// (cuda_rasterizer/backward.cu:672-843): T is un-multiplied step by step, accum_rec / last_alpha /
+// last_color carry the colour behind the current Gaussian, and the derivatives of the pixel colour
+// w.r.t. the Gaussian's 2-D mean, conic, opacity and colour are the same expressions.  The reference
+// then issues 9 global float atomics per (pixel, Gaussian) pair (backward.cu:805,829-840).  Here:
+//   * the tile list is cut at the tile's largest n_contrib (nothing behind it was blended);
+//   * entries are tile-culled and stably compacted into shared memory like in the forward;
+//   * a CTA is two warps; each warp owns a 16x8 half-tile and each LANE owns four pixels, one in each
+//     8x4 sub-block of that half.  The warp tests 32 staged entries at a time against its four
+//     sub-blocks (one entry per lane, four ballots) and visits only entries that can reach it;
+//   * per visited entry every lane adds up, over its (up to four) contributing pixels, nine raw sums:
+//       u*dx, u*dy, u*dx^2, u*dx*dy, u*dy^2 (u = dL/dG * G), G*dL/dalpha and the three colour terms.
+//     They are reduced over the warp with ONE transposing butterfly (14 shuffles for 9 values) —
+//     the fixed cost per entry is paid once per 128 pixels, not once per 32 — combined across the
+//     two warps in shared memory, turned into the reference's quantities once per (tile, Gaussian)
+//       dL/dmean2D.x = -(W/2) (A Su_dx + B Su_dy),  dL/dconic.x = -1/2 Su_dx2, ...
+//     and flushed with one vectorised L2 reduction set: 2 x red.global.add.v4.f32 + 1 x red.global.add.f32
+//     into a packed 12-float accumulator row.
+// Summation order differs from the reference's (unordered) atomics; parity is within the stated tolerance.
 #include "render_common.cuh"
 #include "launchers.cuh"
 
 namespace ogs {
 
 constexpr int kAccStride = 9;
+constexpr int kBwdThreads = 64;                 // two warps per tile
+constexpr int kBwdSlots = 4;                    // pixels per lane (one per 8x4 sub-block)
+constexpr int kBwdPerThread = kBatch / kBwdThreads;
 
 // Sum v[0..7] and v8 over the 32 lanes.  On return lane L holds in `z` the total of value (L>>2)
 // (replicated over the 4 lanes of a quad) and every lane holds the total of v8 in `z8`.
@@ -54,7 +61,7 @@ OGS_D void warp_transpose_reduce9(const float (&v)[8], float v8, float& z, float
 	for (int o = 16; o > 0; o >>= 1) z8 += __shfl_xor_sync(full, z8, o);
 }
 
-__global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
+__global__ void __launch_bounds__(kBwdThreads, 10) render_bwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
 	const float* __restrict__ bg_color,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float* __restrict__ gb,
@@ -63,149 +70,188 @@ __global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
 {
 	__shared__ StagedEntry s_e[kBatch];
 	__shared__ float s_acc[kBatch * kAccStride];
-	__shared__ uint32_t s_warp_cnt[kRenderThreads / 32];
+	__shared__ int s_warp_cnt[kBwdThreads / 32];
 	__shared__ int s_max_contrib;
 
 	const int tile = blockIdx.x;
 	const int tile_x = tile % gx, tile_y = tile / gx;
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int sub_x0 = tile_x * kTile + (warp & 1) * kSubW;
-	const int sub_y0 = tile_y * kTile + (warp >> 1) * kSubH;
-	const int px = sub_x0 + (lane & (kSubW - 1));
-	const int py = sub_y0 + (lane / kSubW);
-	const bool inside = px < W && py < H;
-	const size_t pix_id = (size_t)W * py + px;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const size_t HW = (size_t)H * W;
-	const float2 pixf = { (float)px, (float)py };
 
 	const float tx0 = (float)(tile_x * kTile), ty0 = (float)(tile_y * kTile);
 	const float tx1 = tx0 + (kTile - 1), ty1 = ty0 + (kTile - 1);
-	const float sx0 = (float)sub_x0, sy0 = (float)sub_y0;
-	const float sx1 = sx0 + (kSubW - 1), sy1 = sy0 + (kSubH - 1);
+	// this warp's half-tile starts at row 8*warp; slot s is the 8x4 sub-block (s & 1, s >> 1) of it
+	const int half_x0 = tile_x * kTile, half_y0 = tile_y * kTile + 8 * warp;
 
 	const uint2 range = ranges[tile];
 
-	// per-pixel state (backward.cu:717-740)
-	const float T_final = inside ? final_Ts[pix_id] : 0;
-	float T = T_final;
-	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
-	float accum_rec[3] = { 0.f, 0.f, 0.f };
-	float dL_dpixel[3] = { 0.f, 0.f, 0.f };
-	if (inside) {
+	// per-pixel state (backward.cu:717-740), one set per slot
+	// accum_rec holds the colour accumulated behind the NEXT Gaussian to be visited: the reference's
+	// update accum_rec = last_alpha*last_color + (1-last_alpha)*accum_rec (backward.cu:797) is applied
+	// right after a Gaussian is processed instead of right before the next one (same expression, same
+	// values, no last_alpha / last_color registers).
+	float T[kBwdSlots], neg_Tfinal_bg[kBwdSlots];
+	float accum_rec[kBwdSlots][3], dL_dpixel[kBwdSlots][3];
+	int last_contributor[kBwdSlots];
+	const float px0f = (float)(half_x0 + (lane & (kSubW - 1))), py0f = (float)(half_y0 + (lane / kSubW));
+	const float bg[3] = { bg_color[0], bg_color[1], bg_color[2] };
+	int my_max = 0;
 #pragma unroll
-		for (int ch = 0; ch < 3; ch++) dL_dpixel[ch] = dL_dpixels[ch * HW + pix_id];
+	for (int s = 0; s < kBwdSlots; s++) {
+		const int px = half_x0 + kSubW * (s & 1) + (lane & (kSubW - 1));
+		const int py = half_y0 + kSubH * (s >> 1) + (lane / kSubW);
+		const bool inside = px < W && py < H;
+		const size_t pix_id = (size_t)W * py + px;
+		const float T_final = inside ? final_Ts[pix_id] : 0.f;
+		T[s] = T_final;
+		last_contributor[s] = inside ? (int)n_contrib[pix_id] : 0;   // 0 => no list position passes the test
+		my_max = max(my_max, last_contributor[s]);
+		float bg_dot = 0.f;
+#pragma unroll
+		for (int ch = 0; ch < 3; ch++) {
+			accum_rec[s][ch] = 0.f;
+			dL_dpixel[s][ch] = inside ? dL_dpixels[ch * HW + pix_id] : 0.f;
+			bg_dot += bg[ch] * dL_dpixel[s][ch];
+		}
+		neg_Tfinal_bg[s] = -T_final * bg_dot;   // (-T_final / (1 - alpha)) * bg_dot = this * 1/(1 - alpha)
 	}
-	float last_alpha = 0.f;
-	float last_color[3] = { 0.f, 0.f, 0.f };
 	const float ddelx_dx = 0.5 * W;
 	const float ddely_dy = 0.5 * H;
-	float bg_dot_dpixel = 0.f;
-#pragma unroll
-	for (int ch = 0; ch < 3; ch++) bg_dot_dpixel += bg_color[ch] * dL_dpixel[ch];
-	const float neg_Tfinal_bg = -T_final * bg_dot_dpixel;   // (-T_final / (1 - alpha)) * bg_dot = this * 1/(1 - alpha)
 
 	// entries at list positions >= max(n_contrib) of the tile were blended by no pixel
-	if (threadIdx.x == 0) s_max_contrib = 0;
+	if (tid == 0) s_max_contrib = 0;
 	__syncthreads();
-	if (last_contributor > 0) atomicMax(&s_max_contrib, last_contributor);
+	if (my_max > 0) atomicMax(&s_max_contrib, my_max);
 	__syncthreads();
 	const int n = min((int)(range.y - range.x), s_max_contrib);
 	const int rounds = (n + kBatch - 1) / kBatch;
 
 	for (int round = 0; round < rounds; round++) {
-		// ---- gather (reverse list order), tile-level cull, stable compaction ----
-		const int i = n - 1 - (round * kBatch + (int)threadIdx.x); // 0-based list position
-		bool keep = false;
-		float4 a = make_float4(0, 0, 0, 0), b = a;
-		float cb = 0.f, tau = 0.f;
-		uint32_t id = 0;
-		if (i >= 0) {
-			id = point_list[range.x + i];
-			a = g0[id];
-			b = g1[id];
-			cb = gb[id];
-			tau = alpha_power_threshold(b.y);
-			keep = gaussian_touches_box(a.x, a.y, a.z, a.w, b.x, tau, tx0, ty0, tx1, ty1);
+		// ---- gather (reverse list order, 4 consecutive entries per thread), tile-level cull ----
+		float4 a[kBwdPerThread], b[kBwdPerThread];
+		float cb[kBwdPerThread], tau[kBwdPerThread];
+		uint32_t id[kBwdPerThread];
+		int pos[kBwdPerThread];
+		bool keep[kBwdPerThread];
+		int my_keep = 0;
+#pragma unroll
+		for (int q = 0; q < kBwdPerThread; q++) {
+			pos[q] = n - 1 - (round * kBatch + tid * kBwdPerThread + q);   // 0-based list position
+			id[q] = (pos[q] >= 0) ? point_list[range.x + pos[q]] : 0u;
 		}
-		int total;
-		const int slot = block_compact_slot(keep, s_warp_cnt, total); // contains a __syncthreads
-		if (keep) {
-			s_e[slot].a = a;
-			s_e[slot].b = make_float4(b.x, tau, b.y, __int_as_float(i));   // 0-based list position
-			s_e[slot].c = make_float4(b.z, b.w, cb, __uint_as_float(id));
+#pragma unroll
+		for (int q = 0; q < kBwdPerThread; q++) {
+			keep[q] = false;
+			if (pos[q] >= 0) {
+				a[q] = g0[id[q]];
+				b[q] = g1[id[q]];
+				cb[q] = gb[id[q]];
+				tau[q] = alpha_power_threshold(b[q].y);
+				keep[q] = gaussian_touches_box(a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, tau[q], tx0, ty0, tx1, ty1);
+			}
+			my_keep += keep[q] ? 1 : 0;
 		}
-		for (int k = threadIdx.x; k < total * kAccStride; k += kRenderThreads) s_acc[k] = 0.f;
+		// stable compaction: thread-major order == descending list position
+		int incl = my_keep;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const int u = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += u;
+		}
+		if (lane == 31) s_warp_cnt[warp] = incl;
+		__syncthreads();   // also orders the previous round's flush before s_e / s_acc are rewritten
+		int slot = incl - my_keep + (warp == 1 ? s_warp_cnt[0] : 0);
+		const int total = s_warp_cnt[0] + s_warp_cnt[1];
+#pragma unroll
+		for (int q = 0; q < kBwdPerThread; q++) {
+			if (keep[q]) {
+				s_e[slot].a = a[q];
+				s_e[slot].b = make_float4(b[q].x, tau[q], b[q].y, __int_as_float(pos[q]));
+				s_e[slot].c = make_float4(b[q].z, b[q].w, cb[q], __uint_as_float(id[q]));
+				slot++;
+			}
+		}
+		for (int k = tid; k < total * kAccStride; k += kBwdThreads) s_acc[k] = 0.f;
 		__syncthreads();
 
-		// ---- per-warp replay over the entries that can reach this sub-tile ----
+		// ---- per-warp replay over the entries that can reach this half-tile ----
 		for (int base = 0; base < total; base += 32) {
-			const int s = base + lane;
-			bool hit = false;
-			if (s < total) {
-				const float4 ea = s_e[s].a;
-				const float4 eb = s_e[s].b;
-				hit = gaussian_touches_box(ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, sx0, sy0, sx1, sy1);
+			const int e_idx = base + lane;
+			unsigned m[kBwdSlots];
+			{
+				bool hit[kBwdSlots] = { false, false, false, false };
+				if (e_idx < total) {
+					const float4 ea = s_e[e_idx].a;
+					const float4 eb = s_e[e_idx].b;
+#pragma unroll
+					for (int s = 0; s < kBwdSlots; s++) {
+						const float bx0 = (float)(half_x0 + kSubW * (s & 1)), by0 = (float)(half_y0 + kSubH * (s >> 1));
+						hit[s] = gaussian_touches_box(ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, bx0, by0, bx0 + (kSubW - 1), by0 + (kSubH - 1));
+					}
+				}
+#pragma unroll
+				for (int s = 0; s < kBwdSlots; s++) m[s] = __ballot_sync(0xffffffffu, hit[s]);
 			}
-			unsigned m = __ballot_sync(0xffffffffu, hit);
-			while (m) {
-				const int j = base + __ffs(m) - 1;
-				m &= m - 1;
+			unsigned m_any = m[0] | m[1] | m[2] | m[3];
+			while (m_any) {
+				const int bit = __ffs(m_any) - 1;
+				m_any &= m_any - 1;
+				const int j = base + bit;
 				const StagedEntry* e = &s_e[j];
 				const float4 ea = e->a;
 				const float4 eb = e->b;
+				const float4 ec = e->c;
+				const int list_pos = __float_as_int(eb.w);
 
-				// backward.cu:766-782: same guards (and the same pinned arithmetic) as the forward
-				float2 d;
-				const float power = pair_power(ea.x, ea.y, ea.z, ea.w, eb.x, pixf, d.x, d.y);
-				bool valid = inside && (__float_as_int(eb.w) < last_contributor) && !(power > 0.0f) && !(power < eb.y);
-				float G = 0.f, alpha = 0.f;
-				if (valid) {
-					G = expf(power);
-					alpha = fminf(0.99f, __fmul_rn(eb.z, G));
-					valid = !(alpha < kAlphaMin);
-				}
-				if (!__any_sync(0xffffffffu, valid)) continue;
-
-				float v[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
-				float v8 = 0.f;
-				if (valid) {
-					// backward.cu:784-840.  One correctly rounded reciprocal replaces the reference's two
-					// divisions by (1 - alpha): T/(1-a) and -T_final/(1-a) (difference <= 1 ulp, inside the
-					// 1e-4 gradient tolerance).
-					const float4 ec = e->c;
-					const float inv = __frcp_rn(1.f - alpha);
-					T = T * inv;
-					const float dchannel_dcolor = alpha * T;
-					float dL_dalpha = 0.0f;
-					const float col[3] = { ec.x, ec.y, ec.z };
+				float r[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+				float r8 = 0.f;
+				bool any_valid = false;
 #pragma unroll
-					for (int ch = 0; ch < 3; ch++) {
-						const float c = col[ch];
-						accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-						last_color[ch] = c;
-						dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
+				for (int s = 0; s < kBwdSlots; s++) {
+					if (!((m[s] >> bit) & 1u)) continue;   // warp-uniform
+					// backward.cu:766-782: same guards (and the same pinned arithmetic) as the forward
+					float dx, dy;
+					const float2 pixf = { px0f + (float)(kSubW * (s & 1)), py0f + (float)(kSubH * (s >> 1)) };   // exact
+					const float power = pair_power(ea.x, ea.y, ea.z, ea.w, eb.x, pixf, dx, dy);
+					bool valid = (list_pos < last_contributor[s]) && !(power > 0.0f) && !(power < eb.y);
+					float G = 0.f, alpha = 0.f;
+					if (valid) {
+						G = expf(power);
+						alpha = fminf(0.99f, __fmul_rn(eb.z, G));
+						valid = !(alpha < kAlphaMin);
 					}
-					v[6] = dchannel_dcolor * dL_dpixel[0];
-					v[7] = dchannel_dcolor * dL_dpixel[1];
-					v8 = dchannel_dcolor * dL_dpixel[2];
-					dL_dalpha *= T;
-					last_alpha = alpha;
-					dL_dalpha += neg_Tfinal_bg * inv;
+					if (valid) {
+						any_valid = true;
+						// backward.cu:784-840; one correctly rounded reciprocal replaces the two divisions by (1 - alpha)
+						const float inv = __frcp_rn(1.f - alpha);
+						T[s] = T[s] * inv;
+						const float dchannel_dcolor = alpha * T[s];
+						float dL_dalpha = 0.0f;
+						const float col[3] = { ec.x, ec.y, ec.z };
+#pragma unroll
+						for (int ch = 0; ch < 3; ch++) {
+							dL_dalpha += (col[ch] - accum_rec[s][ch]) * dL_dpixel[s][ch];
+							accum_rec[s][ch] = alpha * col[ch] + (1.f - alpha) * accum_rec[s][ch];
+						}
+						r[6] += dchannel_dcolor * dL_dpixel[s][0];
+						r[7] += dchannel_dcolor * dL_dpixel[s][1];
+						r8 += dchannel_dcolor * dL_dpixel[s][2];
+						dL_dalpha *= T[s];
+						dL_dalpha += neg_Tfinal_bg[s] * inv;
 
-					const float dL_dG = eb.z * dL_dalpha;
-					const float gdx = G * d.x;
-					const float gdy = G * d.y;
-					const float dG_ddelx = -gdx * ea.z - gdy * ea.w;
-					const float dG_ddely = -gdy * eb.x - gdx * ea.w;
-					v[0] = dL_dG * dG_ddelx * ddelx_dx;
-					v[1] = dL_dG * dG_ddely * ddely_dy;
-					v[2] = -0.5f * gdx * d.x * dL_dG;
-					v[3] = -0.5f * gdx * d.y * dL_dG;
-					v[4] = -0.5f * gdy * d.y * dL_dG;
-					v[5] = G * dL_dalpha;
+						const float u = (eb.z * dL_dalpha) * G;   // dL/dG * G
+						const float udx = u * dx, udy = u * dy;
+						r[0] += udx;
+						r[1] += udy;
+						r[2] += udx * dx;
+						r[3] += udx * dy;
+						r[4] += udy * dy;
+						r[5] += G * dL_dalpha;
+					}
 				}
+				if (!__any_sync(0xffffffffu, any_valid)) continue;
 				float z, z8;
-				warp_transpose_reduce9(v, v8, z, z8);
+				warp_transpose_reduce9(r, r8, z, z8);
 				// lanes 0,4,..,28 hold sums 0..7, lane 1 takes the ninth: one shared-memory atomic pass
 				const bool ninth = (lane == 1);
 				if ((lane & 3) == 0 || ninth)
@@ -214,24 +260,26 @@ __global__ void __launch_bounds__(kRenderThreads) render_bwd_kernel(
 		}
 		__syncthreads();
 
-		// ---- flush: one packed reduction set per (tile, Gaussian) ----
-		if ((int)threadIdx.x < total) {
-			const float* acc = &s_acc[threadIdx.x * kAccStride];
+		// ---- flush: raw sums -> the reference's quantities, one packed reduction set per (tile, Gaussian) ----
+		for (int k = tid; k < total; k += kBwdThreads) {
+			const float* acc = &s_acc[k * kAccStride];
 			float r[9];
 			bool nz = false;
 #pragma unroll
-			for (int k = 0; k < 9; k++) {
-				r[k] = acc[k];
-				nz |= (r[k] != 0.f);
+			for (int i = 0; i < 9; i++) {
+				r[i] = acc[i];
+				nz |= (r[i] != 0.f);
 			}
 			if (nz) {
-				float* dst = grad_acc + (size_t)__float_as_uint(s_e[threadIdx.x].c.w) * 12;
-				red_add_v4(dst, r[0], r[1], r[2], r[3]);
-				red_add_v4(dst + 4, r[4], r[5], r[6], r[7]);
+				const float4 ea = s_e[k].a;
+				const float A = ea.z, B = ea.w, C = s_e[k].b.x;
+				float* dst = grad_acc + (size_t)__float_as_uint(s_e[k].c.w) * 12;
+				// dL/dmean2D = dL/dG * dG/ddel * ddel/dx summed; dL/dconic = -1/2 * sum u d d^T  (backward.cu:821-836)
+				red_add_v4(dst, -ddelx_dx * (A * r[0] + B * r[1]), -ddely_dy * (C * r[1] + B * r[0]), -0.5f * r[2], -0.5f * r[3]);
+				red_add_v4(dst + 4, -0.5f * r[4], r[5], r[6], r[7]);
 				red_add(dst + 8, r[8]);
 			}
 		}
-		__syncthreads();
 	}
 }
 
@@ -241,8 +289,8 @@ int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, in
                       float* grad_acc, cudaStream_t st)
 {
 	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
-	render_bwd_kernel<<<gx * gy, kRenderThreads, 0, st>>>(ranges, point_list, W, H, gx, bg, g0, g1, gb,
-	                                                     final_T, n_contrib, dL_dpix, grad_acc);
+	render_bwd_kernel<<<gx * gy, kBwdThreads, 0, st>>>(ranges, point_list, W, H, gx, bg, g0, g1, gb,
+	                                                  final_T, n_contrib, dL_dpix, grad_acc);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }
