@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -116,7 +116,7 @@ def cpu_port_baseline(scene, view, dL_np, budget_s=45.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -224,12 +224,21 @@ def main():
     vbuf = torch.empty(19, device=dev)
     h2d = gt_host.numel() * 4 + 19 * 4
 
+    copy_stream = torch.cuda.Stream()
+    gt_ready = torch.cuda.Event()
+
     def e2e_step(s):
+        # the pose is needed at once; the 25 MB target image only by the loss, so its copy runs on a side
+        # stream underneath the forward (what a trainer's prefetcher does) and is waited for before the loss
         vbuf.copy_(view_host[s], non_blocking=True)
-        gt_dev.copy_(gt_host, non_blocking=True)
+        copy_stream.wait_stream(torch.cuda.current_stream())   # the previous step's loss has consumed gt_dev
+        with torch.cuda.stream(copy_stream):
+            gt_dev.copy_(gt_host, non_blocking=True)
+            gt_ready.record()
         d["viewmatrix"], d["campos"] = vbuf[:16].view(4, 4), vbuf[16:19]
         d["projmatrix"] = d["viewmatrix"]
         fwd = h.run_forward(mod, d)
+        torch.cuda.current_stream().wait_event(gt_ready)
         diff = fwd[1] - gt_dev
         loss = diff.abs().mean()                       # L1 (the reference's main loss term)
         g = h.run_backward(mod, d, fwd, torch.sign(diff) / diff.numel())

@@ -131,17 +131,18 @@ OGS_D uint32_t lookback_sum(const uint32_t* __restrict__ status, int tile, size_
 	return excl;
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
 	uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-	uint32_t n, int shift, int bits,
+	uint32_t n, int shift,
 	const uint32_t* __restrict__ digit_counts, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int nbins = 1 << bits;
-	const uint32_t mask = (uint32_t)nbins - 1u;
+	constexpr int nbins = 1 << BITS;
+	constexpr uint32_t mask = (uint32_t)nbins - 1u;
 
 	if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
 	for (int w = 0; w < kSortThreads / 32; w++)
@@ -188,10 +189,11 @@ __global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 		const bool valid = idx < n;
 		const uint32_t d = (key[k] >> shift) & mask;
 		unsigned peers = __ballot_sync(0xffffffffu, valid);
-		for (int bit = 0; bit < bits; bit++) {
-			const bool one = (d >> bit) & 1u;
-			const unsigned b = __ballot_sync(0xffffffffu, one);
-			peers &= one ? b : ~b;
+#pragma unroll
+		for (int bit = 0; bit < BITS; bit++) {
+			const unsigned one = (d >> bit) & 1u;
+			const unsigned b = __ballot_sync(0xffffffffu, one != 0u);
+			peers &= b ^ (one - 1u);   // lanes whose bit equals mine: b if set, ~b if clear
 		}
 		const int rank_in = __popc(peers & lanemask_lt());
 		uint32_t prev = 0;
@@ -513,8 +515,12 @@ TileSortPlan make_tile_sort_plan(int W, int H)
 static cudaError_t ensure_onesweep_smem()
 {
 	// per device/context attribute, cheap host call: set on every use (several devices per process)
-	return cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                            (int)sizeof(OnesweepSmem));
+	const int bytes = (int)sizeof(OnesweepSmem);
+	cudaError_t e = cudaSuccess;
+#define OGS_SET(B) if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	OGS_SET(1) OGS_SET(2) OGS_SET(3) OGS_SET(4) OGS_SET(5) OGS_SET(6) OGS_SET(7) OGS_SET(8) OGS_SET(9)
+#undef OGS_SET
+	return e;
 }
 
 // Depth ordering of the P Gaussians (stage 1).  Keys: g.sort_key[0]; result order in g.sort_val[0];
@@ -533,8 +539,8 @@ int launch_depth_order(const GeomState& g, int P, cudaStream_t st)
 		const uint32_t* vin = p == 0 ? nullptr : g.sort_val[p & 1];
 		uint32_t* kout = g.sort_key[(p + 1) & 1];
 		uint32_t* vout = g.sort_val[(p + 1) & 1];
-		onesweep_pass_kernel<<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(
-			kin, vin, kout, vout, n, 8 * p, 8, g.depth_hist + 256 * p,
+		onesweep_pass_kernel<8><<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(
+			kin, vin, kout, vout, n, 8 * p, g.depth_hist + 256 * p,
 			g.depth_status + (size_t)p * tiles * 256, tickets + p);
 	}
 	// 4 passes: result back in buffer 0
@@ -572,9 +578,18 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 	size_t status_off = 0;
 	for (int p = 0; p < plan.passes; p++) {
 		const bool last = (p == plan.passes - 1);
-		onesweep_pass_kernel<<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(
-			b.key[p & 1], b.val[p & 1], last ? nullptr : b.key[(p + 1) & 1], b.val[(p + 1) & 1],
-			n, plan.shift[p], plan.bits[p], img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p);
+#define OGS_SORT_CASE(B)                                                                                      \
+	case B:                                                                                                   \
+		onesweep_pass_kernel<B><<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(                           \
+			b.key[p & 1], b.val[p & 1], last ? nullptr : b.key[(p + 1) & 1], b.val[(p + 1) & 1], n,           \
+			plan.shift[p], img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p);               \
+		break;
+		switch (plan.bits[p]) {
+			OGS_SORT_CASE(1) OGS_SORT_CASE(2) OGS_SORT_CASE(3) OGS_SORT_CASE(4) OGS_SORT_CASE(5)
+			OGS_SORT_CASE(6) OGS_SORT_CASE(7) OGS_SORT_CASE(8) OGS_SORT_CASE(9)
+		default: return fail(OGS_ERR_INVALID_ARG, "bad radix digit width");
+		}
+#undef OGS_SORT_CASE
 		status_off += (size_t)tiles << plan.bits[p];
 	}
 	prof_end(OGS_PROF_TILE_SORT, st);
