@@ -187,6 +187,19 @@ OGS_API int ogs_lonlat_train_view_host(
 	int64_t* num_rendered_host, size_t* binning_needed, void* stream);
 
 /*
+ * Longitude-seam wrap-around (opt-in extension; off by default = reference parity).
+ * The reference's live code clamps tile rects at the left/right image edge (auxiliary.h:56-66,
+ * forward.cu:678-681), so a Gaussian straddling lon = +-pi is cut at the seam; its dead code
+ * (getRectCyclic, auxiliary.h:68-83; renderLonlat, forward.h:118-129) sketches the fix implemented
+ * here: the x tile range is taken modulo the tile grid and every tile uses the copy of the mean
+ * (x, x - W or x + W) nearest to it.  Requires W % 16 == 0.  Process-global; also enabled by the
+ * environment variable OMNIGS_B200_SEAM_WRAP=1.  The mode a forward ran in is recorded in its geometry
+ * buffer, so the matching backward follows it regardless of later changes.
+ */
+OGS_API int ogs_set_seam_wrap(int on);
+OGS_API int ogs_get_seam_wrap(void);
+
+/*
  * Per-stage device timing (CUDA events on the launching stream), for bench.py's roofline block.
  * Off by default; when enabled on the calling thread every stage of the next forward/backward is
  * bracketed by events.  ogs_profile_read synchronises those events and writes milliseconds per stage

@@ -15,13 +15,14 @@ from .rasterize_points import (  # noqa: F401
     RasterizeGaussiansBackwardCUDA,
     markVisible,
     export_forward_state,
+    set_seam_wrap,
     LONLAT,
     PINHOLE,
 )
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians  # noqa: F401
 
 __all__ = [
-    "RasterizeGaussiansCUDA", "RasterizeGaussiansBackwardCUDA", "markVisible", "export_forward_state",
+    "RasterizeGaussiansCUDA", "RasterizeGaussiansBackwardCUDA", "markVisible", "export_forward_state", "set_seam_wrap",
     "GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians",
     "load_library", "library_path", "OgsError", "LONLAT", "PINHOLE",
 ]

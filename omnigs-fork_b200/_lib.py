@@ -37,6 +37,8 @@ SYMBOLS = {
     "ogs_mark_all_visible": (_c_int, [_c_int, _p, _p]),
     "ogs_export_geometry": (_c_int, [_c_int, _p] + [_p] * 7 + [_p]),
     "ogs_export_binning": (_c_int, [_c_int] * 3 + [_c_i64] + [_p] * 3 + [_p] * 5 + [_p]),
+    "ogs_set_seam_wrap": (_c_int, [_c_int]),
+    "ogs_get_seam_wrap": (_c_int, []),
     "ogs_profile_enable": (_c_int, [_c_int]),
     "ogs_profile_read": (_c_int, [ctypes.POINTER(_c_f), _c_int]),
     "ogs_lonlat_train_view_host": (_c_int, [_c_int] * 5 + [_p] * 5 + [_c_f] + [_p] * 4 + [_p] * 2 + [_p] * 3 + [_c_sz, _p]

@@ -478,7 +478,9 @@ __global__ void __launch_bounds__(kEmitThreads) emit_instances_kernel(
 		const uint32_t w = x1 - x0;
 		const uint32_t local = o - s_off[src];
 		const uint32_t q = local / w;
-		tile_keys[o] = (y0 + q) * (uint32_t)gx + x0 + (local - q * w);
+		uint32_t x = x0 + (local - q * w);
+		if (x >= (uint32_t)gx) x -= (uint32_t)gx;   // only rects that wrap around the longitude seam (opt-in mode)
+		tile_keys[o] = (y0 + q) * (uint32_t)gx + x;
 		values[o] = s_gid[src];
 	}
 }

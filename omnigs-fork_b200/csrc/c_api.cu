@@ -6,6 +6,7 @@
 #include "ogs_common.cuh"
 #include "launchers.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -24,6 +25,16 @@ int fail_cuda(cudaError_t e)
 	g_last_error = std::string("CUDA error: ") + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
 	return OGS_ERR_CUDA;
 }
+
+// ------------------------------------------------------------------ options
+namespace {
+int env_seam_wrap()
+{
+	const char* e = getenv("OMNIGS_B200_SEAM_WRAP");
+	return (e && e[0] && e[0] != '0') ? 1 : 0;
+}
+int g_seam_wrap = env_seam_wrap();
+} // namespace
 
 // ------------------------------------------------------------------ per-stage profiling
 namespace {
@@ -239,12 +250,16 @@ int forward_stage1_impl(
 		return fail(OGS_ERR_INVALID_ARG, "SH degree / coefficient count mismatch");
 	band_y0 = max(0, band_y0);
 	band_y1 = min(gy, band_y1);
+	const int seam_wrap = g_seam_wrap;
+	if (seam_wrap && (W % kTile != 0 || 2 * gx > 65535))
+		return fail(OGS_ERR_INVALID_ARG, "seam wrap-around needs an image width that is a multiple of 16");
 
 	GeomState g = GeomState::carve(geom_buffer, P);
 	OGS_CUDA_TRY(cudaMemsetAsync(g.zero_begin, 0, g.zero_bytes, st));
 
 	PreprocessFwdArgs a{};
 	a.P = P; a.D = D; a.M = M; a.W = W; a.H = H; a.gx = gx; a.gy = gy; a.band_y0 = band_y0; a.band_y1 = band_y1;
+	a.seam_wrap = seam_wrap;
 	a.scale_modifier = scale_modifier;
 	a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
 	a.scales = scales; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
@@ -286,6 +301,9 @@ using namespace ogs;
 extern "C" {
 
 OGS_API int ogs_abi_version(void) { return OGS_ABI_VERSION; }
+
+OGS_API int ogs_set_seam_wrap(int on) { g_seam_wrap = on ? 1 : 0; return OGS_OK; }
+OGS_API int ogs_get_seam_wrap(void) { return g_seam_wrap; }
 
 OGS_API int ogs_profile_enable(int on)
 {
@@ -365,7 +383,7 @@ OGS_API int ogs_lonlat_forward_stage2(
 		if (int rc = launch_emit_and_tile_sort(g, img, b, P, num_rendered, W, H, st)) return rc;
 	}
 	prof_begin(OGS_PROF_RENDER_FWD, st);
-	const int rc = launch_render_fwd(img.ranges, b.point_list, W, H, g.g0, g.g1, g.gb, background,
+	const int rc = launch_render_fwd(img.ranges, b.point_list, W, H, g.g0, g.g1, g.gb, g.scalars, background,
 	                                 img.final_T, img.n_contrib, out_color, st);
 	prof_end(OGS_PROF_RENDER_FWD, st);
 	return rc;
@@ -388,7 +406,7 @@ OGS_API int ogs_lonlat_backward_render(
 	if (num_rendered > 0) b = BinningState::carve(binning_buffer, num_rendered, W, H);
 	OGS_CUDA_TRY(cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * (size_t)P, st));
 	prof_begin(OGS_PROF_RENDER_BWD, st);
-	if (int rc = launch_render_bwd(img.ranges, b.point_list, W, H, background, g.g0, g.g1, g.gb,
+	if (int rc = launch_render_bwd(img.ranges, b.point_list, W, H, background, g.g0, g.g1, g.gb, g.scalars,
 	                               img.final_T, img.n_contrib, dL_dpix, g.grad_acc, st)) return rc;
 	prof_end(OGS_PROF_RENDER_BWD, st);
 	return OGS_OK;

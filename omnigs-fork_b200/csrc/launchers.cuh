@@ -6,7 +6,7 @@
 namespace ogs {
 
 struct PreprocessFwdArgs {
-	int P, D, M, W, H, gx, gy, band_y0, band_y1;
+	int P, D, M, W, H, gx, gy, band_y0, band_y1, seam_wrap;
 	float scale_modifier;
 	const float* means3D;
 	const float* shs;
@@ -28,7 +28,7 @@ struct PreprocessFwdArgs {
 	uint8_t* clamped;
 	uint32_t* sort_key;
 	int* tile_diff;
-	unsigned long long* total_tiles;
+	unsigned long long* total_tiles;   // scalars[0] = sum tiles_touched; scalars[7] = seam-wrap flag of this frame
 };
 struct PreprocessBwdArgs {
 	int P, D, M, W, H;
@@ -62,10 +62,10 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 int launch_rebuild_keys(const ImageState& img, const BinningState& b, const GeomState& g, int W, int H,
                         uint64_t* keys, cudaStream_t st);
 int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
-                      const float4* g0, const float4* g1, const float* gb, const float* bg,
+                      const float4* g0, const float4* g1, const float* gb, const unsigned long long* scalars, const float* bg,
                       float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st);
 int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, int H, const float* bg,
-                      const float4* g0, const float4* g1, const float* gb,
+                      const float4* g0, const float4* g1, const float* gb, const unsigned long long* scalars,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
                       float* grad_acc, cudaStream_t st);
 int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st);

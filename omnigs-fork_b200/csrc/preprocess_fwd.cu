@@ -103,6 +103,16 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 				point_image = { ndc_to_pix_p(p_proj.x, a.W), ndc_to_pix_p(p_proj.y, a.H) };
 				int y0, y1;
 				tile_rect_p(point_image, (int)my_radius, a.gx, a.gy, x0, y0, x1, y1);
+				if (a.seam_wrap) {
+					// opt-in extension: x range modulo the tile grid (cf. the reference's unused getRectCyclic,
+					// auxiliary.h:68-83).  x0 in [0, gx), x1 = x0 + width <= x0 + gx.
+					const float R = (float)(int)my_radius;
+					const int xa = (int)floorf((point_image.x - R) * (1.0f / kTile));
+					const int xb = (int)floorf((point_image.x + R) * (1.0f / kTile)) + 1;
+					const int w = min(xb - xa, a.gx);
+					x0 = ((xa % a.gx) + a.gx) % a.gx;
+					x1 = x0 + w;
+				}
 				if ((x1 - x0) * (y1 - y0) != 0) {
 					out_radius = (int)my_radius;
 					visible = true;
@@ -155,10 +165,17 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 			my_tiles = (uint32_t)((by1 - by0) * (x1 - x0));
 			key = __float_as_uint(r);
 			const int pitch = a.gx + 1;
+			const int xe = min(x1, a.gx);   // x1 > gx only for a rect that wraps around the seam
 			atomicAdd(&a.tile_diff[by0 * pitch + x0], 1);
-			atomicAdd(&a.tile_diff[by0 * pitch + x1], -1);
+			atomicAdd(&a.tile_diff[by0 * pitch + xe], -1);
 			atomicAdd(&a.tile_diff[by1 * pitch + x0], -1);
-			atomicAdd(&a.tile_diff[by1 * pitch + x1], 1);
+			atomicAdd(&a.tile_diff[by1 * pitch + xe], 1);
+			if (x1 > a.gx) {               // the wrapped part [0, x1 - gx)
+				atomicAdd(&a.tile_diff[by0 * pitch], 1);
+				atomicAdd(&a.tile_diff[by0 * pitch + (x1 - a.gx)], -1);
+				atomicAdd(&a.tile_diff[by1 * pitch], -1);
+				atomicAdd(&a.tile_diff[by1 * pitch + (x1 - a.gx)], 1);
+			}
 		}
 	}
 	if (idx < a.P) {
@@ -174,6 +191,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 	if ((tid & 31) == 0 && wsum) atomicAdd(&s_block_tiles, (unsigned long long)wsum);
 	__syncthreads();
 	if (tid == 0 && s_block_tiles) atomicAdd(a.total_tiles, s_block_tiles);
+	if (tid == 0 && blockIdx.x == 0) a.total_tiles[7] = (unsigned long long)a.seam_wrap;
 }
 
 __global__ void mark_all_visible_kernel(int P, uint8_t* present)

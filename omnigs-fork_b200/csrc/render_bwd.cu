@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kBwdThreads, 10) render_bwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
 	const float* __restrict__ bg_color,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float* __restrict__ gb,
+	const unsigned long long* __restrict__ scalars,
 	const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
 	const float* __restrict__ dL_dpixels, float* __restrict__ grad_acc /*[P,12]*/)
 {
@@ -125,6 +126,8 @@ __global__ void __launch_bounds__(kBwdThreads, 10) render_bwd_kernel(
 	__syncthreads();
 	const int n = min((int)(range.y - range.x), s_max_contrib);
 	const int rounds = (n + kBatch - 1) / kBatch;
+	const bool seam_wrap = n > 0 && scalars[7] != 0ull;   // mode of the forward that built these lists
+	const float tile_cx = tx0 + 0.5f * (kTile - 1), Wf = (float)W;
 
 	for (int round = 0; round < rounds; round++) {
 		// ---- gather (reverse list order, 4 consecutive entries per thread), tile-level cull ----
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(kBwdThreads, 10) render_bwd_kernel(
 				a[q] = g0[id[q]];
 				b[q] = g1[id[q]];
 				cb[q] = gb[id[q]];
+				if (seam_wrap) a[q].x = nearest_copy_x(a[q].x, tile_cx, Wf);
 				tau[q] = alpha_power_threshold(b[q].y);
 				keep[q] = gaussian_touches_box(a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, tau[q], tx0, ty0, tx1, ty1);
 			}
@@ -284,12 +288,12 @@ __global__ void __launch_bounds__(kBwdThreads, 10) render_bwd_kernel(
 }
 
 int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, int H, const float* bg,
-                      const float4* g0, const float4* g1, const float* gb,
+                      const float4* g0, const float4* g1, const float* gb, const unsigned long long* scalars,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
                       float* grad_acc, cudaStream_t st)
 {
 	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
-	render_bwd_kernel<<<gx * gy, kBwdThreads, 0, st>>>(ranges, point_list, W, H, gx, bg, g0, g1, gb,
+	render_bwd_kernel<<<gx * gy, kBwdThreads, 0, st>>>(ranges, point_list, W, H, gx, bg, g0, g1, gb, scalars,
 	                                                  final_T, n_contrib, dL_dpix, grad_acc);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;

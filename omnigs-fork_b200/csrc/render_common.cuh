@@ -70,6 +70,13 @@ OGS_D float pair_power(float mx, float my, float A, float B, float C, float2 pix
 	return __fmaf_rn(q, -0.5f, -__fmul_rn(__fmul_rn(B, dx), dy));
 }
 
+// Seam wrap-around (opt-in): a tile uses the copy of the Gaussian (x, x - W, x + W) nearest to its centre.
+OGS_D float nearest_copy_x(float mx, float tile_cx, float Wf)
+{
+	const float d = mx - tile_cx;
+	return d > 0.5f * Wf ? mx - Wf : (d < -0.5f * Wf ? mx + Wf : mx);
+}
+
 // One staged list entry in shared memory (48 bytes, a single base address per inner-loop iteration):
 //   a = (mean.x, mean.y, conic.x, conic.y)
 //   b = (conic.z, tau_safe, opacity, list position as bits)

@@ -20,7 +20,7 @@ namespace ogs {
 __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float* __restrict__ gb,
-	const float* __restrict__ bg_color,
+	const unsigned long long* __restrict__ scalars, const float* __restrict__ bg_color,
 	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)
 {
 	__shared__ StagedEntry s_e[kBatch];
@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 	const uint2 range = ranges[tile];
 	const int n = (int)(range.y - range.x);
 	const int rounds = (n + kBatch - 1) / kBatch;
+	const bool seam_wrap = n > 0 && scalars[7] != 0ull;   // mode of the forward that built these lists
+	const float tile_cx = tx0 + 0.5f * (kTile - 1), Wf = (float)W;
 
 	bool done = !inside;
 	float T = 1.0f;
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 			a = g0[id];
 			b = g1[id];
 			cb = gb[id];
+			if (seam_wrap) a.x = nearest_copy_x(a.x, tile_cx, Wf);
 			tau = alpha_power_threshold(b.y);
 			keep = gaussian_touches_box(a.x, a.y, a.z, a.w, b.x, tau, tx0, ty0, tx1, ty1);
 		}
@@ -127,11 +130,11 @@ __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 }
 
 int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
-                      const float4* g0, const float4* g1, const float* gb, const float* bg,
+                      const float4* g0, const float4* g1, const float* gb, const unsigned long long* scalars, const float* bg,
                       float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st)
 {
 	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
-	render_fwd_kernel<<<gx * gy, kRenderThreads, 0, st>>>(ranges, point_list, W, H, gx, g0, g1, gb, bg,
+	render_fwd_kernel<<<gx * gy, kRenderThreads, 0, st>>>(ranges, point_list, W, H, gx, g0, g1, gb, scalars, bg,
 	                                                     final_T, n_contrib, out_color);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;

@@ -19,6 +19,15 @@ NUM_CHANNELS = 3  # reference cuda_rasterizer/config.h:25
 _BINNING_GRANULE = 64 << 20
 
 
+def set_seam_wrap(on):
+    """Opt-in longitude-seam wrap-around (non-parity extension, see include/omnigs_b200.h).  Process-global;
+    returns the previous setting."""
+    lib = load_library()
+    prev = bool(lib.ogs_get_seam_wrap())
+    check(lib.ogs_set_seam_wrap(1 if on else 0))
+    return prev
+
+
 def _ptr(t):
     """Device pointer of a tensor; an empty tensor is the reference's "None" (nullptr)."""
     if t is None or t.numel() == 0:

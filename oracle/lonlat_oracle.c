@@ -36,6 +36,9 @@ static const float SH_C3[7] = { -0.5900435899266435f, 2.890611442640554f, -0.457
                                 0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                 -0.5900435899266435f };
 
+static int g_wrap = 0;
+void ogs_oracle_set_seam_wrap(int on) { g_wrap = on ? 1 : 0; }
+
 int ogs_oracle_num_threads(void)
 {
 #ifdef _OPENMP
@@ -102,6 +105,26 @@ static void tile_rect(float px, float py, int max_radius, int gx, int gy, int* x
 	*y0 = imin(gy, imax(0, (int)((py - max_radius) / TILE)));
 	*x1 = imin(gx, imax(0, (int)((px + max_radius + TILE - 1) / TILE)));
 	*y1 = imin(gy, imax(0, (int)((py + max_radius + TILE - 1) / TILE)));
+}
+
+/* wrap-around variant of the x range (extension, see ogs_oracle_set_seam_wrap): x0 in [0,gx), x1 = x0 + width */
+static void tile_rect_any(float px, float py, int max_radius, int gx, int gy, int* x0, int* y0, int* x1, int* y1)
+{
+	tile_rect(px, py, max_radius, gx, gy, x0, y0, x1, y1);
+	if (g_wrap) {
+		const float R = (float)max_radius;
+		int xa = (int)floorf((px - R) * (1.0f / TILE));
+		int xb = (int)floorf((px + R) * (1.0f / TILE)) + 1;
+		int w = imin(xb - xa, gx);
+		*x0 = ((xa % gx) + gx) % gx;
+		*x1 = *x0 + w;
+	}
+}
+static float nearest_copy_x(float mx, float tile_cx, float Wf)
+{
+	const float d = mx - tile_cx;
+	if (!g_wrap) return mx;
+	return d > 0.5f * Wf ? mx - Wf : (d < -0.5f * Wf ? mx + Wf : mx);
 }
 
 /* rasterizer_impl.cu:47-62 */
@@ -279,7 +302,7 @@ int64_t ogs_oracle_preprocess_fwd(
 		/* forward.cu:677-683 */
 		float px = ndc_to_pix(sx, W), py = ndc_to_pix(sy, H);
 		int x0, y0, x1, y1;
-		tile_rect(px, py, (int)my_radius, gx, gy, &x0, &y0, &x1, &y1);
+		tile_rect_any(px, py, (int)my_radius, gx, gy, &x0, &y0, &x1, &y1);
 		if ((x1 - x0) * (y1 - y0) == 0) continue;
 
 		/* forward.cu:688-694 */
@@ -321,12 +344,12 @@ void ogs_oracle_bin(
 		if (radii[idx] > 0) {
 			uint32_t off = (idx == 0) ? 0 : point_offsets[idx - 1];
 			int x0, y0, x1, y1;
-			tile_rect(means2D[2 * idx], means2D[2 * idx + 1], radii[idx], gx, gy, &x0, &y0, &x1, &y1);
+			tile_rect_any(means2D[2 * idx], means2D[2 * idx + 1], radii[idx], gx, gy, &x0, &y0, &x1, &y1);
 			uint32_t dbits;
 			memcpy(&dbits, &depths[idx], 4);
 			for (int y = y0; y < y1; y++)
 				for (int x = x0; x < x1; x++) {
-					uint64_t key = (uint64_t)(y * gx + x);
+					uint64_t key = (uint64_t)(y * gx + (x >= gx ? x - gx : x));
 					key <<= 32;
 					key |= dbits;
 					keys_unsorted[off] = key;
@@ -410,7 +433,7 @@ void ogs_oracle_render_fwd(
 					for (uint32_t k = r0; k < r1; k++) {
 						contributor++;
 						uint32_t id = point_list[k];
-						float dx = means2D[2 * id] - pixf[0], dy = means2D[2 * id + 1] - pixf[1];
+						float dx = nearest_copy_x(means2D[2 * id], tx * TILE + 7.5f, (float)W) - pixf[0], dy = means2D[2 * id + 1] - pixf[1];
 						const float* co = conic_opacity + 4 * (size_t)id;
 						float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
 						if (power > 0.0f) continue;
@@ -473,7 +496,7 @@ void ogs_oracle_render_bwd(
 						contributor--;
 						if (contributor >= (uint32_t)last_contributor) continue; /* int promoted to unsigned, :767 */
 						uint32_t id = point_list[k];
-						float dx = means2D[2 * id] - pixf[0], dy = means2D[2 * id + 1] - pixf[1];
+						float dx = nearest_copy_x(means2D[2 * id], tx * TILE + 7.5f, (float)W) - pixf[0], dy = means2D[2 * id + 1] - pixf[1];
 						const float* co = conic_opacity + 4 * (size_t)id;
 						float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
 						if (power > 0.0f) continue;

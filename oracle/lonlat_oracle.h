@@ -21,6 +21,15 @@
 extern "C" {
 #endif
 
+/*
+ * Seam wrap-around switch (process-global, default 0 = the reference's live behaviour).  With 1 the
+ * oracle follows the NON-parity extension of omnigs_b200.h (ogs_set_seam_wrap): x tile range modulo the
+ * grid as sketched by the reference's unused getRectCyclic (auxiliary.h:68-83), each tile blends the
+ * nearest copy (x, x-W, x+W) of a Gaussian.  No reference output exists for this mode; it is checked by
+ * the yaw-invariance property (tests/test_seam_wrap.py).
+ */
+void ogs_oracle_set_seam_wrap(int on);
+
 /* threads the OpenMP build will use (1 when built without OpenMP) */
 int ogs_oracle_num_threads(void);
 

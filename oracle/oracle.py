@@ -32,6 +32,11 @@ def lib():
     return _LIB
 
 
+def set_seam_wrap(on):
+    """Switch the oracle to the non-parity seam wrap-around extension (default off = reference behaviour)."""
+    lib().ogs_oracle_set_seam_wrap(1 if on else 0)
+
+
 def num_threads():
     return int(lib().ogs_oracle_num_threads())
 
