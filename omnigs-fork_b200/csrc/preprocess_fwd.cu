@@ -107,8 +107,10 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 					// opt-in extension: x range modulo the tile grid (cf. the reference's unused getRectCyclic,
 					// auxiliary.h:68-83).  x0 in [0, gx), x1 = x0 + width <= x0 + gx.
 					const float R = (float)(int)my_radius;
-					const int xa = (int)floorf((point_image.x - R) * (1.0f / kTile));
-					const int xb = (int)floorf((point_image.x + R) * (1.0f / kTile)) + 1;
+					// same expressions as getRect (auxiliary.h:59,63) with floor instead of clamp-to-zero truncation,
+					// so rects that do not touch the seam are identical in both modes
+					const int xa = (int)floorf(__fmul_rn(__fsub_rn(point_image.x, R), 1.0f / kTile));
+					const int xb = (int)floorf(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(point_image.x, R), (float)kTile), -1.0f), 1.0f / kTile));
 					const int w = min(xb - xa, a.gx);
 					x0 = ((xa % a.gx) + a.gx) % a.gx;
 					x1 = x0 + w;

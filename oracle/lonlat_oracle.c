@@ -113,8 +113,9 @@ static void tile_rect_any(float px, float py, int max_radius, int gx, int gy, in
 	tile_rect(px, py, max_radius, gx, gy, x0, y0, x1, y1);
 	if (g_wrap) {
 		const float R = (float)max_radius;
-		int xa = (int)floorf((px - R) * (1.0f / TILE));
-		int xb = (int)floorf((px + R) * (1.0f / TILE)) + 1;
+		/* getRect's expressions (auxiliary.h:59,63) with floor instead of clamp-to-zero truncation */
+		int xa = (int)floorf((px - R) / TILE);
+		int xb = (int)floorf((px + R + TILE - 1) / TILE);
 		int w = imin(xb - xa, gx);
 		*x0 = ((xa % gx) + gx) % gx;
 		*x1 = *x0 + w;
