@@ -27,7 +27,8 @@ namespace ogs {
 constexpr int kAccStride = 9;
 constexpr int kBwdThreads = 64;                 // two warps per tile
 constexpr int kBwdSlots = 4;                    // pixels per lane (one per 8x4 sub-block)
-constexpr int kBwdPerThread = kBatch / kBwdThreads;
+constexpr int kBwdBatch = 128;                  // list entries staged per round
+constexpr int kBwdPerThread = kBwdBatch / kBwdThreads;
 
 // Sum v[0..7] and v8 over the 32 lanes.  On return lane L holds in `z` the total of value (L>>2)
 // (replicated over the 4 lanes of a quad) and every lane holds the total of v8 in `z8`.
@@ -61,7 +62,7 @@ OGS_D void warp_transpose_reduce9(const float (&v)[8], float v8, float& z, float
 	for (int o = 16; o > 0; o >>= 1) z8 += __shfl_xor_sync(full, z8, o);
 }
 
-__global__ void __launch_bounds__(kBwdThreads, 10) render_bwd_kernel(
+__global__ void __launch_bounds__(kBwdThreads, 14) render_bwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
 	const float* __restrict__ bg_color,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float* __restrict__ gb,
@@ -69,8 +70,8 @@ __global__ void __launch_bounds__(kBwdThreads, 10) render_bwd_kernel(
 	const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
 	const float* __restrict__ dL_dpixels, float* __restrict__ grad_acc /*[P,12]*/)
 {
-	__shared__ StagedEntry s_e[kBatch];
-	__shared__ float s_acc[kBatch * kAccStride];
+	__shared__ StagedEntry s_e[kBwdBatch];
+	__shared__ float s_acc[kBwdBatch * kAccStride];
 	__shared__ int s_warp_cnt[kBwdThreads / 32];
 	__shared__ int s_max_contrib;
 
@@ -125,9 +126,8 @@ __global__ void __launch_bounds__(kBwdThreads, 10) render_bwd_kernel(
 	if (my_max > 0) atomicMax(&s_max_contrib, my_max);
 	__syncthreads();
 	const int n = min((int)(range.y - range.x), s_max_contrib);
-	const int rounds = (n + kBatch - 1) / kBatch;
-	const bool seam_wrap = n > 0 && scalars[7] != 0ull;   // mode of the forward that built these lists
-	const float tile_cx = tx0 + 0.5f * (kTile - 1), Wf = (float)W;
+	const int rounds = (n + kBwdBatch - 1) / kBwdBatch;
+	const float wrap_W = (n > 0 && scalars[7] != 0ull) ? (float)W : 0.f;   // > 0: seam wrap-around mode of this frame
 
 	for (int round = 0; round < rounds; round++) {
 		// ---- gather (reverse list order, 4 consecutive entries per thread), tile-level cull ----
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kBwdThreads, 10) render_bwd_kernel(
 		int my_keep = 0;
 #pragma unroll
 		for (int q = 0; q < kBwdPerThread; q++) {
-			pos[q] = n - 1 - (round * kBatch + tid * kBwdPerThread + q);   // 0-based list position
+			pos[q] = n - 1 - (round * kBwdBatch + tid * kBwdPerThread + q);   // 0-based list position
 			id[q] = (pos[q] >= 0) ? point_list[range.x + pos[q]] : 0u;
 		}
 #pragma unroll
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kBwdThreads, 10) render_bwd_kernel(
 				a[q] = g0[id[q]];
 				b[q] = g1[id[q]];
 				cb[q] = gb[id[q]];
-				if (seam_wrap) a[q].x = nearest_copy_x(a[q].x, tile_cx, Wf);
+				if (wrap_W > 0.f) a[q].x = nearest_copy_x(a[q].x, tx0 + 0.5f * (kTile - 1), wrap_W);
 				tau[q] = alpha_power_threshold(b[q].y);
 				keep[q] = gaussian_touches_box(a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, tau[q], tx0, ty0, tx1, ty1);
 			}

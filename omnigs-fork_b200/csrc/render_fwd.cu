@@ -17,7 +17,7 @@
 
 namespace ogs {
 
-__global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
+__global__ void __launch_bounds__(kRenderThreads, 5) render_fwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float* __restrict__ gb,
 	const unsigned long long* __restrict__ scalars, const float* __restrict__ bg_color,
@@ -44,8 +44,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 	const uint2 range = ranges[tile];
 	const int n = (int)(range.y - range.x);
 	const int rounds = (n + kBatch - 1) / kBatch;
-	const bool seam_wrap = n > 0 && scalars[7] != 0ull;   // mode of the forward that built these lists
-	const float tile_cx = tx0 + 0.5f * (kTile - 1), Wf = (float)W;
+	const float wrap_W = (n > 0 && scalars[7] != 0ull) ? (float)W : 0.f;   // > 0: seam wrap-around mode of this frame
 
 	bool done = !inside;
 	float T = 1.0f;
@@ -66,7 +65,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_fwd_kernel(
 			a = g0[id];
 			b = g1[id];
 			cb = gb[id];
-			if (seam_wrap) a.x = nearest_copy_x(a.x, tile_cx, Wf);
+			if (wrap_W > 0.f) a.x = nearest_copy_x(a.x, tx0 + 0.5f * (kTile - 1), wrap_W);
 			tau = alpha_power_threshold(b.y);
 			keep = gaussian_touches_box(a.x, a.y, a.z, a.w, b.x, tau, tx0, ty0, tx1, ty1);
 		}
