@@ -117,10 +117,12 @@ OGS_API int ogs_lonlat_backward(
 /*
  * The two halves of ogs_lonlat_backward, for callers that exchange data between them (latitude bands,
  * SURVEY.md §8(e-b)): ..._render zero-fills the packed accumulators ([P,12] float at byte
- * ogs_grad_acc_offset(P) of the 256-byte-aligned geometry buffer: dL_dmean2D.xy, dL_dconic.x.y.w,
- * dL_dopacity, dL_dcolour.rgb, 3 pad) and replays the blend of this rank's tiles into them
+ * ogs_grad_acc_offset(P) of the 256-byte-aligned geometry buffer: per-Gaussian raw sums over pixels
+ * u*dx, u*dy, u*dx^2, u*dx*dy, u*dy^2 (u = dL/dG * G), G*dL/dalpha, colour.rgb terms, 3 pad — linear in
+ * the pixels, so band partials add up) and replays the blend of this rank's tiles into them
  * (backward.cu:672-843); the caller may sum them over ranks (48 B/Gaussian instead of 324);
- * ..._finish runs the fused per-Gaussian backward (backward.cu:297-485, :613-669) from them.
+ * ..._finish applies the conic factors (backward.cu:821-836) and runs the fused per-Gaussian backward
+ * (backward.cu:297-485, :613-669) from them.
  */
 OGS_API int ogs_lonlat_backward_render(
 	int P, int64_t num_rendered, int W, int H, const float* background,

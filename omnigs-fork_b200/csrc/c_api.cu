@@ -436,6 +436,7 @@ OGS_API int ogs_lonlat_backward_finish(
 	a.means3D = means3D; a.shs = shs; a.scales = scales; a.rotations = rotations;
 	a.cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
 	a.viewmatrix = viewmatrix; a.campos = campos; a.radii = radii; a.clamped = g.clamped; a.grad_acc = g.grad_acc;
+	a.g0 = g.g0; a.g1 = g.g1;
 	a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
 	a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = shs ? dL_dsh : nullptr;
 	a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
@@ -445,8 +446,8 @@ OGS_API int ogs_lonlat_backward_finish(
 	return rc;
 }
 
-// Byte offset of the packed render-backward accumulators ([P,12] float: dL_dmean2D.xy, dL_dconic.x.y.w,
-// dL_dopacity, dL_dcolour.rgb, 3 pad) inside a 256-byte aligned geometry buffer.
+// Byte offset of the packed render-backward accumulators ([P,12] float, raw sums over pixels: u*dx, u*dy,
+// u*dx^2, u*dx*dy, u*dy^2, G*dL/dalpha, colour.rgb terms, 3 pad; linear, so band partials add up) inside a 256-byte aligned geometry buffer.
 OGS_API size_t ogs_grad_acc_offset(int P)
 {
 	if (P <= 0) return 0;

@@ -42,7 +42,9 @@ struct PreprocessBwdArgs {
 	const float* campos;
 	const int* radii;
 	const uint8_t* clamped;
-	const float* grad_acc;
+	const float* grad_acc;   // [P,12] raw render-backward sums
+	const float4* g0;        // conic.xy in .zw
+	const float4* g1;        // conic.z in .x
 	float* dL_dmean2D;
 	float* dL_dconic;
 	float* dL_dopacity;

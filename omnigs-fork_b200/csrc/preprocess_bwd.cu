@@ -3,7 +3,8 @@
 // One kernel does what the reference spreads over computeCov2DLonLatCUDA + preprocessLonLatCUDA
 // (cuda_rasterizer/backward.cu:297-485, :613-669) plus the zero-fills of its LibTorch shim
 // (src/rasterize_points.cu:200-208,246-247):
-//   packed render-backward accumulators -> dL/dmean2D, dL/dconic, dL/dopacity, dL/dcolour,
+//   packed render-backward accumulators (raw per-Gaussian sums over pixels, render_bwd.cu) x conic
+//   -> dL/dmean2D, dL/dconic, dL/dopacity, dL/dcolour (backward.cu:821-840),
 //   conic/covariance branch (incl. the projection's second derivatives) -> dL/dcov3D, dL/dmean,
 //   screen-position branch through the Jacobian rows (kept in registers; the reference round-trips
 //   them through the dpx_dt / dpy_dt tensors) -> dL/dmean,
@@ -50,10 +51,16 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 
 	float g[9];
 	if (visible) {
+		// raw sums  Su_dx, Su_dy, Su_dx2, Su_dxdy, Su_dy2 (u = dL/dG * G), S G*dL/dalpha, S colour terms
 		const float4* row = reinterpret_cast<const float4*>(a.grad_acc + (size_t)idx * 12);
 		const float4 r0 = row[0], r1 = row[1];
-		g[0] = r0.x; g[1] = r0.y; g[2] = r0.z; g[3] = r0.w;
-		g[4] = r1.x; g[5] = r1.y; g[6] = r1.z; g[7] = r1.w;
+		const float4 c0 = a.g0[idx];
+		const float A = c0.z, B = c0.w, C = a.g1[idx].x;
+		const float ddelx_dx = 0.5 * a.W, ddely_dy = 0.5 * a.H;
+		g[0] = -ddelx_dx * (A * r0.x + B * r0.y);
+		g[1] = -ddely_dy * (C * r0.y + B * r0.x);
+		g[2] = -0.5f * r0.z; g[3] = -0.5f * r0.w;
+		g[4] = -0.5f * r1.x; g[5] = r1.y; g[6] = r1.z; g[7] = r1.w;
 		g[8] = a.grad_acc[(size_t)idx * 12 + 8];
 	} else {
 #pragma unroll

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 	uint32_t my_tiles = 0;
 	int out_radius = 0;
 	uint32_t key = 0xFFFFFFFFu;
-	bool emits = false;           // visible inside this band: needs a packed record and tile instances
+	bool emits = false;           // visible inside this band: needs tile instances
 	bool visible = false;         // visible in the full frame (radii > 0): needs its SH clamp mask
 	float3 p_orig = { 0.f, 0.f, 0.f }, conic = { 0.f, 0.f, 0.f };
 	float2 point_image = { 0.f, 0.f };
@@ -158,11 +158,12 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 			        a.colors_precomp[3 * (size_t)idx + 2] };
 		}
 		a.clamped[idx] = (uint8_t)cmask;
+		// so is the packed record: its conic turns the summed raw accumulators into gradients (preprocess_bwd.cu)
+		a.g0[idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+		a.g1[idx] = make_float4(conic.z, a.opacities[idx], rgb.x, rgb.y);
+		a.gb[idx] = rgb.z;
 		if (emits) {
 			a.depth[idx] = r;
-			a.g0[idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-			a.g1[idx] = make_float4(conic.z, a.opacities[idx], rgb.x, rgb.y);
-			a.gb[idx] = rgb.z;
 			a.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));
 			my_tiles = (uint32_t)((by1 - by0) * (x1 - x0));
 			key = __float_as_uint(r);

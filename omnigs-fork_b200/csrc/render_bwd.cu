@@ -13,18 +13,19 @@
 //   * per visited entry every lane adds up, over its (up to four) contributing pixels, nine raw sums:
 //       u*dx, u*dy, u*dx^2, u*dx*dy, u*dy^2 (u = dL/dG * G), G*dL/dalpha and the three colour terms.
 //     They are reduced over the warp with ONE transposing butterfly (14 shuffles for 9 values) —
-//     the fixed cost per entry is paid once per 128 pixels, not once per 32 — combined across the
-//     two warps in shared memory, turned into the reference's quantities once per (tile, Gaussian)
+//     the fixed cost per entry is paid once per 128 pixels, not once per 32 — and go to L2 as they are:
+//     one red.global.add.f32 instruction per (half-tile, Gaussian) whose nine active lanes cover 36
+//     contiguous bytes of the Gaussian's packed 12-float accumulator row.  The raw sums are linear in the
+//     pixels, so the conic factors of the reference's quantities
 //       dL/dmean2D.x = -(W/2) (A Su_dx + B Su_dy),  dL/dconic.x = -1/2 Su_dx2, ...
-//     and flushed with one vectorised L2 reduction set: 2 x red.global.add.v4.f32 + 1 x red.global.add.f32
-//     into a packed 12-float accumulator row.
+//     are applied once per Gaussian by the per-Gaussian backward (preprocess_bwd.cu), not here.
 // Summation order differs from the reference's (unordered) atomics; parity is within the stated tolerance.
 #include "render_common.cuh"
 #include "launchers.cuh"
+#include <cstdlib>
 
 namespace ogs {
 
-constexpr int kAccStride = 9;
 constexpr int kBwdThreads = 64;                 // two warps per tile
 constexpr int kBwdSlots = 4;                    // pixels per lane (one per 8x4 sub-block)
 constexpr int kBwdBatch = 128;                  // list entries staged per round
@@ -62,7 +63,8 @@ OGS_D void warp_transpose_reduce9(const float (&v)[8], float v8, float& z, float
 	for (int o = 16; o > 0; o >>= 1) z8 += __shfl_xor_sync(full, z8, o);
 }
 
-__global__ void __launch_bounds__(kBwdThreads, 14) render_bwd_kernel(
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
 	const float* __restrict__ bg_color,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float* __restrict__ gb,
@@ -71,7 +73,6 @@ __global__ void __launch_bounds__(kBwdThreads, 14) render_bwd_kernel(
 	const float* __restrict__ dL_dpixels, float* __restrict__ grad_acc /*[P,12]*/)
 {
 	__shared__ StagedEntry s_e[kBwdBatch];
-	__shared__ float s_acc[kBwdBatch * kAccStride];
 	__shared__ int s_warp_cnt[kBwdThreads / 32];
 	__shared__ int s_max_contrib;
 
@@ -117,8 +118,6 @@ __global__ void __launch_bounds__(kBwdThreads, 14) render_bwd_kernel(
 		}
 		neg_Tfinal_bg[s] = -T_final * bg_dot;   // (-T_final / (1 - alpha)) * bg_dot = this * 1/(1 - alpha)
 	}
-	const float ddelx_dx = 0.5 * W;
-	const float ddely_dy = 0.5 * H;
 
 	// entries at list positions >= max(n_contrib) of the tile were blended by no pixel
 	if (tid == 0) s_max_contrib = 0;
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(kBwdThreads, 14) render_bwd_kernel(
 			if (lane >= o) incl += u;
 		}
 		if (lane == 31) s_warp_cnt[warp] = incl;
-		__syncthreads();   // also orders the previous round's flush before s_e / s_acc are rewritten
+		__syncthreads();   // every warp has finished replaying the previous round's s_e
 		int slot = incl - my_keep + (warp == 1 ? s_warp_cnt[0] : 0);
 		const int total = s_warp_cnt[0] + s_warp_cnt[1];
 #pragma unroll
@@ -175,7 +174,6 @@ __global__ void __launch_bounds__(kBwdThreads, 14) render_bwd_kernel(
 				slot++;
 			}
 		}
-		for (int k = tid; k < total * kAccStride; k += kBwdThreads) s_acc[k] = 0.f;
 		__syncthreads();
 
 		// ---- per-warp replay over the entries that can reach this half-tile ----
@@ -256,32 +254,10 @@ __global__ void __launch_bounds__(kBwdThreads, 14) render_bwd_kernel(
 				if (!__any_sync(0xffffffffu, any_valid)) continue;
 				float z, z8;
 				warp_transpose_reduce9(r, r8, z, z8);
-				// lanes 0,4,..,28 hold sums 0..7, lane 1 takes the ninth: one shared-memory atomic pass
+				// lanes 0,4,..,28 hold sums 0..7, lane 1 takes the ninth: one 9-lane L2 reduction
 				const bool ninth = (lane == 1);
 				if ((lane & 3) == 0 || ninth)
-					atomicAdd(&s_acc[j * kAccStride + (ninth ? 8 : (lane >> 2))], ninth ? z8 : z);
-			}
-		}
-		__syncthreads();
-
-		// ---- flush: raw sums -> the reference's quantities, one packed reduction set per (tile, Gaussian) ----
-		for (int k = tid; k < total; k += kBwdThreads) {
-			const float* acc = &s_acc[k * kAccStride];
-			float r[9];
-			bool nz = false;
-#pragma unroll
-			for (int i = 0; i < 9; i++) {
-				r[i] = acc[i];
-				nz |= (r[i] != 0.f);
-			}
-			if (nz) {
-				const float4 ea = s_e[k].a;
-				const float A = ea.z, B = ea.w, C = s_e[k].b.x;
-				float* dst = grad_acc + (size_t)__float_as_uint(s_e[k].c.w) * 12;
-				// dL/dmean2D = dL/dG * dG/ddel * ddel/dx summed; dL/dconic = -1/2 * sum u d d^T  (backward.cu:821-836)
-				red_add_v4(dst, -ddelx_dx * (A * r[0] + B * r[1]), -ddely_dy * (C * r[1] + B * r[0]), -0.5f * r[2], -0.5f * r[3]);
-				red_add_v4(dst + 4, -0.5f * r[4], r[5], r[6], r[7]);
-				red_add(dst + 8, r[8]);
+					red_add(grad_acc + (size_t)__float_as_uint(ec.w) * 12 + (ninth ? 8 : (lane >> 2)), ninth ? z8 : z);
 			}
 		}
 	}
@@ -293,8 +269,18 @@ int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, in
                       float* grad_acc, cudaStream_t st)
 {
 	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
-	render_bwd_kernel<<<gx * gy, kBwdThreads, 0, st>>>(ranges, point_list, W, H, gx, bg, g0, g1, gb, scalars,
-	                                                  final_T, n_contrib, dL_dpix, grad_acc);
+	// resident CTAs per SM the kernel is compiled for (register budget); OGS_BWD_MINBLOCKS is a tuning knob
+	static const int variant = [] { const char* e = getenv("OGS_BWD_MINBLOCKS"); return e ? atoi(e) : 16; }();
+#define OGS_BWD_LAUNCH(MB) render_bwd_kernel<MB><<<gx * gy, kBwdThreads, 0, st>>>(ranges, point_list, W, H, gx, bg, g0, g1, gb, \
+	                                                                      scalars, final_T, n_contrib, dL_dpix, grad_acc)
+	switch (variant) {
+	case 8: OGS_BWD_LAUNCH(8); break;
+	case 10: OGS_BWD_LAUNCH(10); break;
+	case 12: OGS_BWD_LAUNCH(12); break;
+	case 14: OGS_BWD_LAUNCH(14); break;
+	default: OGS_BWD_LAUNCH(16); break;
+	}
+#undef OGS_BWD_LAUNCH
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }
