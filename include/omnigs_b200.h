@@ -16,6 +16,14 @@
  *     rasterizer.h:98-100, rasterizer_impl.cu:185-192
  *   required<GeometryState/ImageState/BinningState>(n)         ogs_geom_bytes / ogs_img_bytes /
  *     rasterizer_impl.h:96-102, rasterizer_impl.cu:198-245       ogs_binning_bytes
+ *   model activations + rasterizer + their autograd            ogs_lonlat_forward_raw_stage1 /
+ *     gaussian_model.cpp:54-77, gaussian_renderer.cpp:212-258    ogs_lonlat_backward_raw
+ *   loss_utils::l1_loss / ssim + autograd                      ogs_photometric_loss
+ *     loss_utils.h:31-34,58-131, gaussian_mapper.cpp:391-413
+ *   torch::optim::Adam::step over the six groups               ogs_adam_step
+ *     gaussian_model.cpp:485-511
+ *   max_radii2D / addDensificationStats                        ogs_densify_stats
+ *     gaussian_mapper.cpp:427-434, gaussian_model.cpp:839-853
  *
  * The reference passes std::function<char*(size_t)> allocators (rasterize_points.cu:41-47,92-94);
  * a C ABI cannot, so the forward is split in two at the one point where a buffer size depends on a
@@ -187,6 +195,67 @@ OGS_API int ogs_lonlat_train_view_host(
 	float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
 	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
 	int64_t* num_rendered_host, size_t* binning_needed, void* stream);
+
+/*
+ * Raw-parameter entry points.  Before every render the reference turns the model's
+ * stored tensors into the rasterizer's arguments with separate LibTorch ops — opacity = sigmoid(opacity_),
+ * scales = exp(scaling_), rotations = normalize(rotation_), shs = cat(features_dc_, features_rest_)
+ * (src/gaussian_model.cpp:54-77, called from src/gaussian_renderer.cpp:212-258) — and autograd walks the
+ * same ops backwards.  These calls take the stored tensors themselves:
+ *   xyz [P,3], features_dc [P,1,3], features_rest [P,M-1,3], opacity_raw [P,1] (logit),
+ *   scaling_raw [P,3] (log), rotation_raw [P,4] (unnormalised w,x,y,z)
+ * and return gradients with respect to them (what the optimiser's six parameter groups receive,
+ * gaussian_model.cpp:485-511).  Stage 2 is ogs_lonlat_forward_stage2, unchanged.  dL_dmean2D [P,3]
+ * (optional, NULL to skip) is the screen-space gradient the densification statistics use.
+ * Every output element is written.
+ */
+OGS_API int ogs_lonlat_forward_raw_stage1(
+	int P, int D, int M, int W, int H,
+	const float* xyz, const float* features_dc, const float* features_rest, const float* opacity_raw,
+	const float* scaling_raw, float scale_modifier, const float* rotation_raw,
+	const float* viewmatrix, const float* campos,
+	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, void* stream);
+OGS_API int ogs_lonlat_backward_raw(
+	int P, int D, int M, int64_t num_rendered, int W, int H, const float* background,
+	const float* xyz, const float* features_dc, const float* features_rest,
+	const float* scaling_raw, float scale_modifier, const float* rotation_raw,
+	const float* viewmatrix, const float* campos, const int* radii,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, const float* dL_dpix,
+	float* dL_dmean2D, float* dL_dxyz, float* dL_dfeatures_dc, float* dL_dfeatures_rest,
+	float* dL_dopacity_raw, float* dL_dscaling_raw, float* dL_drotation_raw, void* stream);
+
+/*
+ * The training iteration either side of the rasterizer (SURVEY.md §8 f-3;
+ * GaussianMapper::trainForOneIteration, src/gaussian_mapper.cpp:391-434).
+ *
+ * ogs_photometric_loss: loss = (1 - lambda) * L1 + lambda * (1 - SSIM) between rendered * mask and gt
+ * (gaussian_mapper.cpp:391-413; l1_loss and ssim of include/loss_utils.h:31-34,58-131: 11x11 Gaussian
+ * window, sigma 1.5, zero padding, mean over all elements), forward AND backward: writes
+ * loss_out[3] = {loss, L1, SSIM} (device) and dL_dpix [3,H,W] = dloss/drendered.  mask is NULL, [1,H,W]
+ * (mask_channels 1) or [3,H,W] (3).  rows_used < H drops the bottom rows from the loss as
+ * skip_bottom_ratio does (gaussian_mapper.cpp:395-407); their dL_dpix is 0.  workspace: 8-byte aligned,
+ * ogs_photometric_loss_workspace_bytes(W, H) bytes.
+ *
+ * ogs_adam_step: one launch of torch::optim::Adam::step over up to 8 parameter groups (the reference's
+ * six: xyz, f_dc, f_rest, opacity, scaling, rotation with their own learning rates,
+ * gaussian_model.cpp:485-511; eps 1e-15, no weight decay, no amsgrad).  params/grads/exp_avg/exp_avg_sq
+ * are HOST arrays of device pointers, counts[g] elements each; `step` counts from 1; betas and eps are
+ * doubles as in torch::optim::AdamOptions (1 - beta and the bias corrections are evaluated in double).
+ *
+ * ogs_densify_stats: for every Gaussian with radii > 0: max_radii2D = max(max_radii2D, radii),
+ * xyz_gradient_accum += ||dL_dmean2D.xy||, denom += 1 (gaussian_mapper.cpp:427-434,
+ * gaussian_model.cpp:839-853).
+ */
+OGS_API size_t ogs_photometric_loss_workspace_bytes(int W, int H);
+OGS_API int ogs_photometric_loss(
+	int W, int H, int rows_used, float lambda_dssim, const float* rendered, const float* gt,
+	const float* mask, int mask_channels, char* workspace, float* loss_out, float* dL_dpix, void* stream);
+OGS_API int ogs_adam_step(
+	int groups, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+	const size_t* counts, const float* lrs, int64_t step, double beta1, double beta2, double eps, void* stream);
+OGS_API int ogs_densify_stats(
+	int P, const int* radii, const float* dL_dmean2D, float* max_radii2D, float* xyz_gradient_accum, float* denom,
+	void* stream);
 
 /*
  * Longitude-seam wrap-around (opt-in extension; off by default = reference parity).

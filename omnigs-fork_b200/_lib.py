@@ -37,6 +37,14 @@ SYMBOLS = {
     "ogs_mark_all_visible": (_c_int, [_c_int, _p, _p]),
     "ogs_export_geometry": (_c_int, [_c_int, _p] + [_p] * 7 + [_p]),
     "ogs_export_binning": (_c_int, [_c_int] * 3 + [_c_i64] + [_p] * 3 + [_p] * 5 + [_p]),
+    "ogs_lonlat_forward_raw_stage1": (_c_int, [_c_int] * 5 + [_p] * 5 + [_c_f] + [_p] * 3 + [_p] * 3
+                                      + [ctypes.POINTER(_c_i64), _p]),
+    "ogs_lonlat_backward_raw": (_c_int, [_c_int] * 3 + [_c_i64] + [_c_int] * 2 + [_p] + [_p] * 4 + [_c_f] + [_p] * 4
+                                + [_p] * 3 + [_p] + [_p] * 7 + [_p]),
+    "ogs_photometric_loss_workspace_bytes": (_c_sz, [_c_int, _c_int]),
+    "ogs_photometric_loss": (_c_int, [_c_int] * 3 + [_c_f] + [_p] * 3 + [_c_int] + [_p] * 3 + [_p]),
+    "ogs_adam_step": (_c_int, [_c_int] + [_p] * 6 + [_c_i64] + [ctypes.c_double] * 3 + [_p]),
+    "ogs_densify_stats": (_c_int, [_c_int] + [_p] * 5 + [_p]),
     "ogs_set_seam_wrap": (_c_int, [_c_int]),
     "ogs_get_seam_wrap": (_c_int, []),
     "ogs_profile_enable": (_c_int, [_c_int]),

@@ -22,6 +22,10 @@ OGS_D void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+OGS_D void mbar_arrive(uint64_t* bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 OGS_D void mbar_wait(uint64_t* bar, uint32_t parity)
 {
 	asm volatile(
@@ -52,6 +56,10 @@ OGS_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::
 
 constexpr int kShRowFloats = 48;     // 16 coefficients x RGB
 constexpr int kShPitchFloats = 52;   // 208-byte pitch
+// raw-parameter mode: the CTA's features_rest_ rows (45 floats each, contiguous) at the start of the
+// staging area, its features_dc_ rows (3 floats each) behind them
+constexpr int kRawRestFloats = 45;
+constexpr int kRawDcOffset = 128 * kRawRestFloats;   // 23040 B: 16-byte aligned
 
 // Host-side check: can the SH rows of this call go through the bulk path?
 inline bool sh_rows_bulk_capable(const void* base, int M)

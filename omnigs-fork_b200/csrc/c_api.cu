@@ -5,6 +5,7 @@
 // (reference cuda_rasterizer/rasterizer_impl.cu:540-697, :701-795, :185-192).
 #include "ogs_common.cuh"
 #include "launchers.cuh"
+#include <cmath>
 
 #include <cstdlib>
 #include <mutex>
@@ -229,8 +230,12 @@ int forward_stage1_impl(
 	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
 	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
 	const float* viewmatrix, const float* campos,
-	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, cudaStream_t st)
+	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, cudaStream_t st,
+	const float* features_dc = nullptr, const float* features_rest = nullptr)
 {
+	// raw-parameter mode: features_dc / features_rest given instead of shs; opacities, scales and rotations
+	// are then the stored (pre-activation) tensors
+	const bool raw = features_dc != nullptr;
 	if (P < 0 || !num_rendered_host) return fail(OGS_ERR_INVALID_ARG, "bad P / num_rendered_host");
 	if (int rc = check_image(W, H)) return rc;
 	*num_rendered_host = 0;
@@ -242,11 +247,14 @@ int forward_stage1_impl(
 
 	if (!means3D || !opacities || !viewmatrix || !campos || !radii || !geom_buffer)
 		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
-	if ((shs == nullptr) == (colors_precomp == nullptr))
+	if (raw) {
+		if (shs || colors_precomp || cov3D_precomp || !features_rest || !scales || !rotations || M < 2)
+			return fail(OGS_ERR_INVALID_ARG, "raw-parameter mode takes features_dc, features_rest, scaling and rotation only");
+	} else if ((shs == nullptr) == (colors_precomp == nullptr))
 		return fail(OGS_ERR_INVALID_ARG, "exactly one of shs / colors_precomp must be given");
 	if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
 		return fail(OGS_ERR_INVALID_ARG, "exactly one of (scales, rotations) / cov3D_precomp must be given");
-	if (shs && (M <= 0 || (D + 1) * (D + 1) > M || D < 0 || D > 3))
+	if ((shs || raw) && (M <= 0 || (D + 1) * (D + 1) > M || D < 0 || D > 3))
 		return fail(OGS_ERR_INVALID_ARG, "SH degree / coefficient count mismatch");
 	band_y0 = max(0, band_y0);
 	band_y1 = min(gy, band_y1);
@@ -263,6 +271,7 @@ int forward_stage1_impl(
 	a.scale_modifier = scale_modifier;
 	a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
 	a.scales = scales; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
+	a.raw = raw ? 1 : 0; a.features_dc = features_dc; a.features_rest = features_rest;
 	a.viewmatrix = viewmatrix; a.campos = campos; a.radii = radii;
 	a.g0 = g.g0; a.g1 = g.g1; a.gb = g.gb; a.depth = g.depth; a.rect = g.rect;
 	a.tiles_touched = g.tiles_touched; a.cov3D = g.cov3D; a.clamped = g.clamped;
@@ -473,6 +482,106 @@ OGS_API int ogs_lonlat_backward(
 	return ogs_lonlat_backward_finish(P, D, M, W, H, means3D, shs, scales, scale_modifier, rotations, cov3D_precomp,
 	                                  viewmatrix, campos, radii, geom_buffer, dL_dmean2D, dL_dconic, dL_dopacity,
 	                                  dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, stream);
+}
+
+// ---- raw-parameter entry points: activations and their backward inside the kernels
+OGS_API int ogs_lonlat_forward_raw_stage1(
+	int P, int D, int M, int W, int H,
+	const float* xyz, const float* features_dc, const float* features_rest, const float* opacity_raw,
+	const float* scaling_raw, float scale_modifier, const float* rotation_raw,
+	const float* viewmatrix, const float* campos,
+	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, void* stream)
+{
+	if (P > 0 && (!features_dc || !features_rest)) return fail(OGS_ERR_INVALID_ARG, "features_dc / features_rest are NULL");
+	const int gy = H > 0 ? ceil_div(H, kTile) : 0;
+	return forward_stage1_impl(P, D, M, W, H, 0, gy, xyz, nullptr, nullptr, opacity_raw, scaling_raw, scale_modifier,
+	                           rotation_raw, nullptr, viewmatrix, campos, radii, geom_buffer, img_buffer,
+	                           num_rendered_host, (cudaStream_t)stream, features_dc, features_rest);
+}
+
+OGS_API int ogs_lonlat_backward_raw(
+	int P, int D, int M, int64_t num_rendered, int W, int H, const float* background,
+	const float* xyz, const float* features_dc, const float* features_rest,
+	const float* scaling_raw, float scale_modifier, const float* rotation_raw,
+	const float* viewmatrix, const float* campos, const int* radii,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, const float* dL_dpix,
+	float* dL_dmean2D, float* dL_dxyz, float* dL_dfeatures_dc, float* dL_dfeatures_rest,
+	float* dL_dopacity_raw, float* dL_dscaling_raw, float* dL_drotation_raw, void* stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (int rc = ogs_lonlat_backward_render(P, num_rendered, W, H, background, geom_buffer, binning_buffer,
+	                                        img_buffer, dL_dpix, stream)) return rc;
+	if (P == 0) return OGS_OK;
+	if (!xyz || !features_dc || !features_rest || !scaling_raw || !rotation_raw || !viewmatrix || !campos || !radii ||
+	    !dL_dxyz || !dL_dfeatures_dc || !dL_dfeatures_rest || !dL_dopacity_raw || !dL_dscaling_raw || !dL_drotation_raw)
+		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	if (M < 2 || (D + 1) * (D + 1) > M || D < 0 || D > 3) return fail(OGS_ERR_INVALID_ARG, "SH degree / coefficient count mismatch");
+	GeomState g = GeomState::carve(geom_buffer, P);
+	PreprocessBwdArgs a{};
+	a.P = P; a.D = D; a.M = M; a.W = W; a.H = H; a.scale_modifier = scale_modifier;
+	a.means3D = xyz; a.scales = scaling_raw; a.rotations = rotation_raw; a.cov3D = g.cov3D;
+	a.viewmatrix = viewmatrix; a.campos = campos; a.radii = radii; a.clamped = g.clamped; a.grad_acc = g.grad_acc;
+	a.g0 = g.g0; a.g1 = g.g1;
+	a.raw = 1; a.features_dc = features_dc; a.features_rest = features_rest;
+	a.dL_dfeatures_dc = dL_dfeatures_dc; a.dL_dfeatures_rest = dL_dfeatures_rest;
+	a.dL_dmean2D = dL_dmean2D; a.dL_dopacity = dL_dopacity_raw; a.dL_dmean3D = dL_dxyz;
+	a.dL_dscale = dL_dscaling_raw; a.dL_drot = dL_drotation_raw;
+	prof_begin(OGS_PROF_PREPROCESS_BWD, st);
+	const int rc = launch_preprocess_bwd(a, st);
+	prof_end(OGS_PROF_PREPROCESS_BWD, st);
+	return rc;
+}
+
+// ---- the training step either side of the rasterizer
+OGS_API size_t ogs_photometric_loss_workspace_bytes(int W, int H)
+{
+	return (W > 0 && H > 0) ? photometric_loss_workspace_bytes(W, H) : 0;
+}
+
+OGS_API int ogs_photometric_loss(
+	int W, int H, int rows_used, float lambda_dssim, const float* rendered, const float* gt,
+	const float* mask, int mask_channels, char* workspace, float* loss_out, float* dL_dpix, void* stream)
+{
+	if (int rc = check_image(W, H)) return rc;
+	if (rows_used <= 0 || rows_used > H) return fail(OGS_ERR_INVALID_ARG, "rows_used must be in (0, H]");
+	if (!rendered || !gt || !workspace || !loss_out || !dL_dpix) return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	if (mask && mask_channels != 1 && mask_channels != 3) return fail(OGS_ERR_INVALID_ARG, "mask_channels must be 1 or 3");
+	if (reinterpret_cast<uintptr_t>(workspace) & 7u) return fail(OGS_ERR_INVALID_ARG, "workspace must be 8-byte aligned");
+	return launch_photometric_loss(W, H, rows_used, lambda_dssim, rendered, gt, mask, mask_channels,
+	                               reinterpret_cast<float*>(workspace), loss_out, dL_dpix, (cudaStream_t)stream);
+}
+
+OGS_API int ogs_adam_step(
+	int groups, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+	const size_t* counts, const float* lrs, int64_t step, double beta1, double beta2, double eps, void* stream)
+{
+	if (groups < 0 || groups > kAdamMaxGroups) return fail(OGS_ERR_INVALID_ARG, "between 0 and 8 parameter groups");
+	if (step < 1) return fail(OGS_ERR_INVALID_ARG, "step counts from 1");
+	if (groups && (!params || !grads || !exp_avg || !exp_avg_sq || !counts || !lrs)) return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	AdamLaunch a{};
+	a.groups = groups; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps;
+	// torch/csrc/api/src/optim/adam.cpp: bias corrections and step size in double
+	const double bc1 = 1.0 - std::pow(beta1, (double)step);
+	const double bc2 = 1.0 - std::pow(beta2, (double)step);
+	a.sqrt_bias_correction2 = (float)std::sqrt(bc2);
+	a.one_minus_beta1 = (float)(1.0 - beta1);
+	a.one_minus_beta2 = (float)(1.0 - beta2);
+	for (int g = 0; g < groups; g++) {
+		if (counts[g] && (!params[g] || !grads[g] || !exp_avg[g] || !exp_avg_sq[g]))
+			return fail(OGS_ERR_INVALID_ARG, "a parameter group has a NULL tensor");
+		a.group[g] = AdamGroup{ params[g], grads[g], exp_avg[g], exp_avg_sq[g], counts[g], (float)((double)lrs[g] / bc1) };
+	}
+	return launch_adam(a, (cudaStream_t)stream);
+}
+
+OGS_API int ogs_densify_stats(
+	int P, const int* radii, const float* dL_dmean2D, float* max_radii2D, float* xyz_gradient_accum, float* denom,
+	void* stream)
+{
+	if (P < 0) return fail(OGS_ERR_INVALID_ARG, "bad P");
+	if (P > 0 && (!radii || !dL_dmean2D || !max_radii2D || !xyz_gradient_accum || !denom))
+		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	return launch_densify_stats(P, radii, dL_dmean2D, max_radii2D, xyz_gradient_accum, denom, (cudaStream_t)stream);
 }
 
 OGS_API int ogs_mark_all_visible(int P, uint8_t* present, void* stream)

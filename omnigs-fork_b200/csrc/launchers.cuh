@@ -15,6 +15,11 @@ struct PreprocessFwdArgs {
 	const float* scales;
 	const float* rotations;
 	const float* cov3D_precomp;
+	// raw-parameter mode (raw != 0): opacities / scales / rotations hold the stored (pre-activation)
+	// tensors and the SH row is split into features_dc [P,1,3] and features_rest [P,M-1,3]
+	int raw;
+	const float* features_dc;
+	const float* features_rest;
 	const float* viewmatrix;
 	const float* campos;
 	int* radii;
@@ -44,7 +49,15 @@ struct PreprocessBwdArgs {
 	const uint8_t* clamped;
 	const float* grad_acc;   // [P,12] raw render-backward sums
 	const float4* g0;        // conic.xy in .zw
-	const float4* g1;        // conic.z in .x
+	const float4* g1;        // conic.z in .x, activated opacity in .y
+	// raw-parameter mode (raw != 0): scales / rotations are the stored tensors, the SH row is split, and the
+	// outputs are gradients w.r.t. the stored tensors (dL_dopacity, dL_dscale, dL_drot, dL_dfeatures_*);
+	// dL_dmean2D and dL_dcov3D are optional, dL_dcolor / dL_dsh unused
+	int raw;
+	const float* features_dc;
+	const float* features_rest;
+	float* dL_dfeatures_dc;
+	float* dL_dfeatures_rest;
 	float* dL_dmean2D;
 	float* dL_dconic;
 	float* dL_dopacity;
@@ -71,6 +84,32 @@ int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, in
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
                       float* grad_acc, cudaStream_t st);
 int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st);
+
+// ---- train_step.cu: the per-iteration work either side of the rasterizer
+size_t photometric_loss_workspace_bytes(int W, int H);
+int launch_photometric_loss(int W, int H, int H_used, float lambda_dssim, const float* rendered, const float* gt,
+                            const float* mask, int mask_channels, float* workspace, float* loss_out, float* dL_dpix,
+                            cudaStream_t st);
+constexpr int kAdamMaxGroups = 8;
+constexpr int kAdamPerBlock = 1024;
+struct AdamGroup {
+	float* param;
+	const float* grad;
+	float* exp_avg;
+	float* exp_avg_sq;
+	size_t n;
+	float step_size;             // lr / (1 - beta1^t), evaluated in double on the host like torch::optim::Adam
+};
+struct AdamLaunch {
+	int groups;
+	int first_block[kAdamMaxGroups + 1];
+	float beta1, beta2, eps, sqrt_bias_correction2;
+	float one_minus_beta1, one_minus_beta2;   // 1 - beta evaluated in double (1 - 0.999f is off by 1.3e-5)
+	AdamGroup group[kAdamMaxGroups];
+};
+int launch_adam(AdamLaunch a, cudaStream_t st);
+int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D,
+                         float* xyz_gradient_accum, float* denom, cudaStream_t st);
 
 
 } // namespace ogs

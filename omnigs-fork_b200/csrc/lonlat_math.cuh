@@ -186,6 +186,18 @@ OGS_D void tile_rect_p(float2 p, int max_radius, int gx, int gy, int& x0, int& y
 	x1 = min(gx, max(0, (int)__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p.x, R), (float)kTile), -1.0f), inv)));
 	y1 = min(gy, max(0, (int)__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p.y, R), (float)kTile), -1.0f), inv)));
 }
+// The model's activations (gaussian_model.cpp:54-77) as LibTorch evaluates them in float32:
+// sigmoid(x) = 1 / (1 + exp(-x)); normalize(q) = q / max(||q||_2, 1e-12).
+OGS_D float sigmoid_act(float x) { return 1.0f / (1.0f + expf(-x)); }
+OGS_D float quat_norm_clamped(float4 q)
+{
+	return fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+}
+OGS_D float4 normalize_quat(float4 q)
+{
+	const float n = quat_norm_clamped(q);
+	return make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+}
 OGS_D void cov3d_from_scale_rot_p(float3 scale, float mod, float4 q, float* cov6)
 {
 	const float r = q.x, x = q.y, y = q.z, z = q.w;

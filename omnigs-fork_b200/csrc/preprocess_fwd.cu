@@ -11,6 +11,13 @@
 //   * the depth-sort key (float bits of r; 0xFFFFFFFF for Gaussians that emit nothing).
 // The 192-byte SH rows of the CTA are fetched by the bulk-copy engine (cp.async.bulk + mbarrier) while
 // the threads do the projection math; see async_copy.cuh.
+//
+// Raw-parameter mode: the kernel reads the model's stored tensors and applies the
+// activations the reference applies with separate LibTorch ops before every render
+// (gaussian_model.cpp:54-77 via gaussian_renderer.cpp:212-258): opacity = sigmoid(opacity_),
+// scales = exp(scaling_), rotations = normalize(rotation_), SH row = cat(features_dc_, features_rest_).
+// The CTA's features_rest_ rows (128 x 180 B, contiguous) and features_dc_ rows (128 x 12 B) come in as
+// two bulk copies; a thread reads its row with a 45-word stride (conflict-free).
 #include "lonlat_math.cuh"
 #include "launchers.cuh"
 #include "async_copy.cuh"
@@ -19,9 +26,13 @@ namespace ogs {
 
 constexpr int kPreThreads = 128;
 
-template <bool kBulkSH>
+// kMode: 0 SH rows by plain loads, 1 SH rows [P,16,3] by per-row bulk copies,
+//        2 raw parameters with split SH by per-CTA bulk copies, 3 raw parameters by plain loads.
+template <int kMode>
 __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(const PreprocessFwdArgs a)
 {
+	constexpr bool kBulkSH = (kMode == 1 || kMode == 2);
+	constexpr bool kRaw = (kMode >= 2);
 	__shared__ float sV[16];
 	__shared__ float sCam[3];
 	__shared__ unsigned long long s_block_tiles;
@@ -37,12 +48,30 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 		if (kBulkSH) {
 			const int rows = min(kPreThreads, a.P - (int)blockIdx.x * kPreThreads);
 			mbar_init(&s_bar, 1);
-			mbar_arrive_expect_tx(&s_bar, (uint32_t)rows * kShRowFloats * 4u);
+			if constexpr (kMode == 2) {
+				// whole multiples of 4 rows keep both chunk sizes multiples of 16 bytes; <= 3 tail rows load plainly
+				const uint32_t rows4 = (uint32_t)rows & ~3u;
+				mbar_arrive_expect_tx(&s_bar, rows4 * kShRowFloats * 4u);
+				if (rows4) {
+					const size_t first = (size_t)blockIdx.x * kPreThreads;
+					bulk_load(&s_sh[0], a.features_rest + first * kRawRestFloats, rows4 * kRawRestFloats * 4u, &s_bar);
+					bulk_load(&s_sh[kRawDcOffset], a.features_dc + first * 3, rows4 * 12u, &s_bar);
+				}
+			} else {
+				mbar_arrive_expect_tx(&s_bar, (uint32_t)rows * kShRowFloats * 4u);
+			}
 		}
 	}
 	__syncthreads();
-	if (kBulkSH && idx < a.P)
+	if constexpr (kMode == 1) if (idx < a.P)
 		bulk_load(&s_sh[tid * kShPitchFloats], a.shs + (size_t)idx * kShRowFloats, kShRowFloats * 4u, &s_bar);
+	if constexpr (kMode == 2) if (idx < a.P) {
+		const int rows = min(kPreThreads, a.P - (int)blockIdx.x * kPreThreads);
+		if (tid >= (rows & ~3)) {
+			for (int k = 0; k < kRawRestFloats; k++) s_sh[tid * kRawRestFloats + k] = a.features_rest[(size_t)idx * kRawRestFloats + k];
+			for (int k = 0; k < 3; k++) s_sh[kRawDcOffset + tid * 3 + k] = a.features_dc[(size_t)idx * 3 + k];
+		}
+	}
 
 	uint32_t my_tiles = 0;
 	int out_radius = 0;
@@ -78,8 +107,12 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 #pragma unroll
 				for (int i = 0; i < 6; i++) cov6[i] = a.cov3D_precomp[6 * (size_t)idx + i];
 			} else {
-				const float3 sc = { a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2] };
-				const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+				float3 sc = { a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2] };
+				float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+				if (kRaw) {
+					sc = { expf(sc.x), expf(sc.y), expf(sc.z) };   // getScalingActivation, gaussian_model.cpp:54-57
+					q = normalize_quat(q);                          // getRotationActivation, :59-62
+				}
 				cov3d_from_scale_rot_p(sc, a.scale_modifier, q, cov6);
 #pragma unroll
 				for (int i = 0; i < 6; i++) a.cov3D[6 * (size_t)idx + i] = cov6[i];
@@ -137,7 +170,23 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 		unsigned cmask = 0;
 		if (a.colors_precomp == nullptr) {
 			V3 c;
-			if (kBulkSH) {
+			if constexpr (kMode == 2) {
+				float shr[kShRowFloats];
+#pragma unroll
+				for (int k = 0; k < 3; k++) shr[k] = s_sh[kRawDcOffset + tid * 3 + k];
+#pragma unroll
+				for (int k = 0; k < kRawRestFloats; k++) shr[3 + k] = s_sh[tid * kRawRestFloats + k];
+				auto sh = [&shr](int k) { return V3{ shr[3 * k], shr[3 * k + 1], shr[3 * k + 2] }; };
+				c = sh_to_rgb(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
+			} else if constexpr (kMode == 3) {
+				const float* dc = a.features_dc + (size_t)idx * 3;
+				const float* rest = a.features_rest + (size_t)idx * (a.M - 1) * 3;
+				auto sh = [dc, rest](int k) {
+					const float* p = k == 0 ? dc : rest + 3 * (k - 1);
+					return V3{ p[0], p[1], p[2] };
+				};
+				c = sh_to_rgb(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
+			} else if constexpr (kBulkSH) {
 				float shr[kShRowFloats];
 				const float4* row = reinterpret_cast<const float4*>(&s_sh[tid * kShPitchFloats]);
 #pragma unroll
@@ -160,7 +209,9 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 		a.clamped[idx] = (uint8_t)cmask;
 		// so is the packed record: its conic turns the summed raw accumulators into gradients (preprocess_bwd.cu)
 		a.g0[idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-		a.g1[idx] = make_float4(conic.z, a.opacities[idx], rgb.x, rgb.y);
+		float opacity = a.opacities[idx];
+		if (kRaw) opacity = sigmoid_act(opacity);   // getOpacityActivation, gaussian_model.cpp:74-77
+		a.g1[idx] = make_float4(conic.z, opacity, rgb.x, rgb.y);
 		a.gb[idx] = rgb.z;
 		if (emits) {
 			a.depth[idx] = r;
@@ -206,10 +257,15 @@ __global__ void mark_all_visible_kernel(int P, uint8_t* present)
 int launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t st)
 {
 	const int blocks = ceil_div(a.P, kPreThreads);
-	if (a.shs != nullptr && sh_rows_bulk_capable(a.shs, a.M))
-		preprocess_lonlat_fwd_kernel<true><<<blocks, kPreThreads, 0, st>>>(a);
+	if (a.raw) {
+		if (sh_rows_bulk_capable(a.features_rest, a.M) && sh_rows_bulk_capable(a.features_dc, a.M))
+			preprocess_lonlat_fwd_kernel<2><<<blocks, kPreThreads, 0, st>>>(a);
+		else
+			preprocess_lonlat_fwd_kernel<3><<<blocks, kPreThreads, 0, st>>>(a);
+	} else if (a.shs != nullptr && sh_rows_bulk_capable(a.shs, a.M))
+		preprocess_lonlat_fwd_kernel<1><<<blocks, kPreThreads, 0, st>>>(a);
 	else
-		preprocess_lonlat_fwd_kernel<false><<<blocks, kPreThreads, 0, st>>>(a);
+		preprocess_lonlat_fwd_kernel<0><<<blocks, kPreThreads, 0, st>>>(a);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }

@@ -1,0 +1,276 @@
+// train_step.cu — the per-iteration work either side of the rasterizer:
+//
+//   * photometric loss, forward and backward in two kernels:
+//       loss = (1 - lambda) * mean|I - gt| + lambda * (1 - SSIM(I, gt))
+//     with I = rendered * mask, optionally cropped at the bottom (gaussian_mapper.cpp:391-413).
+//     SSIM is the reference's: 11x11 Gaussian window (sigma 1.5), zero padding, per channel, mean over all
+//     elements (include/loss_utils.h:58-131, built there from five grouped conv2d calls and autograd).
+//     Forward kernel: one CTA per 16x16 pixel block and channel stages the 26x26 halo of both images in shared
+//     memory, runs the separable window over the five moment maps, evaluates the SSIM map and its three
+//     partial derivatives (w.r.t. mu1, sigma1^2, sigma12) and accumulates the two loss sums.
+//     Backward kernel: the window is self-adjoint, so dL/dI is the same separable filter applied to the three
+//     derivative maps:  dSSIM/dI(p) = (w * dm_dmu1)(p) + 2 I(p) (w * dm_dsigma1sq)(p) + gt(p) (w * dm_dsigma12)(p).
+//   * Adam over the optimiser's parameter groups in ONE launch (torch::optim::Adam as configured at
+//     gaussian_model.cpp:485-518: betas (0.9, 0.999), eps 1e-15, no weight decay, per-group learning rate);
+//   * densification statistics (gaussian_mapper.cpp:427-434, gaussian_model.cpp:839-853).
+#include "launchers.cuh"
+#include <cmath>
+
+namespace ogs {
+
+constexpr int kLossTile = 16;
+constexpr int kWin = 11, kHalf = 5;
+constexpr int kHalo = kLossTile + 2 * kHalf;   // 26
+
+struct LossArgs {
+	int W, H, H_used;          // rows >= H_used are cropped away (skip_bottom_ratio)
+	int mask_channels;         // 0: no mask, 1: [1,H,W], 3: [3,H,W]
+	float lambda_dssim;
+	float w[kWin];             // normalised 1-D window
+	const float* rendered;     // [3,H,W]
+	const float* gt;           // [3,H,W]
+	const float* mask;
+	float* dmaps;              // [3 maps][3,H,W] workspace: dm_dmu1, dm_dsigma1sq, dm_dsigma12
+	double* sums;              // [2]: sum |I - gt|, sum SSIM map
+	float* loss_out;           // [3]: loss, L1, SSIM
+	float* dL_dpix;            // [3,H,W]
+};
+
+OGS_D float masked_pixel(const LossArgs& a, int ch, int x, int y)
+{
+	const size_t i = (size_t)y * a.W + x, HW = (size_t)a.H * a.W;
+	float v = a.rendered[ch * HW + i];
+	if (a.mask_channels == 1) v *= a.mask[i];
+	else if (a.mask_channels == 3) v *= a.mask[ch * HW + i];
+	return v;
+}
+
+__global__ void __launch_bounds__(kLossTile * kLossTile) ssim_l1_fwd_kernel(const LossArgs a)
+{
+	__shared__ float s_x[kHalo][kHalo + 1], s_y[kHalo][kHalo + 1];
+	__shared__ float s_h[5][kHalo][kLossTile];
+	__shared__ float s_red[2][8];
+	const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kLossTile + tx;
+	const int ch = blockIdx.z;
+	const int x0 = blockIdx.x * kLossTile - kHalf, y0 = blockIdx.y * kLossTile - kHalf;
+	const size_t HW = (size_t)a.H * a.W;
+
+	for (int i = tid; i < kHalo * kHalo; i += kLossTile * kLossTile) {
+		const int r = i / kHalo, c = i % kHalo;
+		const int x = x0 + c, y = y0 + r;
+		float vx = 0.f, vy = 0.f;   // zero padding outside the (cropped) image
+		if (x >= 0 && x < a.W && y >= 0 && y < a.H_used) {
+			vx = masked_pixel(a, ch, x, y);
+			vy = a.gt[ch * HW + (size_t)y * a.W + x];
+		}
+		s_x[r][c] = vx;
+		s_y[r][c] = vy;
+	}
+	__syncthreads();
+	// horizontal pass: 26 rows x 16 columns, five moment maps
+	for (int i = tid; i < kHalo * kLossTile; i += kLossTile * kLossTile) {
+		const int r = i / kLossTile, c = i % kLossTile;
+		float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+		for (int k = 0; k < kWin; k++) {
+			const float w = a.w[k], vx = s_x[r][c + k], vy = s_y[r][c + k];
+			m1 += w * vx; m2 += w * vy;
+			e11 += w * vx * vx; e22 += w * vy * vy; e12 += w * vx * vy;
+		}
+		s_h[0][r][c] = m1; s_h[1][r][c] = m2; s_h[2][r][c] = e11; s_h[3][r][c] = e22; s_h[4][r][c] = e12;
+	}
+	__syncthreads();
+	const int x = blockIdx.x * kLossTile + tx, y = blockIdx.y * kLossTile + ty;
+	float l1 = 0.f, ssim = 0.f;
+	if (x < a.W && y < a.H_used) {
+		float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+		for (int k = 0; k < kWin; k++) {
+			const float w = a.w[k];
+			mu1 += w * s_h[0][ty + k][tx]; mu2 += w * s_h[1][ty + k][tx];
+			e11 += w * s_h[2][ty + k][tx]; e22 += w * s_h[3][ty + k][tx]; e12 += w * s_h[4][ty + k][tx];
+		}
+		// loss_utils.h:93-108
+		const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
+		const float sigma1_sq = e11 - mu1_sq, sigma2_sq = e22 - mu2_sq, sigma12 = e12 - mu1_mu2;
+		const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+		const float A = mu1_sq + mu2_sq + C1, B = sigma1_sq + sigma2_sq + C2;
+		const float C = 2.f * mu1_mu2 + C1, D = 2.f * sigma12 + C2;
+		const float invAB = 1.f / (A * B);
+		ssim = C * D * invAB;
+		// partial derivatives of the map (sigma's dependence on mu1 folded into dm_dmu1)
+		const float dm_dmu1 = 2.f * invAB * (mu2 * (D - C) - mu1 * C * D / A + mu1 * C * D / B);
+		const float dm_ds1 = -C * D * invAB / B;
+		const float dm_ds12 = 2.f * C * invAB;
+		const size_t i = (size_t)y * a.W + x;
+		a.dmaps[(0 * 3 + ch) * HW + i] = dm_dmu1;
+		a.dmaps[(1 * 3 + ch) * HW + i] = dm_ds1;
+		a.dmaps[(2 * 3 + ch) * HW + i] = dm_ds12;
+		l1 = fabsf(s_x[ty + kHalf][tx + kHalf] - s_y[ty + kHalf][tx + kHalf]);
+	}
+	l1 = warp_sum(l1);
+	ssim = warp_sum(ssim);
+	if ((tid & 31) == 0) { s_red[0][tid >> 5] = l1; s_red[1][tid >> 5] = ssim; }
+	__syncthreads();
+	if (tid < 2) {
+		double t = 0.0;
+		for (int w = 0; w < 8; w++) t += (double)s_red[tid][w];
+		atomicAdd(&a.sums[tid], t);
+	}
+}
+
+__global__ void __launch_bounds__(kLossTile * kLossTile) ssim_l1_bwd_kernel(const LossArgs a)
+{
+	__shared__ float s_d[3][kHalo][kHalo + 1];
+	__shared__ float s_h[3][kHalo][kLossTile];
+	const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kLossTile + tx;
+	const int ch = blockIdx.z;
+	const int x0 = blockIdx.x * kLossTile - kHalf, y0 = blockIdx.y * kLossTile - kHalf;
+	const size_t HW = (size_t)a.H * a.W;
+	const double count = 3.0 * (double)a.W * (double)a.H_used;
+
+	if (blockIdx.x == 0 && blockIdx.y == 0 && ch == 0 && tid == 0) {
+		const double l1 = a.sums[0] / count, ssim = a.sums[1] / count;
+		a.loss_out[0] = (float)((1.0 - (double)a.lambda_dssim) * l1 + (double)a.lambda_dssim * (1.0 - ssim));
+		a.loss_out[1] = (float)l1;
+		a.loss_out[2] = (float)ssim;
+	}
+	for (int i = tid; i < kHalo * kHalo; i += kLossTile * kLossTile) {
+		const int r = i / kHalo, c = i % kHalo;
+		const int x = x0 + c, y = y0 + r;
+		const bool in = x >= 0 && x < a.W && y >= 0 && y < a.H_used;
+		const size_t p = (size_t)y * a.W + x;
+#pragma unroll
+		for (int m = 0; m < 3; m++) s_d[m][r][c] = in ? a.dmaps[(m * 3 + ch) * HW + p] : 0.f;
+	}
+	__syncthreads();
+	for (int i = tid; i < kHalo * kLossTile; i += kLossTile * kLossTile) {
+		const int r = i / kLossTile, c = i % kLossTile;
+		float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+		for (int k = 0; k < kWin; k++) {
+			const float w = a.w[k];
+			h0 += w * s_d[0][r][c + k]; h1 += w * s_d[1][r][c + k]; h2 += w * s_d[2][r][c + k];
+		}
+		s_h[0][r][c] = h0; s_h[1][r][c] = h1; s_h[2][r][c] = h2;
+	}
+	__syncthreads();
+	const int x = blockIdx.x * kLossTile + tx, y = blockIdx.y * kLossTile + ty;
+	if (x >= a.W || y >= a.H) return;
+	const size_t i = (size_t)y * a.W + x;
+	float grad = 0.f;
+	if (y < a.H_used) {
+		float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+		for (int k = 0; k < kWin; k++) {
+			const float w = a.w[k];
+			c0 += w * s_h[0][ty + k][tx]; c1 += w * s_h[1][ty + k][tx]; c2 += w * s_h[2][ty + k][tx];
+		}
+		const float I = masked_pixel(a, ch, x, y), g = a.gt[ch * HW + i];
+		const float dssim = c0 + 2.f * I * c1 + g * c2;
+		const float diff = I - g;
+		const float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
+		const float inv = (float)(1.0 / count);
+		grad = (1.f - a.lambda_dssim) * sgn * inv - a.lambda_dssim * dssim * inv;
+		if (a.mask_channels == 1) grad *= a.mask[i];
+		else if (a.mask_channels == 3) grad *= a.mask[ch * HW + i];
+	}
+	a.dL_dpix[ch * HW + i] = grad;
+}
+
+int launch_photometric_loss(int W, int H, int H_used, float lambda_dssim, const float* rendered, const float* gt,
+                            const float* mask, int mask_channels, float* workspace, float* loss_out, float* dL_dpix,
+                            cudaStream_t st)
+{
+	LossArgs a{};
+	a.W = W; a.H = H; a.H_used = H_used; a.mask_channels = mask ? mask_channels : 0; a.lambda_dssim = lambda_dssim;
+	// loss_utils.h:58-68: exp(-(x - 5)^2 / (2 sigma^2)) in float32, normalised by its float32 sum
+	float wsum = 0.f;
+	for (int k = 0; k < kWin; k++) {
+		const int t = k - kWin / 2;
+		a.w[k] = std::exp(-(float)(t * t) / (2.0f * 1.5f * 1.5f));
+		wsum += a.w[k];
+	}
+	for (int k = 0; k < kWin; k++) a.w[k] /= wsum;
+	a.rendered = rendered; a.gt = gt; a.mask = mask;
+	a.sums = reinterpret_cast<double*>(workspace);
+	a.dmaps = workspace + 4;   // behind the two 8-byte sums
+	a.loss_out = loss_out; a.dL_dpix = dL_dpix;
+	OGS_CUDA_TRY(cudaMemsetAsync(a.sums, 0, 2 * sizeof(double), st));
+	const dim3 grid(ceil_div(W, kLossTile), ceil_div(H, kLossTile), 3), block(kLossTile, kLossTile);
+	ssim_l1_fwd_kernel<<<grid, block, 0, st>>>(a);
+	ssim_l1_bwd_kernel<<<grid, block, 0, st>>>(a);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+size_t photometric_loss_workspace_bytes(int W, int H) { return (4 + 9 * (size_t)W * H) * sizeof(float); }
+
+// ------------------------------------------------------------------ Adam, all parameter groups in one launch
+__global__ void __launch_bounds__(256) adam_groups_kernel(const AdamLaunch a)
+{
+	// the block's group: a.first_block[g] <= blockIdx.x < a.first_block[g + 1]
+	int g = 0;
+#pragma unroll
+	for (int k = 1; k < kAdamMaxGroups; k++)
+		if (k < a.groups && (int)blockIdx.x >= a.first_block[k]) g = k;
+	const AdamGroup grp = a.group[g];
+	const size_t base = ((size_t)blockIdx.x - a.first_block[g]) * kAdamPerBlock;
+	const float step_size = grp.step_size;
+#pragma unroll
+	for (int u = 0; u < kAdamPerBlock / 256; u++) {
+		const size_t i = base + (size_t)u * 256 + threadIdx.x;
+		if (i < grp.n) {
+			// torch/csrc/api/src/optim/adam.cpp step(): exp_avg, exp_avg_sq, denom, addcdiv_
+			const float grad = grp.grad[i];
+			const float m = grp.exp_avg[i] * a.beta1 + grad * a.one_minus_beta1;
+			const float v = grp.exp_avg_sq[i] * a.beta2 + (a.one_minus_beta2 * grad) * grad;
+			const float denom = sqrtf(v) / a.sqrt_bias_correction2 + a.eps;
+			grp.exp_avg[i] = m;
+			grp.exp_avg_sq[i] = v;
+			grp.param[i] = grp.param[i] - step_size * (m / denom);
+		}
+	}
+}
+
+int launch_adam(AdamLaunch a, cudaStream_t st)
+{
+	int blocks = 0;
+	for (int g = 0; g < a.groups; g++) {
+		a.first_block[g] = blocks;
+		blocks += (int)((a.group[g].n + kAdamPerBlock - 1) / kAdamPerBlock);
+	}
+	a.first_block[a.groups] = blocks;
+	if (blocks == 0) return OGS_OK;
+	adam_groups_kernel<<<blocks, 256, 0, st>>>(a);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+// ------------------------------------------------------------------ densification statistics
+// gaussian_mapper.cpp:427-434 + gaussian_model.cpp:839-853, for the Gaussians with radii > 0:
+//   max_radii2D = max(max_radii2D, radii);  xyz_gradient_accum += ||dL/dmean2D.xy||;  denom += 1
+__global__ void densify_stats_kernel(int P, const int* __restrict__ radii, const float* __restrict__ dL_dmean2D,
+                                     float* __restrict__ max_radii2D, float* __restrict__ xyz_gradient_accum,
+                                     float* __restrict__ denom)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	const int r = radii[i];
+	if (r <= 0) return;
+	const float gx = dL_dmean2D[3 * (size_t)i], gy = dL_dmean2D[3 * (size_t)i + 1];
+	max_radii2D[i] = fmaxf(max_radii2D[i], (float)r);
+	xyz_gradient_accum[i] += sqrtf(gx * gx + gy * gy);
+	denom[i] += 1.f;
+}
+
+int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D,
+                         float* xyz_gradient_accum, float* denom, cudaStream_t st)
+{
+	if (P == 0) return OGS_OK;
+	densify_stats_kernel<<<ceil_div(P, 256), 256, 0, st>>>(P, radii, dL_dmean2D, max_radii2D, xyz_gradient_accum, denom);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+} // namespace ogs
