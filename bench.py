@@ -113,6 +113,60 @@ def cpu_port_baseline(scene, view, dL_np, budget_s=45.0):
                       f"is ~11x larger"}
 
 
+def training_iteration_bench(h, scene, views, dev, K, Wm, ref_mod):
+    """one whole training iteration per step (lr schedule, render from the stored tensors, L1 + SSIM
+    loss, backward, densification statistics, Adam; loss read back) on the WORKLOAD scene.  ref_mod None: this
+    package's fused calls (trainer.train_for_one_iteration).  ref_mod = the reference rasterizer library: the
+    reference's composition (LibTorch activations / conv2d SSIM / autograd / torch.optim.Adam around its own
+    rasterizer, gaussian_mapper.cpp:300-470).  Reported beside the BASELINE metric, not instead of it."""
+    import torch
+    from importlib import import_module
+    tr = import_module("omnigs-fork_b200.trainer")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    op = np.clip(scene.opacities.astype(np.float64), 1e-4, 1 - 1e-4)
+    raw = [t(scene.means3D), t(scene.shs[:, :1, :]), t(scene.shs[:, 1:, :]), t(np.log(op / (1 - op)).astype(np.float32)),
+           t(np.log(scene.scales.astype(np.float64)).astype(np.float32)), t(scene.rotations)]
+    W, H = scene.W, scene.H
+    gt = torch.rand((3, H, W), device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    bg = torch.zeros(3, device=dev)
+    view_dev = [(torch.from_numpy(v).to(dev), torch.from_numpy(c).to(dev)) for v, c in views]
+    K = min(K, 50)
+    if ref_mod is None:
+        pc = tr.GaussianModel(*raw, sh_degree=3)
+
+        def step(s):
+            loss_out, _ = tr.train_for_one_iteration(pc, view_dev[s][0], view_dev[s][1], gt, bg, s + 1)
+            return float(loss_out[0].item())
+        what = "fused: 5 library calls per iteration (raw forward, loss fwd+bwd, raw backward, statistics, Adam)"
+    else:
+        from oracle import train_ref as ref   # reference arm only: the LibTorch composition restated
+        leaves = [p.clone().requires_grad_(True) for p in raw]
+        opt = tr.OptimizationParams()
+        lrs = [opt.position_lr_init, opt.feature_lr, opt.feature_lr / 20.0, opt.opacity_lr, opt.scaling_lr, opt.rotation_lr]
+        adam = ref.make_adam(leaves, lrs)
+        P = scene.P
+        stats = [torch.zeros(P, device=dev), torch.zeros((P, 1), device=dev), torch.zeros((P, 1), device=dev)]
+        rasterize = h.make_autograd_rasterizer(ref_mod)
+
+        def step(s):
+            adam.param_groups[0]["lr"] = tr.expon_lr(s + 1, opt.position_lr_init, opt.position_lr_final, 0,
+                                                     opt.position_lr_delay_mult, opt.position_lr_max_steps)
+            return h.reference_training_iteration(rasterize, ref, leaves, adam, stats, view_dev[s][0], view_dev[s][1],
+                                                  gt, bg, opt.lambda_dssim)
+        what = "reference composition: LibTorch-op activations, conv2d SSIM, autograd, torch.optim.Adam around the reference rasterizer"
+    for s in range(Wm):
+        step(s)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(K):
+        loss = step(Wm + s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    return {"ms_per_iteration": ms, "views_per_s": 1000.0 / ms, "steps": K, "final_loss": loss, "what": what}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -285,6 +339,7 @@ def main():
                                 "sample": f"{K} full {WORKLOAD} frames; the reference ships no CPU rasterizer, its CUDA "
                                           "kernels (rebuilt -arch=sm_100) are the reference implementation of the path"}
         line["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        line["train_step"] = training_iteration_bench(h, scene, views, dev, K, Wm, mod)
         print(json.dumps(line))
         return 0
 
@@ -332,6 +387,8 @@ def main():
     line["roofline_frame"] = {"alg_bytes": total_alg, "achieved": total_alg / ms_per_step / 1e6, "peak": peak,
                               "unit": "GB/s", "frac": total_alg / ms_per_step / 1e6 / peak, "stages": per_stage,
                               "stage_ms": stage_ms}
+    if world == 1:
+        line["train_step"] = training_iteration_bench(h, scene, views, dev, K, Wm, None)
     line["gpu_launches"] = K * (12 + 2)   # fwd: preprocess, hist, 4+2 onesweep, scan, ranges, emit, render; bwd: 2
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port_baseline(scene, views[Wm], dL_np)

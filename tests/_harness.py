@@ -104,3 +104,55 @@ def grad_error(a, b):
     rel = float(diff.max()) / scale
     excess = float((diff - (1e-4 * b.abs() + 1e-6 * scale)).max())
     return rel, excess
+
+
+def make_autograd_rasterizer(mod):
+    """GaussianRasterizerFunction (reference src/gaussian_rasterizer.cpp:34-170) over the entry points of `mod`
+    (this package or the reference library): lets bench.py time the reference's training iteration exactly as
+    gaussian_mapper.cpp composes it (LibTorch ops + autograd around the rasterizer)."""
+    import torch
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, means3D, means2D, sh, opacities, scales, rotations, bg, viewmatrix, campos, H, W, degree):
+            empty = torch.empty((0,), dtype=torch.float32, device=means3D.device)
+            R, color, radii, geom, binning, img = mod.RasterizeGaussiansCUDA(
+                bg, means3D, empty, opacities, scales, rotations, 1.0, empty, viewmatrix, viewmatrix, 0.0, 0.0,
+                H, W, sh, degree, campos, False, 3, False)
+            ctx.args = (bg, viewmatrix, campos, degree, R)
+            ctx.save_for_backward(means3D, scales, rotations, radii, sh, geom, binning, img)
+            ctx.mark_non_differentiable(radii)
+            return color, radii
+
+        @staticmethod
+        def backward(ctx, grad_color, _):
+            bg, viewmatrix, campos, degree, R = ctx.args
+            means3D, scales, rotations, radii, sh, geom, binning, img = ctx.saved_tensors
+            empty = torch.empty((0,), dtype=torch.float32, device=means3D.device)
+            g = mod.RasterizeGaussiansBackwardCUDA(
+                bg, means3D, radii, empty, scales, rotations, 1.0, empty, viewmatrix, viewmatrix, 0.0, 0.0,
+                grad_color.contiguous(), sh, degree, campos, geom, R, binning, img, 3)
+            dm2d, _, dop, dm3d, _, dsh, dsc, drot = g
+            return dm3d, dm2d, dsh, dop, dsc, drot, None, None, None, None, None, None
+
+    return Fn.apply
+
+
+def reference_training_iteration(rasterize, ref, leaves, adam, stats, viewmatrix, campos, gt, bg, lambda_dssim, degree=3):
+    """One GaussianMapper::trainForOneIteration (gaussian_mapper.cpp:300-470, no densify/prune) as the reference
+    composes it: activations, rasterizer through autograd, l1 + ssim, backward, statistics, Adam, loss.item()."""
+    import torch
+    H, W = int(gt.size(1)), int(gt.size(2))
+    act = ref.activations(*leaves)
+    means2D = torch.zeros_like(act["means3D"], requires_grad=True)
+    img, radii = rasterize(act["means3D"], means2D, act["shs"], act["opacity"], act["scales"], act["rotations"],
+                           bg, viewmatrix, campos, H, W, degree)
+    loss, _, _ = ref.photometric_loss(img, gt, lambda_dssim)
+    adam.zero_grad(set_to_none=True)
+    loss.backward()
+    torch.cuda.synchronize()            # gaussian_mapper.cpp:416
+    with torch.no_grad():
+        value = loss.item()             # :420 (ema_loss_for_log_)
+        ref.densify_stats(stats[0], stats[1], stats[2], radii, means2D.grad)
+        adam.step()
+    return value
