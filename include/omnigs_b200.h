@@ -16,6 +16,8 @@
  *     rasterizer.h:98-100, rasterizer_impl.cu:185-192
  *   required<GeometryState/ImageState/BinningState>(n)         ogs_geom_bytes / ogs_img_bytes /
  *     rasterizer_impl.h:96-102, rasterizer_impl.cu:198-245       ogs_binning_bytes
+ *   CudaRasterizer::Rasterizer::{forward,backward,markVisible}  ogs_pinhole_forward_stage1 / ogs_pinhole_backward /
+ *     rasterizer.h:39-92, rasterizer_impl.cu:170-183,250-530     ogs_mark_visible_pinhole
  *   model activations + rasterizer + their autograd            ogs_lonlat_forward_raw_stage1 /
  *     gaussian_model.cpp:54-77, gaussian_renderer.cpp:212-258    ogs_lonlat_backward_raw
  *   loss_utils::l1_loss / ssim + autograd                      ogs_photometric_loss
@@ -195,6 +197,37 @@ OGS_API int ogs_lonlat_train_view_host(
 	float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
 	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
 	int64_t* num_rendered_host, size_t* binning_needed, void* stream);
+
+/*
+ * Perspective camera (camera_type = 1): CudaRasterizer::Rasterizer::forward / backward /
+ * markVisible (cuda_rasterizer/rasterizer.h:39-92, rasterizer_impl.cu:170-183,250-530) with preprocessCUDA
+ * (forward.cu:232-340), computeCov2D (:86-128), renderDepthCUDA (:472-590) and the backward kernels
+ * computeCov2DCUDA / preprocessCUDA (backward.cu:156-292, :558-608).  Same conventions and buffers as the lonlat
+ * calls; projmatrix is the full (projection x view) transform stored column-major, tan_fovx/tan_fovy are
+ * tan(fov/2).  Stage 2 is ogs_lonlat_forward_stage2 (binning and blending do not depend on the camera).
+ * render_depth != 0 blends the camera-space depth into all three channels instead of the colour; the reference's
+ * backward has no depth path, so ogs_pinhole_backward after a render_depth forward is undefined.
+ */
+OGS_API int ogs_pinhole_forward_stage1(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+	int render_depth, int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, void* stream);
+OGS_API int ogs_pinhole_backward(
+	int P, int D, int M, int64_t num_rendered, int W, int H,
+	const float* background,
+	const float* means3D, const float* shs, const float* colors_precomp,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+	const int* radii, char* geom_buffer, char* binning_buffer, char* img_buffer,
+	const float* dL_dpix,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+	void* stream);
+/* checkFrustum (rasterizer_impl.cu:64-77): present[i] = camera-space z > 0.2 */
+OGS_API int ogs_mark_visible_pinhole(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                                     uint8_t* present, void* stream);
 
 /*
  * Raw-parameter entry points.  Before every render the reference turns the model's

@@ -37,6 +37,11 @@ SYMBOLS = {
     "ogs_mark_all_visible": (_c_int, [_c_int, _p, _p]),
     "ogs_export_geometry": (_c_int, [_c_int, _p] + [_p] * 7 + [_p]),
     "ogs_export_binning": (_c_int, [_c_int] * 3 + [_c_i64] + [_p] * 3 + [_p] * 5 + [_p]),
+    "ogs_pinhole_forward_stage1": (_c_int, [_c_int] * 5 + [_p] * 5 + [_c_f] + [_p] * 5 + [_c_f] * 2 + [_c_int] + [_p] * 3
+                                   + [ctypes.POINTER(_c_i64), _p]),
+    "ogs_pinhole_backward": (_c_int, [_c_int] * 3 + [_c_i64, _c_int, _c_int] + [_p] * 5 + [_c_f] + [_p] * 5 + [_c_f] * 2
+                             + [_p] * 4 + [_p] + [_p] * 9 + [_p]),
+    "ogs_mark_visible_pinhole": (_c_int, [_c_int] + [_p] * 4 + [_p]),
     "ogs_lonlat_forward_raw_stage1": (_c_int, [_c_int] * 5 + [_p] * 5 + [_c_f] + [_p] * 3 + [_p] * 3
                                       + [ctypes.POINTER(_c_i64), _p]),
     "ogs_lonlat_backward_raw": (_c_int, [_c_int] * 3 + [_c_i64] + [_c_int] * 2 + [_p] + [_p] * 4 + [_c_f] + [_p] * 4

@@ -225,13 +225,19 @@ int check_image(int W, int H)
 	return OGS_OK;
 }
 
+struct PinholeParams {   // camera_type 1: full projection, tan(fov/2), depth instead of colour
+	const float* projmatrix;
+	float tan_fovx, tan_fovy;
+	int render_depth;
+};
+
 int forward_stage1_impl(
 	int P, int D, int M, int W, int H, int band_y0, int band_y1,
 	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
 	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
 	const float* viewmatrix, const float* campos,
 	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, cudaStream_t st,
-	const float* features_dc = nullptr, const float* features_rest = nullptr)
+	const float* features_dc = nullptr, const float* features_rest = nullptr, const PinholeParams* pin = nullptr)
 {
 	// raw-parameter mode: features_dc / features_rest given instead of shs; opacities, scales and rotations
 	// are then the stored (pre-activation) tensors
@@ -272,6 +278,15 @@ int forward_stage1_impl(
 	a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
 	a.scales = scales; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
 	a.raw = raw ? 1 : 0; a.features_dc = features_dc; a.features_rest = features_rest;
+	if (pin) {
+		if (!pin->projmatrix) return fail(OGS_ERR_INVALID_ARG, "projmatrix is NULL");
+		if (raw || seam_wrap) return fail(OGS_ERR_INVALID_ARG, "raw-parameter mode and seam wrap-around are lonlat-only");
+		a.pinhole = 1; a.render_depth = pin->render_depth; a.projmatrix = pin->projmatrix;
+		a.tan_fovx = pin->tan_fovx; a.tan_fovy = pin->tan_fovy;
+		// rasterizer_impl.cu:274-276: tan(fov/2) -> focal length in pixels, float arithmetic
+		a.focal_y = H / (2.0f * pin->tan_fovy);
+		a.focal_x = W / (2.0f * pin->tan_fovx);
+	}
 	a.viewmatrix = viewmatrix; a.campos = campos; a.radii = radii;
 	a.g0 = g.g0; a.g1 = g.g1; a.gb = g.gb; a.depth = g.depth; a.rect = g.rect;
 	a.tiles_touched = g.tiles_touched; a.cov3D = g.cov3D; a.clamped = g.clamped;
@@ -482,6 +497,72 @@ OGS_API int ogs_lonlat_backward(
 	return ogs_lonlat_backward_finish(P, D, M, W, H, means3D, shs, scales, scale_modifier, rotations, cov3D_precomp,
 	                                  viewmatrix, campos, radii, geom_buffer, dL_dmean2D, dL_dconic, dL_dopacity,
 	                                  dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, stream);
+}
+
+// ---- perspective camera (camera_type 1): CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+OGS_API int ogs_pinhole_forward_stage1(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+	int render_depth, int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, void* stream)
+{
+	const PinholeParams pin{ projmatrix, tan_fovx, tan_fovy, render_depth ? 1 : 0 };
+	const int gy = H > 0 ? ceil_div(H, kTile) : 0;
+	return forward_stage1_impl(P, D, M, W, H, 0, gy, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
+	                           rotations, cov3D_precomp, viewmatrix, campos, radii, geom_buffer, img_buffer,
+	                           num_rendered_host, (cudaStream_t)stream, nullptr, nullptr, &pin);
+}
+
+OGS_API int ogs_pinhole_backward(
+	int P, int D, int M, int64_t num_rendered, int W, int H,
+	const float* background,
+	const float* means3D, const float* shs, const float* colors_precomp,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+	const int* radii, char* geom_buffer, char* binning_buffer, char* img_buffer,
+	const float* dL_dpix,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+	void* stream)
+{
+	(void)colors_precomp;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (int rc = ogs_lonlat_backward_render(P, num_rendered, W, H, background, geom_buffer, binning_buffer,
+	                                        img_buffer, dL_dpix, stream)) return rc;
+	if (P == 0) return OGS_OK;
+	if (!means3D || !viewmatrix || !projmatrix || !campos || !radii || !geom_buffer ||
+	    !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot)
+		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	if (shs && M > 0 && !dL_dsh) return fail(OGS_ERR_INVALID_ARG, "dL_dsh is NULL");
+	if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+		return fail(OGS_ERR_INVALID_ARG, "exactly one of (scales, rotations) / cov3D_precomp must be given");
+	GeomState g = GeomState::carve(geom_buffer, P);
+	PreprocessBwdArgs a{};
+	a.P = P; a.D = D; a.M = shs ? M : 0; a.W = W; a.H = H; a.scale_modifier = scale_modifier;
+	a.means3D = means3D; a.shs = shs; a.scales = scales; a.rotations = rotations;
+	a.cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
+	a.viewmatrix = viewmatrix; a.campos = campos; a.radii = radii; a.clamped = g.clamped; a.grad_acc = g.grad_acc;
+	a.g0 = g.g0; a.g1 = g.g1;
+	a.pinhole = 1; a.projmatrix = projmatrix; a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+	a.focal_y = H / (2.0f * tan_fovy);   // rasterizer_impl.cu:476-477
+	a.focal_x = W / (2.0f * tan_fovx);
+	a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
+	a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = shs ? dL_dsh : nullptr;
+	a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+	prof_begin(OGS_PROF_PREPROCESS_BWD, st);
+	const int rc = launch_preprocess_bwd(a, st);
+	prof_end(OGS_PROF_PREPROCESS_BWD, st);
+	return rc;
+}
+
+OGS_API int ogs_mark_visible_pinhole(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                                     uint8_t* present, void* stream)
+{
+	(void)projmatrix;   // in_frustum's projected test is commented out in the reference (auxiliary.h:180)
+	if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(OGS_ERR_INVALID_ARG, "bad argument to mark_visible_pinhole");
+	if (P == 0) return OGS_OK;
+	return launch_check_frustum(P, means3D, viewmatrix, present, (cudaStream_t)stream);
 }
 
 // ---- raw-parameter entry points: activations and their backward inside the kernels

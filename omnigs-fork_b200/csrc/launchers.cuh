@@ -20,6 +20,10 @@ struct PreprocessFwdArgs {
 	int raw;
 	const float* features_dc;
 	const float* features_rest;
+	// perspective camera (pinhole != 0): full projection matrix, focal lengths in pixels, tan(fov/2)
+	int pinhole, render_depth;
+	const float* projmatrix;
+	float focal_x, focal_y, tan_fovx, tan_fovy;
 	const float* viewmatrix;
 	const float* campos;
 	int* radii;
@@ -58,6 +62,10 @@ struct PreprocessBwdArgs {
 	const float* features_rest;
 	float* dL_dfeatures_dc;
 	float* dL_dfeatures_rest;
+	// perspective camera (pinhole != 0)
+	int pinhole;
+	const float* projmatrix;
+	float focal_x, focal_y, tan_fovx, tan_fovy;
 	float* dL_dmean2D;
 	float* dL_dconic;
 	float* dL_dopacity;
@@ -70,6 +78,7 @@ struct PreprocessBwdArgs {
 };
 int launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t st);
 int launch_mark_all_visible(int P, uint8_t* present, cudaStream_t st);
+int launch_check_frustum(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
 int launch_depth_order(const GeomState& g, int P, cudaStream_t st);
 int launch_tile_ranges(const ImageState& img, int W, int H, cudaStream_t st);
 int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const BinningState& b,

@@ -438,45 +438,13 @@ OGS_D void cov3d_backward(float3 scale, float mod, float4 q, const float* dL_dco
 #undef OGS_D_
 }
 
-// Backward through conic = inverse(cov2D), cov2D = T^T Vrk T and the lonlat Jacobian, including
-// the second-derivative terms of the projection (backward.cu:297-485).
-// Outputs: dL/dcov3D (6), the covariance branch of dL/dmean (world), and the Jacobian rows.
-OGS_D void cov2d_lonlat_backward(float3 mean, const float* cov6, const float* V, int W, int H,
-                                 float3 dL_dconic /*(.x,.y,.w of the accumulator)*/,
-                                 float* dL_dcov6, float3& dL_dmean, float3& dpx_dt, float3& dpy_dt)
+// Shared middle of the two cameras' covariance backward (backward.cu:193-268 pinhole, :370-452 lonlat):
+// conic = inverse(cov2D), cov2D = T^T Vrk T + 0.3 I, T = W J.  From dL/dconic: dL/dcov3D (6) and the gradient
+// w.r.t. the five possibly non-zero Jacobian entries (J rows 0 and 1; j01 is structurally zero).
+OGS_D void conic_to_cov3d_and_jacobian_backward(const LonlatJac& Jv, const float* V, const float* cov6, float3 dL_dconic,
+                                                 float* dL_dcov6, float& dL_dJ00, float& dL_dJ02, float& dL_dJ10,
+                                                 float& dL_dJ11, float& dL_dJ12)
 {
-	float3 t = view_point(V, mean);
-
-	float txtx = t.x * t.x;
-	float tyty = t.y * t.y;
-	float tztz = t.z * t.z;
-	float txtytz = t.x * t.y * t.z;
-
-	float trxztrxz = txtx + tztz;
-	float trxztrxz_inv = 1.0f / (trxztrxz + kEps7);
-	float trxztrxztrxztrxz_inv = trxztrxz_inv * trxztrxz_inv;
-	float trxz = sqrtf(trxztrxz);
-	float trxz_inv = 1.0f / (trxz + kEps7);
-	float trtr = trxztrxz + tyty;
-	float trtr_inv = 1.0f / (trtr + kEps7);
-	float trtrtrtr_inv = trtr_inv * trtr_inv;
-	float trxz_trtrtrtr_inv = trxz_inv * trtrtrtr_inv;
-	float trxztrxztrxz_trtrtrtr_inv = trxztrxz_inv * trxz_trtrtrtr_inv;
-	float tyty_minus_trxztrxz = tyty - trxztrxz;
-
-	float W_div_2pi = W * 0.5f * kPiInv;
-	float H_div_pi = H * kPiInv;
-
-	LonlatJac Jv;
-	Jv.j00 = W_div_2pi * t.z * trxztrxz_inv;
-	Jv.j02 = -W_div_2pi * t.x * trxztrxz_inv;
-	Jv.j10 = -H_div_pi * t.x * t.y * trxz_inv * trtr_inv;
-	Jv.j11 = H_div_pi * trxz * trtr_inv;
-	Jv.j12 = -H_div_pi * t.z * t.y * trxz_inv * trtr_inv;
-
-	dpx_dt = { Jv.j00, 0.0f, Jv.j02 };
-	dpy_dt = { Jv.j10, Jv.j11, Jv.j12 };
-
 	M3 T, Vrk, cov2D;
 	lonlat_T_cov(Jv, V, cov6, T, Vrk, cov2D);
 	M3 Wm = m3_cols(V[0], V[4], V[8], V[1], V[5], V[9], V[2], V[6], V[10]);
@@ -523,12 +491,55 @@ OGS_D void cov2d_lonlat_backward(float3 mean, const float* cov6, const float* V,
 #undef T_
 
 #define W_(i, j) Wm.c[i][j]
-	float dL_dJ00 = W_(0, 0) * dL_dT00 + W_(0, 1) * dL_dT01 + W_(0, 2) * dL_dT02;
-	float dL_dJ02 = W_(2, 0) * dL_dT00 + W_(2, 1) * dL_dT01 + W_(2, 2) * dL_dT02;
-	float dL_dJ10 = W_(0, 0) * dL_dT10 + W_(0, 1) * dL_dT11 + W_(0, 2) * dL_dT12;
-	float dL_dJ11 = W_(1, 0) * dL_dT10 + W_(1, 1) * dL_dT11 + W_(1, 2) * dL_dT12;
-	float dL_dJ12 = W_(2, 0) * dL_dT10 + W_(2, 1) * dL_dT11 + W_(2, 2) * dL_dT12;
+	dL_dJ00 = W_(0, 0) * dL_dT00 + W_(0, 1) * dL_dT01 + W_(0, 2) * dL_dT02;
+	dL_dJ02 = W_(2, 0) * dL_dT00 + W_(2, 1) * dL_dT01 + W_(2, 2) * dL_dT02;
+	dL_dJ10 = W_(0, 0) * dL_dT10 + W_(0, 1) * dL_dT11 + W_(0, 2) * dL_dT12;
+	dL_dJ11 = W_(1, 0) * dL_dT10 + W_(1, 1) * dL_dT11 + W_(1, 2) * dL_dT12;
+	dL_dJ12 = W_(2, 0) * dL_dT10 + W_(2, 1) * dL_dT11 + W_(2, 2) * dL_dT12;
 #undef W_
+}
+
+// Backward through conic = inverse(cov2D), cov2D = T^T Vrk T and the lonlat Jacobian, including
+// the second-derivative terms of the projection (backward.cu:297-485).
+// Outputs: dL/dcov3D (6), the covariance branch of dL/dmean (world), and the Jacobian rows.
+OGS_D void cov2d_lonlat_backward(float3 mean, const float* cov6, const float* V, int W, int H,
+                                 float3 dL_dconic /*(.x,.y,.w of the accumulator)*/,
+                                 float* dL_dcov6, float3& dL_dmean, float3& dpx_dt, float3& dpy_dt)
+{
+	float3 t = view_point(V, mean);
+
+	float txtx = t.x * t.x;
+	float tyty = t.y * t.y;
+	float tztz = t.z * t.z;
+	float txtytz = t.x * t.y * t.z;
+
+	float trxztrxz = txtx + tztz;
+	float trxztrxz_inv = 1.0f / (trxztrxz + kEps7);
+	float trxztrxztrxztrxz_inv = trxztrxz_inv * trxztrxz_inv;
+	float trxz = sqrtf(trxztrxz);
+	float trxz_inv = 1.0f / (trxz + kEps7);
+	float trtr = trxztrxz + tyty;
+	float trtr_inv = 1.0f / (trtr + kEps7);
+	float trtrtrtr_inv = trtr_inv * trtr_inv;
+	float trxz_trtrtrtr_inv = trxz_inv * trtrtrtr_inv;
+	float trxztrxztrxz_trtrtrtr_inv = trxztrxz_inv * trxz_trtrtrtr_inv;
+	float tyty_minus_trxztrxz = tyty - trxztrxz;
+
+	float W_div_2pi = W * 0.5f * kPiInv;
+	float H_div_pi = H * kPiInv;
+
+	LonlatJac Jv;
+	Jv.j00 = W_div_2pi * t.z * trxztrxz_inv;
+	Jv.j02 = -W_div_2pi * t.x * trxztrxz_inv;
+	Jv.j10 = -H_div_pi * t.x * t.y * trxz_inv * trtr_inv;
+	Jv.j11 = H_div_pi * trxz * trtr_inv;
+	Jv.j12 = -H_div_pi * t.z * t.y * trxz_inv * trtr_inv;
+
+	dpx_dt = { Jv.j00, 0.0f, Jv.j02 };
+	dpy_dt = { Jv.j10, Jv.j11, Jv.j12 };
+
+	float dL_dJ00, dL_dJ02, dL_dJ10, dL_dJ11, dL_dJ12;
+	conic_to_cov3d_and_jacobian_backward(Jv, V, cov6, dL_dconic, dL_dcov6, dL_dJ00, dL_dJ02, dL_dJ10, dL_dJ11, dL_dJ12);
 
 	float temp1 = H_div_pi * tyty_minus_trxztrxz * trxz_trtrtrtr_inv;
 	float temp2 = H_div_pi * txtytz * (trtr + 2.0f * trxztrxz) * trxztrxztrxz_trtrtrtr_inv;

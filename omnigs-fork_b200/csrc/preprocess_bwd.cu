@@ -20,7 +20,7 @@
 // (sigmoid / exp / normalize / cat, gaussian_model.cpp:54-77), i.e. the kernel returns what LibTorch's
 // autograd would deliver to the optimiser's six parameter tensors (xyz_, features_dc_, features_rest_,
 // opacity_, scaling_, rotation_), and the dL/dfeatures rows of the CTA leave as two bulk stores.
-#include "lonlat_math.cuh"
+#include "pinhole_math.cuh"
 #include "launchers.cuh"
 #include "async_copy.cuh"
 
@@ -29,7 +29,8 @@ namespace ogs {
 constexpr int kPreBwdThreads = 128;
 
 // kMode as in preprocess_fwd.cu: 0 plain SH rows, 1 bulk SH rows, 2 raw parameters (bulk), 3 raw parameters (plain)
-template <int kMode>
+// kPinhole: the perspective camera's covariance and screen-position branches (backward.cu:156-292, :583-597).
+template <int kMode, bool kPinhole = false>
 __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(const PreprocessBwdArgs a)
 {
 	constexpr bool kBulkSH = (kMode == 1 || kMode == 2);
@@ -129,20 +130,29 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 #pragma unroll
 		for (int i = 0; i < 6; i++) cov6[i] = a.cov3D[6 * (size_t)idx + i];
 
-		// covariance / conic branch (backward.cu:297-485); assigns dL/dmean
-		float3 dpx_dt, dpy_dt;
-		cov2d_lonlat_backward(mean, cov6, V, a.W, a.H, float3{ g[2], g[3], g[4] }, dcov6, dmean, dpx_dt, dpy_dt);
+		if constexpr (kPinhole) {
+			// covariance / conic branch (backward.cu:156-292), then the screen position through the full
+			// projection (backward.cu:583-597)
+			cov2d_pinhole_backward(mean, cov6, V, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy,
+			                       float3{ g[2], g[3], g[4] }, dcov6, dmean);
+			const float3 dm2 = proj_point_backward(a.projmatrix, mean, g[0], g[1]);
+			dmean.x += dm2.x; dmean.y += dm2.y; dmean.z += dm2.z;
+		} else {
+			// covariance / conic branch (backward.cu:297-485); assigns dL/dmean
+			float3 dpx_dt, dpy_dt;
+			cov2d_lonlat_backward(mean, cov6, V, a.W, a.H, float3{ g[2], g[3], g[4] }, dcov6, dmean, dpx_dt, dpy_dt);
 
-		// screen-position branch (backward.cu:642-660)
-		const float dsx_dpx = 2.0f / (float)a.W;
-		const float dsy_dpy = 2.0f / (float)a.H;
-		const float dL_dpx = g[0] * dsx_dpx;
-		const float dL_dpy = g[1] * dsy_dpy;
-		const float dL_dtx = dL_dpx * dpx_dt.x + dL_dpy * dpy_dt.x;
-		const float dL_dty = dL_dpx * dpx_dt.y + dL_dpy * dpy_dt.y;
-		const float dL_dtz = dL_dpx * dpx_dt.z + dL_dpy * dpy_dt.z;
-		const float3 dm2 = view_vec_t(V, float3{ dL_dtx, dL_dty, dL_dtz });
-		dmean.x += dm2.x; dmean.y += dm2.y; dmean.z += dm2.z;
+			// screen-position branch (backward.cu:642-660)
+			const float dsx_dpx = 2.0f / (float)a.W;
+			const float dsy_dpy = 2.0f / (float)a.H;
+			const float dL_dpx = g[0] * dsx_dpx;
+			const float dL_dpy = g[1] * dsy_dpy;
+			const float dL_dtx = dL_dpx * dpx_dt.x + dL_dpy * dpy_dt.x;
+			const float dL_dty = dL_dpx * dpx_dt.y + dL_dpy * dpy_dt.y;
+			const float dL_dtz = dL_dpx * dpx_dt.z + dL_dpy * dpy_dt.z;
+			const float3 dm2 = view_vec_t(V, float3{ dL_dtx, dL_dty, dL_dtz });
+			dmean.x += dm2.x; dmean.y += dm2.y; dmean.z += dm2.z;
+		}
 
 		// SH backward (backward.cu:30-151)
 		if (kRaw || a.shs != nullptr) {
@@ -297,7 +307,12 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st)
 {
 	const int blocks = ceil_div(a.P, kPreBwdThreads);
-	if (a.raw) {
+	if (a.pinhole) {
+		if (a.shs != nullptr && a.dL_dsh != nullptr && sh_rows_bulk_capable(a.shs, a.M) && sh_rows_bulk_capable(a.dL_dsh, a.M))
+			preprocess_lonlat_bwd_kernel<1, true><<<blocks, kPreBwdThreads, 0, st>>>(a);
+		else
+			preprocess_lonlat_bwd_kernel<0, true><<<blocks, kPreBwdThreads, 0, st>>>(a);
+	} else if (a.raw) {
 		if (sh_rows_bulk_capable(a.features_rest, a.M) && sh_rows_bulk_capable(a.features_dc, a.M) &&
 		    sh_rows_bulk_capable(a.dL_dfeatures_rest, a.M) && sh_rows_bulk_capable(a.dL_dfeatures_dc, a.M))
 			preprocess_lonlat_bwd_kernel<2><<<blocks, kPreBwdThreads, 0, st>>>(a);

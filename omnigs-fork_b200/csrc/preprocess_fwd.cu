@@ -18,7 +18,7 @@
 // scales = exp(scaling_), rotations = normalize(rotation_), SH row = cat(features_dc_, features_rest_).
 // The CTA's features_rest_ rows (128 x 180 B, contiguous) and features_dc_ rows (128 x 12 B) come in as
 // two bulk copies; a thread reads its row with a 45-word stride (conflict-free).
-#include "lonlat_math.cuh"
+#include "pinhole_math.cuh"
 #include "launchers.cuh"
 #include "async_copy.cuh"
 
@@ -28,12 +28,14 @@ constexpr int kPreThreads = 128;
 
 // kMode: 0 SH rows by plain loads, 1 SH rows [P,16,3] by per-row bulk copies,
 //        2 raw parameters with split SH by per-CTA bulk copies, 3 raw parameters by plain loads.
-template <int kMode>
+// kPinhole: the perspective camera (camera_type 1; forward.cu:232-340) instead of the equirectangular one.
+template <int kMode, bool kPinhole = false>
 __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(const PreprocessFwdArgs a)
 {
 	constexpr bool kBulkSH = (kMode == 1 || kMode == 2);
 	constexpr bool kRaw = (kMode >= 2);
 	__shared__ float sV[16];
+	__shared__ float sP[kPinhole ? 16 : 1];
 	__shared__ float sCam[3];
 	__shared__ unsigned long long s_block_tiles;
 	__shared__ __align__(16) float s_sh[kBulkSH ? kPreThreads * kShPitchFloats : 4];
@@ -42,6 +44,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 	const int tid = threadIdx.x;
 	const int idx = blockIdx.x * kPreThreads + tid;
 	if (tid < 16) sV[tid] = a.viewmatrix[tid];
+	if (kPinhole && tid < 16) sP[tid] = a.projmatrix[tid];
 	if (tid < 3) sCam[tid] = a.campos[tid];
 	if (tid == 0) {
 		s_block_tiles = 0ull;
@@ -88,19 +91,30 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 #pragma unroll
 		for (int i = 0; i < 16; i++) V[i] = sV[i];
 
-		// near cull (auxiliary.h:198-220): r^2 <= 0.04 drops the Gaussian
 		p_orig = { a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2] };
 		const float3 t = view_point_p(V, p_orig);
-		const float rr = dot3p(t.x, t.x, t.y, t.y, t.z, t.z);
-		if (!(rr <= 0.04f)) {
+		bool in_view;
+		float2 p_proj;
+		if constexpr (kPinhole) {
+			// in_frustum (auxiliary.h:166-196): only the near plane culls; depth is the camera-space z
+			in_view = !(t.z <= 0.2f);
+			r = t.z;
+			// projection through the full transform (forward.cu:273-277)
+			const float4 p_hom = proj_point_p(sP, p_orig);
+			const float p_w = __frcp_rn(__fadd_rn(p_hom.w, kEps7));
+			p_proj = { __fmul_rn(p_hom.x, p_w), __fmul_rn(p_hom.y, p_w) };
+		} else {
+			// near cull (auxiliary.h:198-220): r^2 <= 0.04 drops the Gaussian
+			const float rr = dot3p(t.x, t.x, t.y, t.y, t.z, t.z);
+			in_view = !(rr <= 0.04f);
 			r = __fsqrt_rn(rr);
-
 			// lon/lat screen coordinates (auxiliary.h:236-248)
 			const float inv_r = __frcp_rn(__fadd_rn(r, kEps7));
 			const float lon = atan2f(t.x, t.z);
 			const float lat = asinf(__fmul_rn(t.y, inv_r));
-			const float2 p_proj = { __fmul_rn(lon, kPiInv), __fmul_rn(lat, kTwoPiInv) };
-
+			p_proj = { __fmul_rn(lon, kPiInv), __fmul_rn(lat, kTwoPiInv) };
+		}
+		if (in_view) {
 			// 3-D covariance (forward.cu:643-652)
 			float cov6[6];
 			if (a.cov3D_precomp != nullptr) {
@@ -118,8 +132,9 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 				for (int i = 0; i < 6; i++) a.cov3D[6 * (size_t)idx + i] = cov6[i];
 			}
 
-			// 2-D covariance through the lonlat Jacobian + 0.3 px blur (forward.cu:130-189)
-			const float3 cov = cov2d_lonlat_p(t, V, cov6, a.W, a.H);
+			// 2-D covariance through the camera's Jacobian + 0.3 px blur (forward.cu:130-189; pinhole :86-128)
+			const float3 cov = kPinhole ? cov2d_pinhole_p(t, V, cov6, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy)
+			                            : cov2d_lonlat_p(t, V, cov6, a.W, a.H);
 
 			// conic (forward.cu:660-664)
 			const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
@@ -206,6 +221,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 			rgb = { a.colors_precomp[3 * (size_t)idx], a.colors_precomp[3 * (size_t)idx + 1],
 			        a.colors_precomp[3 * (size_t)idx + 2] };
 		}
+		if (kPinhole && a.render_depth) rgb = { r, r, r };   // renderDepthCUDA blends the depth in all channels (forward.cu:566-567)
 		a.clamped[idx] = (uint8_t)cmask;
 		// so is the packed record: its conic turns the summed raw accumulators into gradients (preprocess_bwd.cu)
 		a.g0[idx] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
@@ -257,7 +273,12 @@ __global__ void mark_all_visible_kernel(int P, uint8_t* present)
 int launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t st)
 {
 	const int blocks = ceil_div(a.P, kPreThreads);
-	if (a.raw) {
+	if (a.pinhole) {
+		if (a.shs != nullptr && sh_rows_bulk_capable(a.shs, a.M))
+			preprocess_lonlat_fwd_kernel<1, true><<<blocks, kPreThreads, 0, st>>>(a);
+		else
+			preprocess_lonlat_fwd_kernel<0, true><<<blocks, kPreThreads, 0, st>>>(a);
+	} else if (a.raw) {
 		if (sh_rows_bulk_capable(a.features_rest, a.M) && sh_rows_bulk_capable(a.features_dc, a.M))
 			preprocess_lonlat_fwd_kernel<2><<<blocks, kPreThreads, 0, st>>>(a);
 		else
@@ -266,6 +287,26 @@ int launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t st)
 		preprocess_lonlat_fwd_kernel<1><<<blocks, kPreThreads, 0, st>>>(a);
 	else
 		preprocess_lonlat_fwd_kernel<0><<<blocks, kPreThreads, 0, st>>>(a);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+// checkFrustum (rasterizer_impl.cu:64-77 with in_frustum, auxiliary.h:166-196): only z > 0.2 in camera space
+__global__ void check_frustum_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ viewmatrix,
+                                     uint8_t* present)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	float V[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++) V[k] = viewmatrix[k];
+	const float3 t = view_point_p(V, float3{ means3D[3 * (size_t)i], means3D[3 * (size_t)i + 1], means3D[3 * (size_t)i + 2] });
+	present[i] = (t.z <= 0.2f) ? 0 : 1;
+}
+
+int launch_check_frustum(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st)
+{
+	check_frustum_kernel<<<ceil_div(P, 256), 256, 0, st>>>(P, means3D, viewmatrix, present);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }

@@ -8,7 +8,7 @@
 //   * work is launched on torch's current CUDA stream (the reference uses the legacy default one);
 //   * gradients are allocated with empty(): the library writes every element, so the reference's
 //     324 B/Gaussian of zero-fill (:200-208,246-247) disappears;
-//   * camera_type == 1 (pinhole) is not part of this library and raises.
+//   * camera_type == 1 (pinhole, with render_depth) and 3 (lonlat) both run through the same library kernels.
 #include "rasterize_points.h"
 
 #include <ATen/cuda/CUDAContext.h>
@@ -33,11 +33,9 @@ void check(int status)
 		throw std::runtime_error(std::string("[omnigs_b200] error ") + std::to_string(status) + ": " + ogs_last_error());
 }
 
-[[noreturn]] void reject_camera(int camera_type)
+void check_camera(int camera_type)
 {
-	if (camera_type == 1)
-		throw std::runtime_error("[omnigs_b200] camera_type 1 (pinhole) is outside this library's scope; use 3 (LONLAT)");
-	throw std::runtime_error("[CudaRasterizer]Invalid camera_type");
+	if (camera_type != 1 && camera_type != 3) throw std::runtime_error("[CudaRasterizer]Invalid camera_type");
 }
 
 } // namespace
@@ -51,7 +49,7 @@ RasterizeGaussiansCUDA(
 	const int image_height, const int image_width, const torch::Tensor& sh, const int degree,
 	const torch::Tensor& campos, const bool prefiltered, const int camera_type, const bool render_depth)
 {
-	(void)projmatrix; (void)tan_fovx; (void)tan_fovy; (void)prefiltered; (void)render_depth; // unused in lonlat mode
+	(void)prefiltered;
 	if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
 		AT_ERROR("means3D must have dimensions (num_points, 3)");
 	}
@@ -69,7 +67,7 @@ RasterizeGaussiansCUDA(
 	int rendered = 0;
 	if (P == 0) // the reference launches nothing and returns its zero-filled outputs (:84-85,97)
 		return std::make_tuple(rendered, torch::zeros({kNumChannels, H, W}, float_opts), radii, geomBuffer, binningBuffer, imgBuffer);
-	if (camera_type != 3) reject_camera(camera_type);
+	check_camera(camera_type);
 
 	c10::cuda::CUDAGuard guard(means3D.device());
 	cudaStream_t stream = at::cuda::getCurrentCUDAStream();
@@ -80,15 +78,21 @@ RasterizeGaussiansCUDA(
 	const torch::Tensor bg = background.contiguous(), m3 = means3D.contiguous(), col = colors.contiguous(),
 	                    op = opacity.contiguous(), sc = scales.contiguous(), rot = rotations.contiguous(),
 	                    cov = cov3D_precomp.contiguous(), vm = viewmatrix.contiguous(), shc = sh.contiguous(),
-	                    cam = campos.contiguous();
+	                    cam = campos.contiguous(), pm = projmatrix.contiguous();
 
 	torch::Tensor out_color = torch::empty({kNumChannels, H, W}, float_opts);
 	geomBuffer = torch::empty({(int64_t)ogs_geom_bytes(P)}, byte_opts);
 	imgBuffer = torch::empty({(int64_t)ogs_img_bytes(W, H)}, byte_opts);
 	int64_t num_rendered = 0;
-	check(ogs_lonlat_forward_stage1(P, degree, M, W, H, fptr(m3), fptr(shc), fptr(col), fptr(op), fptr(sc),
-	                                scale_modifier, fptr(rot), fptr(cov), fptr(vm), fptr(cam),
-	                                radii.data_ptr<int>(), bptr(geomBuffer), bptr(imgBuffer), &num_rendered, stream));
+	if (camera_type == 1) // PINHOLE (rasterize_points.cu:105-132)
+		check(ogs_pinhole_forward_stage1(P, degree, M, W, H, fptr(m3), fptr(shc), fptr(col), fptr(op), fptr(sc),
+		                                 scale_modifier, fptr(rot), fptr(cov), fptr(vm), fptr(pm), fptr(cam), tan_fovx,
+		                                 tan_fovy, render_depth ? 1 : 0, radii.data_ptr<int>(), bptr(geomBuffer),
+		                                 bptr(imgBuffer), &num_rendered, stream));
+	else
+		check(ogs_lonlat_forward_stage1(P, degree, M, W, H, fptr(m3), fptr(shc), fptr(col), fptr(op), fptr(sc),
+		                                scale_modifier, fptr(rot), fptr(cov), fptr(vm), fptr(cam),
+		                                radii.data_ptr<int>(), bptr(geomBuffer), bptr(imgBuffer), &num_rendered, stream));
 	binningBuffer = torch::empty({(int64_t)ogs_binning_bytes(num_rendered, W, H)}, byte_opts);
 	check(ogs_lonlat_forward_stage2(P, W, H, num_rendered, fptr(bg), bptr(geomBuffer), bptr(binningBuffer),
 	                                bptr(imgBuffer), out_color.data_ptr<float>(), stream));
@@ -106,7 +110,6 @@ RasterizeGaussiansBackwardCUDA(
 	const torch::Tensor& geomBuffer, const int R, const torch::Tensor& binningBuffer,
 	const torch::Tensor& imageBuffer, const int camera_type)
 {
-	(void)projmatrix; (void)tan_fovx; (void)tan_fovy;
 	const int P = means3D.size(0);
 	const int H = dL_dout_color.size(1);
 	const int W = dL_dout_color.size(2);
@@ -127,34 +130,49 @@ RasterizeGaussiansBackwardCUDA(
 	torch::Tensor dL_drotations = alloc({P, 4});
 
 	if (P != 0) {
-		if (camera_type != 3) reject_camera(camera_type);
+		check_camera(camera_type);
 		c10::cuda::CUDAGuard guard(means3D.device());
 		cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+		const torch::Tensor pm = projmatrix.contiguous();
 		const torch::Tensor bg = background.contiguous(), m3 = means3D.contiguous(), col = colors.contiguous(),
 		                    sc = scales.contiguous(), rot = rotations.contiguous(), cov = cov3D_precomp.contiguous(),
 		                    vm = viewmatrix.contiguous(), shc = sh.contiguous(), cam = campos.contiguous(),
 		                    dL = dL_dout_color.contiguous(), rad = radii.contiguous(), gb = geomBuffer.contiguous(),
 		                    bb = binningBuffer.contiguous(), ib = imageBuffer.contiguous();
-		check(ogs_lonlat_backward(P, degree, M, R, W, H, fptr(bg), fptr(m3), fptr(shc), fptr(col), fptr(sc),
-		                          scale_modifier, fptr(rot), fptr(cov), fptr(vm), fptr(cam), rad.data_ptr<int>(),
-		                          bptr(gb), bptr(bb), bptr(ib), fptr(dL),
-		                          dL_dmeans2D.data_ptr<float>(), nullptr, dL_dopacity.data_ptr<float>(),
-		                          dL_dcolors.data_ptr<float>(), dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(),
-		                          M ? dL_dsh.data_ptr<float>() : nullptr, dL_dscales.data_ptr<float>(),
-		                          dL_drotations.data_ptr<float>(), stream));
+		if (camera_type == 1) // PINHOLE (rasterize_points.cu:212-243)
+			check(ogs_pinhole_backward(P, degree, M, R, W, H, fptr(bg), fptr(m3), fptr(shc), fptr(col), fptr(sc),
+			                           scale_modifier, fptr(rot), fptr(cov), fptr(vm), fptr(pm), fptr(cam), tan_fovx, tan_fovy,
+			                           rad.data_ptr<int>(), bptr(gb), bptr(bb), bptr(ib), fptr(dL),
+			                           dL_dmeans2D.data_ptr<float>(), nullptr, dL_dopacity.data_ptr<float>(),
+			                           dL_dcolors.data_ptr<float>(), dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(),
+			                           M ? dL_dsh.data_ptr<float>() : nullptr, dL_dscales.data_ptr<float>(),
+			                           dL_drotations.data_ptr<float>(), stream));
+		else
+			check(ogs_lonlat_backward(P, degree, M, R, W, H, fptr(bg), fptr(m3), fptr(shc), fptr(col), fptr(sc),
+			                          scale_modifier, fptr(rot), fptr(cov), fptr(vm), fptr(cam), rad.data_ptr<int>(),
+			                          bptr(gb), bptr(bb), bptr(ib), fptr(dL),
+			                          dL_dmeans2D.data_ptr<float>(), nullptr, dL_dopacity.data_ptr<float>(),
+			                          dL_dcolors.data_ptr<float>(), dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(),
+			                          M ? dL_dsh.data_ptr<float>() : nullptr, dL_dscales.data_ptr<float>(),
+			                          dL_drotations.data_ptr<float>(), stream));
 	}
 	return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations);
 }
 
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix, const int camera_type)
 {
-	(void)viewmatrix; (void)projmatrix;
 	const int P = means3D.size(0);
 	torch::Tensor present = torch::full({P}, false, means3D.options().dtype(at::kBool));
 	if (P != 0) {
-		if (camera_type != 3) reject_camera(camera_type);
+		check_camera(camera_type);
 		c10::cuda::CUDAGuard guard(means3D.device());
-		check(ogs_mark_all_visible(P, reinterpret_cast<uint8_t*>(present.data_ptr<bool>()), at::cuda::getCurrentCUDAStream()));
+		uint8_t* out = reinterpret_cast<uint8_t*>(present.data_ptr<bool>());
+		if (camera_type == 1) { // checkFrustum (rasterize_points.cu:299-306)
+			const torch::Tensor m3 = means3D.contiguous(), vm = viewmatrix.contiguous(), pm = projmatrix.contiguous();
+			check(ogs_mark_visible_pinhole(P, fptr(m3), fptr(vm), fptr(pm), out, at::cuda::getCurrentCUDAStream()));
+		} else {
+			check(ogs_mark_all_visible(P, out, at::cuda::getCurrentCUDAStream()));
+		}
 	}
 	return present;
 }

@@ -4,8 +4,9 @@ Same names, argument order/meaning, return tuples and error behaviour as
 ``RasterizeGaussiansCUDA`` / ``RasterizeGaussiansBackwardCUDA`` / ``markVisible`` in the reference's
 src/rasterize_points.cu:49-319 (declared in include/rasterize_points.h:29-80), implemented on the
 C ABI of libomnigs_b200.so.  ``camera_type == 3`` (LONLAT) is the hot path this package covers;
-``camera_type == 1`` (pinhole) is outside its scope and raises NotImplementedError; any other value
-raises the reference's RuntimeError.  The C++ twin of this file is csrc/rasterize_points.cpp.
+``camera_type == 1`` (pinhole, with ``render_depth``) runs through the same kernels (SURVEY.md §8 f-4);
+any other value raises the reference's RuntimeError.  The C++ twin of this file is
+csrc/rasterize_points.cpp.
 """
 import ctypes
 
@@ -61,7 +62,7 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
     Returns (num_rendered, out_color[3,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer);
     the three uint8 buffers are opaque and only meaningful to RasterizeGaussiansBackwardCUDA.
     projmatrix, tan_fovx, tan_fovy, prefiltered and render_depth are ignored in lonlat mode, as in
-    the reference.
+    the reference; with camera_type == 1 they drive the perspective path (rasterize_points.cu:105-132).
 
     ``band=(ty0, ty1)`` (extension) restricts binning and blending to tile rows
     [ty0, ty1): pixels outside the band come back as background, ``radii`` stay the full-frame radii, and
@@ -83,10 +84,10 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
 
     rendered = 0
     if P != 0:
-        if camera_type == PINHOLE:
-            raise NotImplementedError("camera_type=1 (pinhole) is outside this package's scope; use LONLAT (3)")
-        if camera_type != LONLAT:
+        if camera_type not in (PINHOLE, LONLAT):
             raise RuntimeError("[CudaRasterizer]Invalid camera_type")
+        if camera_type == PINHOLE and band is not None:
+            raise RuntimeError("latitude bands are a lonlat extension")
         M = int(sh.size(1)) if sh.size(0) != 0 else 0
         with torch.cuda.device(device):
             out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
@@ -101,7 +102,14 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
                       _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
                       _ptr(viewmatrix), _ptr(campos),
                       _ptr(radii), _ptr(geomBuffer), _ptr(imgBuffer), ctypes.byref(n), st)
-            if band is None:
+            if camera_type == PINHOLE:
+                projmatrix = _f32c(projmatrix)
+                check(lib.ogs_pinhole_forward_stage1(
+                    P, int(degree), M, W, H, _ptr(means3D_c), _ptr(sh), _ptr(colors), _ptr(opacity),
+                    _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                    _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
+                    1 if render_depth else 0, _ptr(radii), _ptr(geomBuffer), _ptr(imgBuffer), ctypes.byref(n), st))
+            elif band is None:
                 check(lib.ogs_lonlat_forward_stage1(P, int(degree), M, W, H, *common))
             else:
                 check(lib.ogs_lonlat_forward_stage1_band(P, int(degree), M, W, H, int(band[0]), int(band[1]), *common))
@@ -152,9 +160,7 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
     dL_dscales = alloc((P, 3), **opts)
     dL_drotations = alloc((P, 4), **opts)
     if P != 0:
-        if camera_type == PINHOLE:
-            raise NotImplementedError("camera_type=1 (pinhole) is outside this package's scope; use LONLAT (3)")
-        if camera_type != LONLAT:
+        if camera_type not in (PINHOLE, LONLAT):
             raise RuntimeError("[CudaRasterizer]Invalid camera_type")
         with torch.cuda.device(device):
             background, means3D_c, colors, scales, rotations, cov3D_precomp, viewmatrix, sh, campos, dL = (
@@ -163,7 +169,15 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
             radii_c = radii.contiguous()
             outs = (_ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors),
                     _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
-            if reduce_accumulators is None:
+            if camera_type == PINHOLE:
+                projmatrix = _f32c(projmatrix)
+                check(lib.ogs_pinhole_backward(
+                    P, int(degree), M, int(R), W, H,
+                    _ptr(background), _ptr(means3D_c), _ptr(sh), _ptr(colors),
+                    _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                    _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy), _ptr(radii_c),
+                    _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer), _ptr(dL), *outs, _stream(device)))
+            elif reduce_accumulators is None:
                 check(lib.ogs_lonlat_backward(
                     P, int(degree), M, int(R), W, H,
                     _ptr(background), _ptr(means3D_c), _ptr(sh), _ptr(colors),
@@ -186,17 +200,20 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
 
 
 def markVisible(means3D, viewmatrix, projmatrix, camera_type=PINHOLE):
-    """reference src/rasterize_points.cu:287-319 (lonlat: every Gaussian is marked visible)."""
+    """reference src/rasterize_points.cu:287-319 (lonlat: every Gaussian is marked visible; pinhole: near-plane test)."""
     _require_cuda(means3D, "means3D")
     P = int(means3D.size(0))
     present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
     if P != 0:
-        if camera_type == PINHOLE:
-            raise NotImplementedError("camera_type=1 (pinhole) is outside this package's scope; use LONLAT (3)")
-        if camera_type != LONLAT:
+        if camera_type not in (PINHOLE, LONLAT):
             raise RuntimeError("[CudaRasterizer]Invalid camera_type")
         with torch.cuda.device(means3D.device):
-            check(load_library().ogs_mark_all_visible(P, _ptr(present), _stream(means3D.device)))
+            if camera_type == PINHOLE:
+                check(load_library().ogs_mark_visible_pinhole(
+                    P, _ptr(_f32c(means3D)), _ptr(_f32c(viewmatrix)), _ptr(_f32c(projmatrix)), _ptr(present),
+                    _stream(means3D.device)))
+            else:
+                check(load_library().ogs_mark_all_visible(P, _ptr(present), _stream(means3D.device)))
     return present
 
 

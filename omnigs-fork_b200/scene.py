@@ -105,6 +105,25 @@ def random_view(seed, ball=0.3):
     return Tcw.T.astype(np.float32).copy(), c.astype(np.float32)
 
 
+def perspective_view(seed, W, H, fovx_deg=90.0, znear=0.01, zfar=100.0, ball=0.3):
+    """A random pinhole camera (camera_type 1): (viewmatrix = Tcw^T, projmatrix = full transform, campos,
+    tan_fovx, tan_fovy).  The projection is the reference's getProjectionMatrix (3DGS convention: z in [0,1],
+    w = z_cam) and projmatrix = viewmatrix @ P^T in row-major terms, i.e. flat element [4*c + r] = (P Tcw)[r, c]
+    (reference src/gaussian_keyframe.cpp:142-160)."""
+    V, c = random_view(seed, ball)
+    tan_fovx = math.tan(math.radians(fovx_deg) / 2)
+    tan_fovy = tan_fovx * H / W
+    top, right = tan_fovy * znear, tan_fovx * znear
+    P = np.zeros((4, 4))
+    P[0, 0] = znear / right
+    P[1, 1] = znear / top
+    P[3, 2] = 1.0
+    P[2, 2] = zfar / (zfar - znear)
+    P[2, 3] = -(zfar * znear) / (zfar - znear)
+    full = (V.astype(np.float64) @ P.T).astype(np.float32)
+    return V, np.ascontiguousarray(full), c, np.float32(tan_fovx).item(), np.float32(tan_fovy).item()
+
+
 def yaw_view(angle):
     """Camera at the origin rotated by `angle` about the vertical (y) axis."""
     c, s = math.cos(angle), math.sin(angle)

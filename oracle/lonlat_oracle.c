@@ -808,3 +808,231 @@ void ogs_oracle_preprocess_bwd(
 			cov3d_bwd(idx, scales + 3 * idx, scale_modifier, rotations + 4 * idx, dL_dcov3D, dL_dscale, dL_drot);
 	}
 }
+
+/* ================================================================ perspective camera (camera_type 1)
+ * The binning and blend restatements above are camera independent (the reference uses the same kernels);
+ * only the two per-Gaussian steps differ. */
+
+/* auxiliary.h:95-105 transformPoint4x4 */
+static void proj_point(const float* M, const float* p, float* h)
+{
+	h[0] = M[0] * p[0] + M[4] * p[1] + M[8] * p[2] + M[12];
+	h[1] = M[1] * p[0] + M[5] * p[1] + M[9] * p[2] + M[13];
+	h[2] = M[2] * p[0] + M[6] * p[1] + M[10] * p[2] + M[14];
+	h[3] = M[3] * p[0] + M[7] * p[1] + M[11] * p[2] + M[15];
+}
+
+/* forward.cu:94-108 / backward.cu:179-196: frustum clamp of t.x, t.y and the perspective Jacobian */
+static lonlat_jac pinhole_jacobian(float* t, float focal_x, float focal_y, float tan_fovx, float tan_fovy,
+                                   float* x_grad_mul, float* y_grad_mul)
+{
+	const float limx = 1.3f * tan_fovx;
+	const float limy = 1.3f * tan_fovy;
+	const float txtz = t[0] / t[2];
+	const float tytz = t[1] / t[2];
+	t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
+	t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
+	*x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+	*y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+	lonlat_jac J;
+	J.j00 = focal_x / t[2];
+	J.j02 = -(focal_x * t[0]) / (t[2] * t[2]);
+	J.j10 = 0.0f;
+	J.j11 = focal_y / t[2];
+	J.j12 = -(focal_y * t[1]) / (t[2] * t[2]);
+	return J;
+}
+
+/* forward.cu:232-340 preprocessCUDA (with in_frustum, auxiliary.h:166-196, and computeCov2D, forward.cu:86-128).
+ * render_depth != 0: rgb = depth in all channels, what renderDepthCUDA blends (forward.cu:566-567). */
+int64_t ogs_oracle_pinhole_preprocess_fwd(
+	int P, int D, int M,
+	const float* means3D, const float* scales, float scale_modifier, const float* rotations,
+	const float* opacities, const float* shs, const float* cov3D_precomp, const float* colors_precomp,
+	const float* viewmatrix, const float* projmatrix, const float* campos, int W, int H,
+	float tan_fovx, float tan_fovy, int render_depth,
+	int32_t* radii, float* means2D, float* depths, float* cov3D, float* rgb,
+	float* conic_opacity, uint32_t* tiles_touched, uint32_t* point_offsets, uint8_t* clamped)
+{
+	const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+	const float* V = viewmatrix;
+	const float focal_y = H / (2.0f * tan_fovy);  /* rasterizer_impl.cu:274-276 */
+	const float focal_x = W / (2.0f * tan_fovx);
+
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+	for (int idx = 0; idx < P; idx++) {
+		radii[idx] = 0;
+		tiles_touched[idx] = 0;
+
+		float p_view[3];
+		view_point(V, means3D + 3 * idx, p_view);
+		if (p_view[2] <= 0.2f) continue;   /* in_frustum */
+
+		float p_hom[4];
+		proj_point(projmatrix, means3D + 3 * idx, p_hom);
+		float p_w = 1.0f / (p_hom[3] + EPS7);
+		float sx = p_hom[0] * p_w, sy = p_hom[1] * p_w;
+
+		const float* c6;
+		if (cov3D_precomp) c6 = cov3D_precomp + 6 * (size_t)idx;
+		else {
+			cov3d_from_scale_rot(scales + 3 * idx, scale_modifier, rotations + 4 * idx, cov3D + 6 * (size_t)idx);
+			c6 = cov3D + 6 * (size_t)idx;
+		}
+
+		float t[3];
+		view_point(V, means3D + 3 * idx, t);
+		float gmx, gmy;
+		lonlat_jac J = pinhole_jacobian(t, focal_x, focal_y, tan_fovx, tan_fovy, &gmx, &gmy);
+		m3 T, Vrk, cov;
+		lonlat_T_and_cov(&J, V, c6, &T, &Vrk, &cov);
+		cov.c[0][0] += 0.3f;
+		cov.c[1][1] += 0.3f;
+		float cx = cov.c[0][0], cy = cov.c[0][1], cz = cov.c[1][1];
+
+		float det = (cx * cz - cy * cy);
+		if (det == 0.0f) continue;
+		float det_inv = 1.f / det;
+		float conic[3] = { cz * det_inv, -cy * det_inv, cx * det_inv };
+
+		float mid = 0.5f * (cx + cz);
+		float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+		float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+		float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+
+		float px = ndc_to_pix(sx, W), py = ndc_to_pix(sy, H);
+		int x0, y0, x1, y1;
+		tile_rect(px, py, (int)my_radius, gx, gy, &x0, &y0, &x1, &y1);
+		if ((x1 - x0) * (y1 - y0) == 0) continue;
+
+		if (!colors_precomp)
+			sh_to_rgb(idx, D, M, means3D, campos, shs, clamped, rgb + 3 * (size_t)idx);
+		if (render_depth)
+			rgb[3 * (size_t)idx] = rgb[3 * (size_t)idx + 1] = rgb[3 * (size_t)idx + 2] = p_view[2];
+
+		depths[idx] = p_view[2];
+		radii[idx] = (int32_t)my_radius;
+		means2D[2 * idx] = px; means2D[2 * idx + 1] = py;
+		conic_opacity[4 * idx + 0] = conic[0];
+		conic_opacity[4 * idx + 1] = conic[1];
+		conic_opacity[4 * idx + 2] = conic[2];
+		conic_opacity[4 * idx + 3] = opacities[idx];
+		tiles_touched[idx] = (uint32_t)((y1 - y0) * (x1 - x0));
+	}
+	uint32_t acc = 0;
+	for (int i = 0; i < P; i++) { acc += tiles_touched[i]; point_offsets[i] = acc; }
+	return P > 0 ? (int64_t)(int32_t)point_offsets[P - 1] : 0;
+}
+
+/* backward.cu:156-292 computeCov2DCUDA + :558-608 preprocessCUDA */
+void ogs_oracle_pinhole_preprocess_bwd(
+	int P, int D, int M,
+	const float* means3D, const int32_t* radii, const float* shs, const uint8_t* clamped,
+	const float* scales, const float* rotations, float scale_modifier, const float* cov3D,
+	const float* viewmatrix, const float* projmatrix, int W, int H, float tan_fovx, float tan_fovy, const float* campos,
+	const float* dL_dmean2D, const float* dL_dconic, float* dL_dcolor,
+	float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot)
+{
+	const float* V = viewmatrix;
+	const float* proj = projmatrix;
+	const float h_y = H / (2.0f * tan_fovy);  /* rasterizer_impl.cu:476-477 */
+	const float h_x = W / (2.0f * tan_fovx);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+	for (int idx = 0; idx < P; idx++) {
+		if (!(radii[idx] > 0)) continue;
+		const float* c6 = cov3D + 6 * (size_t)idx;
+		float gx_ = dL_dconic[4 * (size_t)idx], gy_ = dL_dconic[4 * (size_t)idx + 1], gz_ = dL_dconic[4 * (size_t)idx + 3];
+		float t[3];
+		view_point(V, means3D + 3 * idx, t);
+		float x_grad_mul, y_grad_mul;
+		lonlat_jac Jv = pinhole_jacobian(t, h_x, h_y, tan_fovx, tan_fovy, &x_grad_mul, &y_grad_mul);
+		m3 T, Vrk, cov2D;
+		lonlat_T_and_cov(&Jv, V, c6, &T, &Vrk, &cov2D);
+		m3 Wm = m3_cols(V[0], V[4], V[8], V[1], V[5], V[9], V[2], V[6], V[10]);
+
+		float a = cov2D.c[0][0] += 0.3f;
+		float b = cov2D.c[0][1];
+		float c = cov2D.c[1][1] += 0.3f;
+		float denom = a * c - b * b;
+		float dL_da = 0, dL_db = 0, dL_dc = 0;
+		float denom2inv = 1.0f / ((denom * denom) + EPS7);
+		float* dcov = dL_dcov3D + 6 * (size_t)idx;
+#define Tm(i, j) T.c[i][j]
+		if (denom2inv != 0) {
+			dL_da = denom2inv * (-c * c * gx_ + 2 * b * c * gy_ + (denom - a * c) * gz_);
+			dL_dc = denom2inv * (-a * a * gz_ + 2 * a * b * gy_ + (denom - a * c) * gx_);
+			dL_db = denom2inv * 2 * (b * c * gx_ - (denom + 2 * b * b) * gy_ + a * b * gz_);
+			dcov[0] = (Tm(0, 0) * Tm(0, 0) * dL_da + Tm(0, 0) * Tm(1, 0) * dL_db + Tm(1, 0) * Tm(1, 0) * dL_dc);
+			dcov[3] = (Tm(0, 1) * Tm(0, 1) * dL_da + Tm(0, 1) * Tm(1, 1) * dL_db + Tm(1, 1) * Tm(1, 1) * dL_dc);
+			dcov[5] = (Tm(0, 2) * Tm(0, 2) * dL_da + Tm(0, 2) * Tm(1, 2) * dL_db + Tm(1, 2) * Tm(1, 2) * dL_dc);
+			dcov[1] = 2 * Tm(0, 0) * Tm(0, 1) * dL_da + (Tm(0, 0) * Tm(1, 1) + Tm(0, 1) * Tm(1, 0)) * dL_db + 2 * Tm(1, 0) * Tm(1, 1) * dL_dc;
+			dcov[2] = 2 * Tm(0, 0) * Tm(0, 2) * dL_da + (Tm(0, 0) * Tm(1, 2) + Tm(0, 2) * Tm(1, 0)) * dL_db + 2 * Tm(1, 0) * Tm(1, 2) * dL_dc;
+			dcov[4] = 2 * Tm(0, 2) * Tm(0, 1) * dL_da + (Tm(0, 1) * Tm(1, 2) + Tm(0, 2) * Tm(1, 1)) * dL_db + 2 * Tm(1, 1) * Tm(1, 2) * dL_dc;
+		} else {
+			for (int i = 0; i < 6; i++) dcov[i] = 0;
+		}
+#define Vk(i, j) Vrk.c[i][j]
+		float dL_dT00 = 2 * (Tm(0, 0) * Vk(0, 0) + Tm(0, 1) * Vk(0, 1) + Tm(0, 2) * Vk(0, 2)) * dL_da +
+			(Tm(1, 0) * Vk(0, 0) + Tm(1, 1) * Vk(0, 1) + Tm(1, 2) * Vk(0, 2)) * dL_db;
+		float dL_dT01 = 2 * (Tm(0, 0) * Vk(1, 0) + Tm(0, 1) * Vk(1, 1) + Tm(0, 2) * Vk(1, 2)) * dL_da +
+			(Tm(1, 0) * Vk(1, 0) + Tm(1, 1) * Vk(1, 1) + Tm(1, 2) * Vk(1, 2)) * dL_db;
+		float dL_dT02 = 2 * (Tm(0, 0) * Vk(2, 0) + Tm(0, 1) * Vk(2, 1) + Tm(0, 2) * Vk(2, 2)) * dL_da +
+			(Tm(1, 0) * Vk(2, 0) + Tm(1, 1) * Vk(2, 1) + Tm(1, 2) * Vk(2, 2)) * dL_db;
+		float dL_dT10 = 2 * (Tm(1, 0) * Vk(0, 0) + Tm(1, 1) * Vk(0, 1) + Tm(1, 2) * Vk(0, 2)) * dL_dc +
+			(Tm(0, 0) * Vk(0, 0) + Tm(0, 1) * Vk(0, 1) + Tm(0, 2) * Vk(0, 2)) * dL_db;
+		float dL_dT11 = 2 * (Tm(1, 0) * Vk(1, 0) + Tm(1, 1) * Vk(1, 1) + Tm(1, 2) * Vk(1, 2)) * dL_dc +
+			(Tm(0, 0) * Vk(1, 0) + Tm(0, 1) * Vk(1, 1) + Tm(0, 2) * Vk(1, 2)) * dL_db;
+		float dL_dT12 = 2 * (Tm(1, 0) * Vk(2, 0) + Tm(1, 1) * Vk(2, 1) + Tm(1, 2) * Vk(2, 2)) * dL_dc +
+			(Tm(0, 0) * Vk(2, 0) + Tm(0, 1) * Vk(2, 1) + Tm(0, 2) * Vk(2, 2)) * dL_db;
+#undef Vk
+#undef Tm
+#define Wk(i, j) Wm.c[i][j]
+		float dL_dJ00 = Wk(0, 0) * dL_dT00 + Wk(0, 1) * dL_dT01 + Wk(0, 2) * dL_dT02;
+		float dL_dJ02 = Wk(2, 0) * dL_dT00 + Wk(2, 1) * dL_dT01 + Wk(2, 2) * dL_dT02;
+		float dL_dJ11 = Wk(1, 0) * dL_dT10 + Wk(1, 1) * dL_dT11 + Wk(1, 2) * dL_dT12;
+		float dL_dJ12 = Wk(2, 0) * dL_dT10 + Wk(2, 1) * dL_dT11 + Wk(2, 2) * dL_dT12;
+#undef Wk
+		/* backward.cu:270-283 */
+		float tz = 1.f / t[2];
+		float tz2 = tz * tz;
+		float tz3 = tz2 * tz;
+		float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+		float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+		float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t[0]) * tz3 * dL_dJ02 + (2 * h_y * t[1]) * tz3 * dL_dJ12;
+		float dLdt[3] = { dL_dtx, dL_dty, dL_dtz }, dmean[3];
+		view_vec_transpose(V, dLdt, dmean);
+		float* dm = dL_dmeans3D + 3 * (size_t)idx;
+		dm[0] = dmean[0]; dm[1] = dmean[1]; dm[2] = dmean[2];   /* assignment, backward.cu:291 */
+
+		/* backward.cu:579-597: screen position through the full projection */
+		const float* m = means3D + 3 * (size_t)idx;
+		float m_hom[4];
+		proj_point(proj, m, m_hom);
+		float m_w = 1.0f / (m_hom[3] + EPS7);
+		float mul1 = (proj[0] * m[0] + proj[4] * m[1] + proj[8] * m[2] + proj[12]) * m_w * m_w;
+		float mul2 = (proj[1] * m[0] + proj[5] * m[1] + proj[9] * m[2] + proj[13]) * m_w * m_w;
+		float g2x = dL_dmean2D[3 * (size_t)idx + 0], g2y = dL_dmean2D[3 * (size_t)idx + 1];
+		dm[0] += (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
+		dm[1] += (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
+		dm[2] += (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
+
+		if (shs)
+			sh_bwd(idx, D, M, means3D, campos, shs, clamped, dL_dcolor, dL_dmeans3D, dL_dsh);
+		if (scales)
+			cov3d_bwd(idx, scales + 3 * idx, scale_modifier, rotations + 4 * idx, dL_dcov3D, dL_dscale, dL_drot);
+	}
+}
+
+/* rasterizer_impl.cu:64-77 checkFrustum */
+void ogs_oracle_pinhole_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present)
+{
+	for (int idx = 0; idx < P; idx++) {
+		float p_view[3];
+		view_point(viewmatrix, means3D + 3 * idx, p_view);
+		present[idx] = (p_view[2] <= 0.2f) ? 0 : 1;
+	}
+}

@@ -96,6 +96,30 @@ void ogs_oracle_preprocess_bwd(
 	float* dL_dmeans3D /*P*3*/, float* dL_dcov3D /*P*6*/, float* dL_dsh /*P*M*3*/,
 	float* dL_dscale /*P*3*/, float* dL_drot /*P*4*/, float* dpx_dt /*P*3*/, float* dpy_dt /*P*3*/);
 
+/*
+ * Perspective camera (camera_type 1).  Binning and blending are the functions above (the
+ * reference shares those kernels between cameras); these restate the two per-Gaussian steps:
+ * forward.cu:232-340 (preprocessCUDA, with in_frustum auxiliary.h:166-196 and computeCov2D forward.cu:86-128;
+ * render_depth: what renderDepthCUDA blends, forward.cu:472-590), backward.cu:156-292 + :558-608, and
+ * checkFrustum (rasterizer_impl.cu:64-77).  projmatrix = full transform, column-major; tan_fov = tan(fov/2).
+ */
+int64_t ogs_oracle_pinhole_preprocess_fwd(
+	int P, int D, int M,
+	const float* means3D, const float* scales, float scale_modifier, const float* rotations,
+	const float* opacities, const float* shs, const float* cov3D_precomp, const float* colors_precomp,
+	const float* viewmatrix, const float* projmatrix, const float* campos, int W, int H,
+	float tan_fovx, float tan_fovy, int render_depth,
+	int32_t* radii, float* means2D, float* depths, float* cov3D, float* rgb,
+	float* conic_opacity, uint32_t* tiles_touched, uint32_t* point_offsets, uint8_t* clamped);
+void ogs_oracle_pinhole_preprocess_bwd(
+	int P, int D, int M,
+	const float* means3D, const int32_t* radii, const float* shs, const uint8_t* clamped,
+	const float* scales, const float* rotations, float scale_modifier, const float* cov3D,
+	const float* viewmatrix, const float* projmatrix, int W, int H, float tan_fovx, float tan_fovy, const float* campos,
+	const float* dL_dmean2D, const float* dL_dconic, float* dL_dcolor,
+	float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot);
+void ogs_oracle_pinhole_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@ def lib():
             build()
         _LIB = ctypes.CDLL(path)
         _LIB.ogs_oracle_preprocess_fwd.restype = ctypes.c_int64
+        _LIB.ogs_oracle_pinhole_preprocess_fwd.restype = ctypes.c_int64
         _LIB.ogs_oracle_higher_msb.restype = ctypes.c_uint32
     return _LIB
 
@@ -50,8 +51,9 @@ def _c(a, dtype=_f):
 
 
 def forward(means3D, opacities, viewmatrix, campos, W, H, background, shs=None, degree=0, colors_precomp=None,
-            scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, want_binning=True):
-    """Reference-order forward.  Returns a dict with every intermediate the reference keeps."""
+            scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, want_binning=True, pinhole=None):
+    """Reference-order forward.  Returns a dict with every intermediate the reference keeps.
+    pinhole = dict(projmatrix=[4,4], tan_fovx=, tan_fovy=, render_depth=False) selects camera_type 1."""
     L = lib()
     means3D = _c(means3D); P = means3D.shape[0]
     opacities = _c(opacities).reshape(-1); viewmatrix = _c(viewmatrix).reshape(-1); campos = _c(campos).reshape(-1)
@@ -64,7 +66,16 @@ def forward(means3D, opacities, viewmatrix, campos, W, H, background, shs=None, 
         cov3D=np.zeros((P, 6), _f), rgb=np.zeros((P, 3), _f), conic_opacity=np.zeros((P, 4), _f),
         tiles_touched=np.zeros(P, np.uint32), point_offsets=np.zeros(P, np.uint32), clamped=np.zeros((P, 3), np.uint8))
     R = 0
-    if P:
+    if P and pinhole is not None:
+        proj = _c(pinhole["projmatrix"]).reshape(-1)
+        R = int(L.ogs_oracle_pinhole_preprocess_fwd(
+            P, int(degree), M, _p(means3D), _p(scales), ctypes.c_float(scale_modifier), _p(rotations), _p(opacities),
+            _p(shs), _p(cov3D_precomp), _p(colors_precomp), _p(viewmatrix), _p(proj), _p(campos), W, H,
+            ctypes.c_float(pinhole["tan_fovx"]), ctypes.c_float(pinhole["tan_fovy"]),
+            1 if pinhole.get("render_depth") else 0,
+            _p(o["radii"]), _p(o["means2D"]), _p(o["depths"]), _p(o["cov3D"]), _p(o["rgb"]), _p(o["conic_opacity"]),
+            _p(o["tiles_touched"]), _p(o["point_offsets"]), _p(o["clamped"])))
+    elif P:
         R = int(L.ogs_oracle_preprocess_fwd(
             P, int(degree), M, _p(means3D), _p(scales), ctypes.c_float(scale_modifier), _p(rotations), _p(opacities),
             _p(shs), _p(cov3D_precomp), _p(colors_precomp), _p(viewmatrix), _p(campos), W, H,
@@ -82,6 +93,8 @@ def forward(means3D, opacities, viewmatrix, campos, W, H, background, shs=None, 
                      ctypes.c_int64(R), _p(o["keys_unsorted"]), _p(o["values_unsorted"]), _p(o["point_list_keys"]),
                      _p(o["point_list"]), _p(o["ranges"]))
     colors = colors_precomp if colors_precomp is not None else o["rgb"]
+    if pinhole is not None and pinhole.get("render_depth"):
+        colors = o["rgb"]           # renderDepthCUDA blends the depth whatever the colour source
     o.update(accum_alpha=np.zeros(H * W, _f), n_contrib=np.zeros(H * W, np.uint32), out_color=np.zeros((3, H, W), _f))
     L.ogs_oracle_render_fwd(W, H, _p(o["ranges"]), _p(o["point_list"]), _p(o["means2D"]), _p(colors),
                             _p(o["conic_opacity"]), _p(background), _p(o["accum_alpha"]), _p(o["n_contrib"]),
@@ -90,7 +103,7 @@ def forward(means3D, opacities, viewmatrix, campos, W, H, background, shs=None, 
 
 
 def backward(fwd, dL_dout_color, means3D, viewmatrix, campos, W, H, background, shs=None, degree=0,
-             colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0):
+             colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None, scale_modifier=1.0, pinhole=None):
     """Reference-order backward from a forward() dict.  Returns the 8 returned gradients + dL_dconic."""
     L = lib()
     means3D = _c(means3D); P = means3D.shape[0]
@@ -108,9 +121,26 @@ def backward(fwd, dL_dout_color, means3D, viewmatrix, campos, W, H, background, 
     L.ogs_oracle_render_bwd(W, H, _p(fwd["ranges"]), _p(fwd["point_list"]), _p(background), _p(fwd["means2D"]),
                             _p(fwd["conic_opacity"]), _p(colors), _p(fwd["accum_alpha"]), _p(fwd["n_contrib"]), _p(dL),
                             _p(g["dL_dmeans2D"]), _p(g["dL_dconic"]), _p(g["dL_dopacity"]), _p(g["dL_dcolors"]))
+    if pinhole is not None:
+        proj = _c(pinhole["projmatrix"]).reshape(-1)
+        L.ogs_oracle_pinhole_preprocess_bwd(
+            P, int(degree), M, _p(means3D), _p(fwd["radii"]), _p(shs), _p(fwd["clamped"]), _p(scales), _p(rotations),
+            ctypes.c_float(scale_modifier), _p(_c(fwd["cov3D"])), _p(viewmatrix), _p(proj), W, H,
+            ctypes.c_float(pinhole["tan_fovx"]), ctypes.c_float(pinhole["tan_fovy"]), _p(campos),
+            _p(g["dL_dmeans2D"]), _p(g["dL_dconic"]), _p(g["dL_dcolors"]), _p(g["dL_dmeans3D"]), _p(g["dL_dcov3D"]),
+            _p(g["dL_dsh"]), _p(g["dL_dscales"]), _p(g["dL_drotations"]))
+        return g
     L.ogs_oracle_preprocess_bwd(
         P, int(degree), M, _p(means3D), _p(fwd["radii"]), _p(shs), _p(fwd["clamped"]), _p(scales), _p(rotations),
         ctypes.c_float(scale_modifier), _p(_c(fwd["cov3D"])), _p(viewmatrix), W, H, _p(campos),
         _p(g["dL_dmeans2D"]), _p(g["dL_dconic"]), _p(g["dL_dcolors"]), _p(g["dL_dmeans3D"]), _p(g["dL_dcov3D"]),
         _p(g["dL_dsh"]), _p(g["dL_dscales"]), _p(g["dL_drotations"]), _p(g["dpx_dt"]), _p(g["dpy_dt"]))
     return g
+
+
+def pinhole_mark_visible(means3D, viewmatrix):
+    """checkFrustum (rasterizer_impl.cu:64-77)."""
+    means3D = _c(means3D); P = means3D.shape[0]
+    present = np.zeros(P, np.uint8)
+    lib().ogs_oracle_pinhole_mark_visible(P, _p(means3D), _p(_c(viewmatrix).reshape(-1)), _p(present))
+    return present.astype(bool)

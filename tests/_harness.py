@@ -28,18 +28,26 @@ def load_reference():
     return importlib.import_module("omnigs_ref")
 
 
-def torch_inputs(scene, view, device="cuda", mode="sh", bg=(0.0, 0.0, 0.0), degree=3):
+def torch_inputs(scene, view, device="cuda", mode="sh", bg=(0.0, 0.0, 0.0), degree=3, render_depth=False):
     """Tensors in the argument convention of RasterizeGaussiansCUDA.
     mode: "sh" (SH + scale/rot, the live combination), "colors" (precomputed colours),
-          "cov" (SH + precomputed 3-D covariance)."""
+          "cov" (SH + precomputed 3-D covariance).
+    view: (viewmatrix, campos) for the lonlat camera, or scene.perspective_view()'s 5-tuple for the pinhole one."""
     import torch
+    pin = None
+    if len(view) == 5:
+        pin = view
+        view = (view[0], view[2])
     V, campos = view
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
     empty = torch.empty((0,), dtype=torch.float32, device=device)
     d = dict(background=torch.tensor(bg, dtype=torch.float32, device=device), means3D=t(scene.means3D),
              opacity=t(scene.opacities), viewmatrix=t(V), projmatrix=t(V), campos=t(campos),
              colors=empty, sh=empty, scales=empty, rotations=empty, cov3D_precomp=empty,
-             scale_modifier=1.0, degree=degree, H=scene.H, W=scene.W)
+             scale_modifier=1.0, degree=degree, H=scene.H, W=scene.W, camera_type=3, tan_fovx=0.0, tan_fovy=0.0,
+             render_depth=False)
+    if pin is not None:
+        d.update(projmatrix=t(pin[1]), camera_type=1, tan_fovx=pin[3], tan_fovy=pin[4], render_depth=bool(render_depth))
     if mode == "colors":
         rng = np.random.Generator(np.random.PCG64(7))
         d["colors"] = t(rng.uniform(0, 1, (scene.P, 3)).astype(np.float32))
@@ -67,16 +75,16 @@ def cov3d_numpy(scales, rot):
 def run_forward(mod, d):
     return mod.RasterizeGaussiansCUDA(
         d["background"], d["means3D"], d["colors"], d["opacity"], d["scales"], d["rotations"], d["scale_modifier"],
-        d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], 0.0, 0.0, d["H"], d["W"], d["sh"], d["degree"],
-        d["campos"], False, 3, False)
+        d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], d.get("tan_fovx", 0.0), d.get("tan_fovy", 0.0),
+        d["H"], d["W"], d["sh"], d["degree"], d["campos"], False, d.get("camera_type", 3), d.get("render_depth", False))
 
 
 def run_backward(mod, d, fwd, dL, **kw):
     R, _, radii, geom, binning, img = fwd
     return mod.RasterizeGaussiansBackwardCUDA(
         d["background"], d["means3D"], radii, d["colors"], d["scales"], d["rotations"], d["scale_modifier"],
-        d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], 0.0, 0.0, dL, d["sh"], d["degree"], d["campos"],
-        geom, R, binning, img, 3, **kw)
+        d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], d.get("tan_fovx", 0.0), d.get("tan_fovy", 0.0), dL,
+        d["sh"], d["degree"], d["campos"], geom, R, binning, img, d.get("camera_type", 3), **kw)
 
 
 def ours_state(d, fwd):

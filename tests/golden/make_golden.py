@@ -19,12 +19,16 @@ os.makedirs(out_dir, exist_ok=True)
 ref = h.load_reference()
 assert ref is not None, "oracle/_ref/omnigs_ref.so missing: run oracle/build_ref.sh where /root/reference exists"
 
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
 for name in cases.CASES:
+    if only and name not in only:
+        continue
     scene, view, dL_np, c = cases.build(name)
-    d = h.torch_inputs(scene, view, mode=c["mode"], bg=c["bg"], degree=c["degree"])
+    d = h.torch_inputs(scene, view, mode=c["mode"], bg=c["bg"], degree=c["degree"], render_depth=c.get("render_depth", False))
     dL = torch.from_numpy(dL_np).cuda()
     fwd = h.run_forward(ref, d)
-    grads = h.run_backward(ref, d, fwd, dL)
+    # the reference's backward has no depth path: render_depth fixtures are forward-only
+    grads = h.run_backward(ref, d, fwd, dL) if not c.get("render_depth") else []
     torch.cuda.synchronize()
     st = h.ref_state(ref, d, fwd)
     vis = (fwd[2] > 0)
@@ -36,6 +40,8 @@ for name in cases.CASES:
         means2D=z(st["means2D"], m1[:, None]), depths=z(st["depths"], m1), conic_opacity=z(st["conic_opacity"], m1[:, None]),
         tiles_touched=z(st["tiles_touched"]), ranges=z(st["ranges"]), point_list=z(st["point_list"]),
         point_list_keys=z(st["point_list_keys"]), accum_alpha=z(st["accum_alpha"]), n_contrib=z(st["n_contrib"]))
+    if d["camera_type"] == 1:
+        out["present"] = ref.markVisible(d["means3D"], d["viewmatrix"], d["projmatrix"], 1).cpu().numpy()
     if c["mode"] != "colors":   # uninitialised in the reference when colours are precomputed
         out["rgb"] = z(st["rgb"], m1[:, None])
         out["clamped"] = z(st["clamped"].to(torch.uint8), m1[:, None])

@@ -22,8 +22,14 @@ def run_oracle(name):
     if c["mode"] == "cov":
         kw.update(scales=None, rotations=None, cov3D_precomp=h.cov3d_numpy(scene.scales, scene.rotations))
     bg = np.array(c["bg"], np.float32)
-    f = oracle.forward(scene.means3D, scene.opacities, view[0], view[1], scene.W, scene.H, bg, **kw)
-    g = oracle.backward(f, dL, scene.means3D, view[0], view[1], scene.W, scene.H, bg, **kw)
+    v = view
+    if len(view) == 5:   # perspective camera: (viewmatrix, projmatrix, campos, tan_fovx, tan_fovy)
+        kw["pinhole"] = dict(projmatrix=view[1], tan_fovx=view[3], tan_fovy=view[4], render_depth=c.get("render_depth", False))
+        v = (view[0], view[2])
+    f = oracle.forward(scene.means3D, scene.opacities, v[0], v[1], scene.W, scene.H, bg, **kw)
+    g = None
+    if not c.get("render_depth"):   # the reference's backward has no depth path
+        g = oracle.backward(f, dL, scene.means3D, v[0], v[1], scene.W, scene.H, bg, **kw)
     return scene, view, dL, c, f, g
 
 
@@ -43,7 +49,9 @@ def test_oracle_matches_reference_outputs(name):
     assert np.abs(f["depths"][both] - gold["depths"][both]).max() < 1e-4
     co_scale = np.abs(gold["conic_opacity"][both]).max(axis=0)
     assert (np.abs(f["conic_opacity"][both] - gold["conic_opacity"][both]).max(axis=0) <= 1e-4 * co_scale + 1e-6).all()
-    if "rgb" in gold:
+    if "present" in gold:   # checkFrustum
+        assert (oracle.pinhole_mark_visible(scene.means3D, view[0]) == gold["present"]).all()
+    if "rgb" in gold and not c.get("render_depth"):
         assert np.abs(f["rgb"][both] - gold["rgb"][both]).max() < 1e-5
         assert int((f["clamped"][both] != gold["clamped"][both]).sum()) <= 2
     if "cov3D" in gold:
@@ -59,7 +67,7 @@ def test_oracle_matches_reference_outputs(name):
     assert (diff > 1e-4).mean() <= 2e-3, float((diff > 1e-4).mean())
     assert diff.max() < 0.1
     assert (f["n_contrib"] != gold["n_contrib"].view(np.uint32)).mean() <= 2e-3
-    for n in h.GRAD_NAMES:
+    for n in h.GRAD_NAMES if g is not None else []:
         a, b = g[n].reshape(gold[n].shape), gold[n]
         if b.size == 0:
             continue

@@ -33,7 +33,7 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-def assert_grads_close(ours, ref, names=h.GRAD_NAMES, ref_again=None):
+def assert_grads_close(ours, ref, names=h.GRAD_NAMES, ref_again=None, ill=ILL_CONDITIONED, cap=5e-4, floor=GRAD_REL):
     """ref_again: a second run of the reference on the same input (its own noise floor)."""
     for i, (n, a, b) in enumerate(zip(names, ours, ref)):
         a = torch.as_tensor(a).double().cpu().flatten()
@@ -47,9 +47,9 @@ def assert_grads_close(ours, ref, names=h.GRAD_NAMES, ref_again=None):
             continue
         diff = (a - b).abs()
         tol = GRAD_TOL.get(n, GRAD_REL)
-        if ref_again is not None and n in ILL_CONDITIONED:
+        if ref_again is not None and n in ill:
             noise = float((torch.as_tensor(ref_again[i]).double().cpu().flatten() - b).abs().max()) / scale
-            tol = min(5e-4, max(GRAD_REL, 4.0 * noise))
+            tol = min(cap, max(floor, 4.0 * noise))
         assert float(diff.max()) / scale <= tol, (n, float(diff.max()) / scale)
 
 
@@ -63,12 +63,15 @@ def test_against_golden_reference_outputs(name):
     gold = np.load(f"{h.ROOT}/tests/golden/{name}.npz")
     scene, view, dL_np, c = cases.build(name)
     assert bytes(gold["input_sha256"]).decode() == cases.input_hash(scene, view, dL_np)
-    d = h.torch_inputs(scene, view, mode=c["mode"], bg=c["bg"], degree=c["degree"])
+    d = h.torch_inputs(scene, view, mode=c["mode"], bg=c["bg"], degree=c["degree"], render_depth=c.get("render_depth", False))
     fwd = h.run_forward(h.pkg, d)
-    grads = h.run_backward(h.pkg, d, fwd, torch.from_numpy(dL_np).cuda())
+    depth_only = bool(c.get("render_depth"))   # the reference's backward has no depth path
+    grads = None if depth_only else h.run_backward(h.pkg, d, fwd, torch.from_numpy(dL_np).cuda())
     st = h.ours_state(d, fwd)
     torch.cuda.synchronize()
 
+    if "present" in gold:   # checkFrustum (camera_type 1)
+        assert np.array_equal(_np(h.pkg.markVisible(d["means3D"], d["viewmatrix"], d["projmatrix"], 1)), gold["present"])
     assert fwd[0] == int(gold["num_rendered"])
     assert np.array_equal(_np(fwd[2]), gold["radii"])
     assert np.array_equal(_np(st["tiles_touched"]), gold["tiles_touched"])
@@ -78,13 +81,16 @@ def test_against_golden_reference_outputs(name):
     assert np.array_equal(_np(st["ranges"]), gold["ranges"])
     assert np.array_equal(_np(st["point_list"]), gold["point_list"])
     assert np.array_equal(_np(st["point_list_keys"]), gold["point_list_keys"])
-    if "rgb" in gold:
+    if "rgb" in gold and not depth_only:
         assert np.abs(_np(st["rgb"])[vis] - gold["rgb"][vis]).max() <= 1e-6
         assert np.array_equal(_np(st["clamped"])[vis], gold["clamped"][vis])
-    assert np.abs(_np(fwd[1]) - gold["out_color"]).max() <= IMG_TOL
+    # depth frames blend camera-space depths (up to 20) instead of colours in [0, 1]: same relative bound
+    img_tol = IMG_TOL * (float(np.abs(gold["out_color"]).max()) if depth_only else 1.0)
+    assert np.abs(_np(fwd[1]) - gold["out_color"]).max() <= max(IMG_TOL, img_tol)
     assert np.abs(_np(st["accum_alpha"]) - gold["accum_alpha"]).max() <= IMG_TOL
     assert np.array_equal(_np(st["n_contrib"]), gold["n_contrib"])
-    assert_grads_close(grads, [gold[n] for n in h.GRAD_NAMES])
+    if not depth_only:
+        assert_grads_close(grads, [gold[n] for n in h.GRAD_NAMES])
 
 
 # ------------------------------------------------------------------ (2) CPU oracle
@@ -121,6 +127,10 @@ REF_CASES = {
     "colors": lambda: (sm.make_scene(30000, 400, 200, 0.03, 74), sm.random_view(75), "colors", (0.1, 0.2, 0.3), 0),
     "cov_deg1": lambda: (sm.make_scene(30000, 400, 200, 0.03, 76), sm.random_view(77), "cov", (0, 0, 0), 1),
     "long_lists": lambda: (sm.make_scene(40000, 256, 128, 0.15, 78), sm.identity_view(), "sh", (0, 0, 0), 3),
+    # perspective camera (camera_type 1)
+    "pin_C1": lambda: (sm.make_config_scene("C1"), sm.perspective_view(81, 1024, 512, 90.0), "sh", (0, 0, 0), 3),
+    "pin_odd_cov": lambda: (sm.make_scene(60000, 517, 263, 0.03, 82), sm.perspective_view(83, 517, 263, 60.0), "cov", (1, 1, 1), 2),
+    "pin_colors_wide": lambda: (sm.make_scene(60000, 400, 200, 0.05, 84), sm.perspective_view(85, 400, 200, 120.0), "colors", (0.1, 0.2, 0.3), 0),
 }
 
 
@@ -148,7 +158,14 @@ def test_against_reference_rasterizer(case):
     assert float((fo[1] - fr[1]).abs().max()) <= IMG_TOL
     assert float((so["accum_alpha"] - sr["accum_alpha"]).abs().max()) <= IMG_TOL
     assert torch.equal(so["n_contrib"], sr["n_contrib"])
-    assert_grads_close(go, gr, ref_again=h.run_backward(ref, d, fr, dL))
+    if d["camera_type"] == 1:
+        # perspective camera: dL/dmean carries 1/z^2, 1/z^3 factors (backward.cu:270-283) for Gaussians just behind the
+        # near plane, so it joins the tensors bounded by 4 x the reference's own run-to-run difference (and never
+        # tighter than the 3e-4 the fixtures use for the ill-conditioned ones)
+        assert_grads_close(go, gr, ref_again=h.run_backward(ref, d, fr, dL), ill=ILL_CONDITIONED + ("dL_dmeans3D",),
+                           cap=2e-3, floor=3e-4)
+    else:
+        assert_grads_close(go, gr, ref_again=h.run_backward(ref, d, fr, dL))
 
 
 # ------------------------------------------------------------------ (4) full-size properties (C2)
@@ -268,8 +285,46 @@ def test_invalid_camera_type_raises_like_the_reference():
             d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], 0.0, 0.0, 16, 32, d["sh"], 3, d["campos"], False]
     with pytest.raises(RuntimeError, match=r"\[CudaRasterizer\]Invalid camera_type"):
         h.pkg.RasterizeGaussiansCUDA(*args, 2, False)
-    with pytest.raises(NotImplementedError):
-        h.pkg.RasterizeGaussiansCUDA(*args, 1, False)
+    with pytest.raises(RuntimeError, match=r"\[CudaRasterizer\]Invalid camera_type"):
+        h.pkg.markVisible(d["means3D"], d["viewmatrix"], d["projmatrix"], 0)
+
+
+def test_pinhole_against_cpu_oracle():
+    """camera_type 1 against the C restatement of preprocessCUDA / computeCov2DCUDA, incl. markVisible
+    and a render_depth frame."""
+    from oracle import oracle
+    W, H = 177, 93
+    scene = sm.make_scene(6000, W, H, 0.04, 91, near_frac=0.02)
+    view = sm.perspective_view(92, W, H, 80.0)
+    pin = dict(projmatrix=view[1], tan_fovx=view[3], tan_fovy=view[4])
+    dL_np = sm.make_grad_image(W, H, 93)
+    bgn = np.array((0.2, 0.1, 0.3), np.float32)
+    d = h.torch_inputs(scene, view, bg=tuple(bgn), degree=3)
+    fwd = h.run_forward(h.pkg, d)
+    grads = h.run_backward(h.pkg, d, fwd, torch.from_numpy(dL_np).cuda())
+    kw = dict(shs=scene.shs, degree=3, scales=scene.scales, rotations=scene.rotations, pinhole=pin)
+    of = oracle.forward(scene.means3D, scene.opacities, view[0], view[2], W, H, bgn, **kw)
+    og = oracle.backward(of, dL_np, scene.means3D, view[0], view[2], W, H, bgn, **kw)
+    assert abs(fwd[0] - of["num_rendered"]) <= max(4, of["num_rendered"] // 500)
+    assert int((_np(fwd[2]) != of["radii"]).sum()) <= 2
+    diff = np.abs(_np(fwd[1]) - of["out_color"]).max(axis=0)
+    assert (diff > 1e-4).mean() <= 2e-3 and diff.max() < 0.1
+    for n, g in zip(h.GRAD_NAMES, grads):
+        ref = og[n].reshape(tuple(g.shape))
+        scale = np.abs(ref).max() + 1e-30
+        assert np.abs(_np(g) - ref).max() / scale < 1e-2, n
+    present = h.pkg.markVisible(d["means3D"], d["viewmatrix"], d["projmatrix"], 1)
+    assert np.array_equal(_np(present), oracle.pinhole_mark_visible(scene.means3D, view[0]))
+    assert 0 < int(present.sum()) < scene.P
+    # depth frame: camera-space z blended into all three channels
+    dd = h.torch_inputs(scene, view, bg=(0, 0, 0), degree=3, render_depth=True)
+    fd = h.run_forward(h.pkg, dd)
+    od = oracle.forward(scene.means3D, scene.opacities, view[0], view[2], W, H, np.zeros(3, np.float32),
+                        **dict(kw, pinhole=dict(pin, render_depth=True)))
+    img = _np(fd[1])
+    assert np.array_equal(img[0], img[1]) and np.array_equal(img[1], img[2])
+    ddiff = np.abs(img - od["out_color"]).max(axis=0)
+    assert (ddiff > 1e-3).mean() <= 2e-3
 
 
 def test_mark_visible_marks_everything():
