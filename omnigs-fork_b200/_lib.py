@@ -15,7 +15,8 @@ class OgsError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, _LIB_NAME)
+    # OMNIGS_B200_LIB: an alternative build of the same library (A/B measurements of kernel variants)
+    return os.environ.get("OMNIGS_B200_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 # every symbol include/omnigs_b200.h declares: name -> (restype, argtypes)

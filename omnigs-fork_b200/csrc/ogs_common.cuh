@@ -142,6 +142,12 @@ OGS_D void red_add_v4(float* addr, float a, float b, float c, float d)
 	asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
 	             :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+OGS_D float rcp_approx(float x)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
 OGS_D void red_add(float* addr, float a)
 {
 	asm volatile("red.global.add.f32 [%0], %1;" :: "l"(addr), "f"(a) : "memory");

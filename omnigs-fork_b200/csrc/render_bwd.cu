@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 				const float4 eb = e->b;
 				const float4 ec = e->c;
 				const int list_pos = __float_as_int(eb.w);
+				const float near_cut = eb.y + 2e-3f;   // eb.y = -ln(255 o) - 1e-3: [cut-off - 1e-3, cut-off + 1e-3]
 
 				float r[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
 				float r8 = 0.f;
@@ -218,14 +219,19 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 					bool valid = (list_pos < last_contributor[s]) && !(power > 0.0f) && !(power < eb.y);
 					float G = 0.f, alpha = 0.f;
 					if (valid) {
-						G = expf(power);
+						// gradients are tolerance-bound, not bit-compared: ex2.approx (2 instructions) instead of the
+						// forward's accurate expf (9).  The blend DECISION alpha >= 1/255 must equal the forward's, though
+						// (a pixel that un-multiplies T by a Gaussian the forward skipped is off by 0.4 % for the rest of
+						// its list), so pairs whose power lies within 1e-3 of the cut-off take the accurate expf.
+						G = (power < near_cut) ? expf(power) : __expf(power);
 						alpha = fminf(0.99f, __fmul_rn(eb.z, G));
 						valid = !(alpha < kAlphaMin);
 					}
 					if (valid) {
 						any_valid = true;
-						// backward.cu:784-840; one correctly rounded reciprocal replaces the two divisions by (1 - alpha)
-						const float inv = __frcp_rn(1.f - alpha);
+						// backward.cu:784-840; one reciprocal (rcp.approx, 1 ulp; 1 - alpha >= 0.01) replaces the two
+						// divisions by (1 - alpha)
+						const float inv = rcp_approx(1.f - alpha);
 						T[s] = T[s] * inv;
 						const float dchannel_dcolor = alpha * T[s];
 						float dL_dalpha = 0.0f;
