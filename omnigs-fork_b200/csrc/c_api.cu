@@ -87,7 +87,7 @@ GeomState carve_geom(char* base, int P, size_t* total)
 	const size_t p = (size_t)P;
 	g.g0 = c.take<float4>(p);
 	g.g1 = c.take<float4>(p);
-	g.gb = c.take<float>(p);
+	g.gb = c.take<float2>(p);
 	g.depth = c.take<float>(p);
 	g.rect = c.take<uint2>(p);
 	g.tiles_touched = c.take<uint32_t>(p);
@@ -191,7 +191,7 @@ int get_readback(Readback** out)
 	return OGS_OK;
 }
 
-__global__ void export_geometry_kernel(int P, const float4* g0, const float4* g1, const float* gb, const float* depth,
+__global__ void export_geometry_kernel(int P, const float4* g0, const float4* g1, const float2* gb, const float* depth,
                                        const uint32_t* tiles, const uint8_t* clamped, const float* cov3D_in,
                                        float* means2D, float* depths, float* conic_opacity, float* rgb,
                                        uint32_t* tiles_touched, uint8_t* clamped_out, float* cov3D)
@@ -201,7 +201,7 @@ __global__ void export_geometry_kernel(int P, const float4* g0, const float4* g1
 	const bool vis = tiles[i] > 0;
 	float4 a = vis ? g0[i] : make_float4(0, 0, 0, 0);
 	float4 b = vis ? g1[i] : make_float4(0, 0, 0, 0);
-	float cb = vis ? gb[i] : 0.f;
+	float cb = vis ? gb[i].x : 0.f;
 	if (means2D) { means2D[2 * i] = a.x; means2D[2 * i + 1] = a.y; }
 	if (depths) depths[i] = vis ? depth[i] : 0.f;
 	if (conic_opacity) { conic_opacity[4 * i] = a.z; conic_opacity[4 * i + 1] = a.w; conic_opacity[4 * i + 2] = b.x; conic_opacity[4 * i + 3] = b.y; }
@@ -650,7 +650,7 @@ OGS_API int ogs_adam_step(
 	for (int g = 0; g < groups; g++) {
 		if (counts[g] && (!params[g] || !grads[g] || !exp_avg[g] || !exp_avg_sq[g]))
 			return fail(OGS_ERR_INVALID_ARG, "a parameter group has a NULL tensor");
-		a.group[g] = AdamGroup{ params[g], grads[g], exp_avg[g], exp_avg_sq[g], counts[g], (float)((double)lrs[g] / bc1) };
+		a.group[g] = AdamGroup{ params[g], grads[g], exp_avg[g], exp_avg_sq[g], counts[g], (float)((double)lrs[g] / bc1), 0 };
 	}
 	return launch_adam(a, (cudaStream_t)stream);
 }

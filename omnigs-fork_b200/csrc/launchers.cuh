@@ -29,7 +29,7 @@ struct PreprocessFwdArgs {
 	int* radii;
 	float4* g0;
 	float4* g1;
-	float* gb;
+	float2* gb;
 	float* depth;
 	uint2* rect;
 	uint32_t* tiles_touched;
@@ -86,10 +86,10 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 int launch_rebuild_keys(const ImageState& img, const BinningState& b, const GeomState& g, int W, int H,
                         uint64_t* keys, cudaStream_t st);
 int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
-                      const float4* g0, const float4* g1, const float* gb, const unsigned long long* scalars, const float* bg,
+                      const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars, const float* bg,
                       float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st);
 int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, int H, const float* bg,
-                      const float4* g0, const float4* g1, const float* gb, const unsigned long long* scalars,
+                      const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
                       float* grad_acc, cudaStream_t st);
 int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st);
@@ -108,6 +108,7 @@ struct AdamGroup {
 	float* exp_avg_sq;
 	size_t n;
 	float step_size;             // lr / (1 - beta1^t), evaluated in double on the host like torch::optim::Adam
+	int vec4;                    // all four tensors 16-byte aligned (set by launch_adam)
 };
 struct AdamLaunch {
 	int groups;

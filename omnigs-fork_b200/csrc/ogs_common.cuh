@@ -54,7 +54,7 @@ inline uint32_t higher_msb(uint32_t n)
 struct GeomState {               // per-Gaussian, P-sized
 	float4* g0;                  // (mean2D.x, mean2D.y, conic.x, conic.y)
 	float4* g1;                  // (conic.z, opacity, colour.r, colour.g)
-	float* gb;                   // colour.b
+	float2* gb;                  // (colour.b, alpha cut-off in `power`: see alpha_cutoff_power, render_common.cuh)
 	float* depth;                // r = |t|  (sort key, reference forward.cu:697)
 	uint2* rect;                 // x0 | x1<<16 , y0 | y1<<16   (clamped tile rect, auxiliary.h:56-66)
 	uint32_t* tiles_touched;

@@ -19,6 +19,7 @@
 // The CTA's features_rest_ rows (128 x 180 B, contiguous) and features_dc_ rows (128 x 12 B) come in as
 // two bulk copies; a thread reads its row with a 45-word stride (conflict-free).
 #include "pinhole_math.cuh"
+#include "render_common.cuh"
 #include "launchers.cuh"
 #include "async_copy.cuh"
 
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 		float opacity = a.opacities[idx];
 		if (kRaw) opacity = sigmoid_act(opacity);   // getOpacityActivation, gaussian_model.cpp:74-77
 		a.g1[idx] = make_float4(conic.z, opacity, rgb.x, rgb.y);
-		a.gb[idx] = rgb.z;
+		a.gb[idx] = make_float2(rgb.z, alpha_cutoff_power(opacity));
 		if (emits) {
 			a.depth[idx] = r;
 			a.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));

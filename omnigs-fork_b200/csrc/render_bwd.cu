@@ -67,7 +67,7 @@ template <int kMinBlocks>
 __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
 	const float* __restrict__ bg_color,
-	const float4* __restrict__ g0, const float4* __restrict__ g1, const float* __restrict__ gb,
+	const float4* __restrict__ g0, const float4* __restrict__ g1, const float2* __restrict__ gb,
 	const unsigned long long* __restrict__ scalars,
 	const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
 	const float* __restrict__ dL_dpixels, float* __restrict__ grad_acc /*[P,12]*/)
@@ -147,9 +147,10 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 			if (pos[q] >= 0) {
 				a[q] = g0[id[q]];
 				b[q] = g1[id[q]];
-				cb[q] = gb[id[q]];
+				const float2 bt = gb[id[q]];
+				cb[q] = bt.x;
 				if (wrap_W > 0.f) a[q].x = nearest_copy_x(a[q].x, tx0 + 0.5f * (kTile - 1), wrap_W);
-				tau[q] = alpha_power_threshold(b[q].y);
+				tau[q] = bt.y;
 				keep[q] = gaussian_touches_box(a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, tau[q], tx0, ty0, tx1, ty1);
 			}
 			my_keep += keep[q] ? 1 : 0;
@@ -204,7 +205,6 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 				const float4 eb = e->b;
 				const float4 ec = e->c;
 				const int list_pos = __float_as_int(eb.w);
-				const float near_cut = eb.y + 2e-3f;   // eb.y = -ln(255 o) - 1e-3: [cut-off - 1e-3, cut-off + 1e-3]
 
 				float r[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
 				float r8 = 0.f;
@@ -219,13 +219,11 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 					bool valid = (list_pos < last_contributor[s]) && !(power > 0.0f) && !(power < eb.y);
 					float G = 0.f, alpha = 0.f;
 					if (valid) {
-						// gradients are tolerance-bound, not bit-compared: ex2.approx (2 instructions) instead of the
-						// forward's accurate expf (9).  The blend DECISION alpha >= 1/255 must equal the forward's, though
-						// (a pixel that un-multiplies T by a Gaussian the forward skipped is off by 0.4 % for the rest of
-						// its list), so pairs whose power lies within 1e-3 of the cut-off take the accurate expf.
-						G = (power < near_cut) ? expf(power) : __expf(power);
+						// power >= the Gaussian's cut-off (eb.y) IS the forward's alpha >= 1/255 decision, so the gradient
+						// arithmetic itself is free to use ex2.approx (2 instructions instead of expf's 9): gradients are
+						// tolerance-bound, not bit-compared
+						G = __expf(power);
 						alpha = fminf(0.99f, __fmul_rn(eb.z, G));
-						valid = !(alpha < kAlphaMin);
 					}
 					if (valid) {
 						any_valid = true;
@@ -270,7 +268,7 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 }
 
 int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, int H, const float* bg,
-                      const float4* g0, const float4* g1, const float* gb, const unsigned long long* scalars,
+                      const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
                       float* grad_acc, cudaStream_t st)
 {

@@ -20,12 +20,22 @@ constexpr int kSubW = 8, kSubH = 4;
 constexpr float kCullAbs = 0.01f;
 constexpr float kCullRel = 8e-6f;
 
-// tau_safe for the per-pixel early-out: compares against the SAME float `power` the blend uses,
-// only expf's own error (<= 2 ulp) has to be covered.
-OGS_D float alpha_power_threshold(float opacity)
+// The blend decision in `power` space.  A pair contributes iff alpha = min(0.99, o * expf(power)) >= 1/255
+// (forward.cu:434-438).  o * expf(p) is non-decreasing in p, so per Gaussian there is a smallest float p_cut with
+// o * expf(p_cut) >= 1/255 and the decision is exactly `power >= p_cut` — evaluated with the SAME expf and the same
+// multiply the blend uses.  It is found once per Gaussian (preprocess) by walking a few ulps around -ln(255 o);
+// the blend kernels then skip pairs with one compare, and the backward (which must repeat the forward's decisions:
+// a pixel that un-multiplies T by a Gaussian the forward skipped is off by 0.4 % for the rest of its list) needs
+// no accurate expf at all.  The forward still applies the reference's own alpha test after expf.
+OGS_D float alpha_cutoff_power(float opacity)
 {
-	// opacity <= 0 or NaN: never skip through this path (tau = -inf)
-	return (opacity > 0.f) ? (-logf(255.0f * opacity) - 1e-3f) : -INFINITY;
+	if (!(opacity > 0.f)) return (opacity <= 0.f) ? INFINITY : -INFINITY;   // o <= 0 never contributes; NaN: no skip
+	float p = -logf(255.0f * opacity);
+	int it = 0;
+	for (; it < 16 && !(__fmul_rn(opacity, expf(p)) < kAlphaMin); it++) p = nextafterf(p, -INFINITY);
+	for (; it < 48 && (__fmul_rn(opacity, expf(p)) < kAlphaMin); it++) p = nextafterf(p, INFINITY);
+	// not converged (cannot happen for finite o; guards against a non-monotone expf): fall back to a safe bound
+	return (it < 48) ? p : (-logf(255.0f * opacity) - 1e-3f);
 }
 
 // Can the Gaussian (mean m, conic A,B,C, threshold tau) reach alpha >= 1/255 anywhere on the

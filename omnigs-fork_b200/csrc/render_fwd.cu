@@ -19,7 +19,7 @@ namespace ogs {
 
 __global__ void __launch_bounds__(kRenderThreads, 5) render_fwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
-	const float4* __restrict__ g0, const float4* __restrict__ g1, const float* __restrict__ gb,
+	const float4* __restrict__ g0, const float4* __restrict__ g1, const float2* __restrict__ gb,
 	const unsigned long long* __restrict__ scalars, const float* __restrict__ bg_color,
 	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)
 {
@@ -64,9 +64,10 @@ __global__ void __launch_bounds__(kRenderThreads, 5) render_fwd_kernel(
 			const uint32_t id = point_list[range.x + i];
 			a = g0[id];
 			b = g1[id];
-			cb = gb[id];
+			const float2 bt = gb[id];
+			cb = bt.x;
 			if (wrap_W > 0.f) a.x = nearest_copy_x(a.x, tx0 + 0.5f * (kTile - 1), wrap_W);
-			tau = alpha_power_threshold(b.y);
+			tau = bt.y;
 			keep = gaussian_touches_box(a.x, a.y, a.z, a.w, b.x, tau, tx0, ty0, tx1, ty1);
 		}
 		int total;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kRenderThreads, 5) render_fwd_kernel(
 				float dx, dy;
 				const float power = pair_power(ea.x, ea.y, ea.z, ea.w, eb.x, pixf, dx, dy);
 				if (power > 0.0f) continue;
-				if (power < eb.y) continue; // alpha would be < 1/255 (skips expf)
+				if (power < eb.y) continue; // below the Gaussian's alpha cut-off: alpha would be < 1/255 (skips expf)
 				const float alpha = fminf(0.99f, __fmul_rn(eb.z, expf(power)));
 				if (alpha < kAlphaMin) continue;
 				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(kRenderThreads, 5) render_fwd_kernel(
 }
 
 int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
-                      const float4* g0, const float4* g1, const float* gb, const unsigned long long* scalars, const float* bg,
+                      const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars, const float* bg,
                       float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st)
 {
 	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);

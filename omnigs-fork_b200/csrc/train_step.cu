@@ -207,6 +207,15 @@ int launch_photometric_loss(int W, int H, int H_used, float lambda_dssim, const 
 size_t photometric_loss_workspace_bytes(int W, int H) { return (4 + 9 * (size_t)W * H) * sizeof(float); }
 
 // ------------------------------------------------------------------ Adam, all parameter groups in one launch
+// torch/csrc/api/src/optim/adam.cpp step(): exp_avg, exp_avg_sq, denom, addcdiv_ for one element
+OGS_D void adam_element(const AdamLaunch& a, float step_size, float grad, float& m, float& v, float& p)
+{
+	m = m * a.beta1 + grad * a.one_minus_beta1;
+	v = v * a.beta2 + (a.one_minus_beta2 * grad) * grad;
+	const float denom = sqrtf(v) / a.sqrt_bias_correction2 + a.eps;
+	p = p - step_size * (m / denom);
+}
+
 __global__ void __launch_bounds__(256) adam_groups_kernel(const AdamLaunch a)
 {
 	// the block's group: a.first_block[g] <= blockIdx.x < a.first_block[g + 1]
@@ -215,20 +224,26 @@ __global__ void __launch_bounds__(256) adam_groups_kernel(const AdamLaunch a)
 	for (int k = 1; k < kAdamMaxGroups; k++)
 		if (k < a.groups && (int)blockIdx.x >= a.first_block[k]) g = k;
 	const AdamGroup grp = a.group[g];
-	const size_t base = ((size_t)blockIdx.x - a.first_block[g]) * kAdamPerBlock;
-	const float step_size = grp.step_size;
-#pragma unroll
-	for (int u = 0; u < kAdamPerBlock / 256; u++) {
-		const size_t i = base + (size_t)u * 256 + threadIdx.x;
-		if (i < grp.n) {
-			// torch/csrc/api/src/optim/adam.cpp step(): exp_avg, exp_avg_sq, denom, addcdiv_
-			const float grad = grp.grad[i];
-			const float m = grp.exp_avg[i] * a.beta1 + grad * a.one_minus_beta1;
-			const float v = grp.exp_avg_sq[i] * a.beta2 + (a.one_minus_beta2 * grad) * grad;
-			const float denom = sqrtf(v) / a.sqrt_bias_correction2 + a.eps;
-			grp.exp_avg[i] = m;
-			grp.exp_avg_sq[i] = v;
-			grp.param[i] = grp.param[i] - step_size * (m / denom);
+	// four consecutive elements per thread: 128-bit accesses when the group's tensors are 16-byte aligned
+	const size_t i = ((size_t)blockIdx.x - a.first_block[g]) * kAdamPerBlock + (size_t)threadIdx.x * 4;
+	if (i >= grp.n) return;
+	if (grp.vec4 && i + 4 <= grp.n) {
+		const float4 gr = *reinterpret_cast<const float4*>(grp.grad + i);
+		float4 m = *reinterpret_cast<float4*>(grp.exp_avg + i);
+		float4 v = *reinterpret_cast<float4*>(grp.exp_avg_sq + i);
+		float4 p = *reinterpret_cast<float4*>(grp.param + i);
+		adam_element(a, grp.step_size, gr.x, m.x, v.x, p.x);
+		adam_element(a, grp.step_size, gr.y, m.y, v.y, p.y);
+		adam_element(a, grp.step_size, gr.z, m.z, v.z, p.z);
+		adam_element(a, grp.step_size, gr.w, m.w, v.w, p.w);
+		*reinterpret_cast<float4*>(grp.exp_avg + i) = m;
+		*reinterpret_cast<float4*>(grp.exp_avg_sq + i) = v;
+		*reinterpret_cast<float4*>(grp.param + i) = p;
+	} else {
+		for (size_t k = i; k < min(i + 4, grp.n); k++) {
+			float m = grp.exp_avg[k], v = grp.exp_avg_sq[k], p = grp.param[k];
+			adam_element(a, grp.step_size, grp.grad[k], m, v, p);
+			grp.exp_avg[k] = m; grp.exp_avg_sq[k] = v; grp.param[k] = p;
 		}
 	}
 }
@@ -237,6 +252,9 @@ int launch_adam(AdamLaunch a, cudaStream_t st)
 {
 	int blocks = 0;
 	for (int g = 0; g < a.groups; g++) {
+		AdamGroup& grp = a.group[g];
+		grp.vec4 = ((reinterpret_cast<uintptr_t>(grp.param) | reinterpret_cast<uintptr_t>(grp.grad) |
+		             reinterpret_cast<uintptr_t>(grp.exp_avg) | reinterpret_cast<uintptr_t>(grp.exp_avg_sq)) & 15u) == 0;
 		a.first_block[g] = blocks;
 		blocks += (int)((a.group[g].n + kAdamPerBlock - 1) / kAdamPerBlock);
 	}
