@@ -225,14 +225,18 @@ def main():
         impl_note = "reference CUDA rasterizer rebuilt for sm_100 (oracle/_ref), its own entry points"
 
     names = h.GRAD_NAMES
+    # data parallel: the library writes the optimiser-facing gradients into one flat bucket, exchanged by ONE all-reduce
+    bucket = par.GradientBucket(P, M, dev, peer=None if os.environ.get("OGS_DP_EXCHANGE", "peer") == "peer" else False) if distributed else None
 
     def step(s):
         d["viewmatrix"], d["campos"] = view_dev[s]
         d["projmatrix"] = d["viewmatrix"]
         fwd = h.run_forward(mod, d)
-        g = h.run_backward(mod, d, fwd, dL)
         if distributed:
-            par.allreduce_gradients(dict(zip(names, g)), fwd[2])
+            g = h.run_backward(mod, d, fwd, dL, out=bucket)
+            par.allreduce_bucket(bucket, g[0], fwd[2])
+        else:
+            g = h.run_backward(mod, d, fwd, dL)
         return fwd, g
 
     def sync_all():
@@ -295,9 +299,11 @@ def main():
         torch.cuda.current_stream().wait_event(gt_ready)
         diff = fwd[1] - gt_dev
         loss = diff.abs().mean()                       # L1 (the reference's main loss term)
-        g = h.run_backward(mod, d, fwd, torch.sign(diff) / diff.numel())
         if distributed:
-            par.allreduce_gradients(dict(zip(names, g)), fwd[2])
+            g = h.run_backward(mod, d, fwd, torch.sign(diff) / diff.numel(), out=bucket)
+            par.allreduce_bucket(bucket, g[0], fwd[2])
+        else:
+            g = h.run_backward(mod, d, fwd, torch.sign(diff) / diff.numel())
         return float(loss.item())                      # device->host read of the step's result
 
     for s in range(Wm):
@@ -326,6 +332,8 @@ def main():
         "config": {"workload": WORKLOAD, "gaussians": P, "visible": V, "image": [W, H], "sh_degree": D,
                    "num_rendered": R, "views_per_step_per_gpu": 1,
                    "parallelism": f"dp{world}" if distributed else "single",
+                   "gradient_exchange": ("peer-memory all-reduce kernel (NVLink loads/stores)" if (bucket is not None and bucket.peer)
+                                         else ("NCCL all-reduce" if distributed else "none")),
                    "l2": "no flush: every step touches > 1 GB (params 236 MB, lists, accumulators), L2 is 126 MB; "
                          "a different camera pose each step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -291,6 +291,21 @@ OGS_API int ogs_densify_stats(
 	void* stream);
 
 /*
+ * Data-parallel gradient exchange over NVLink peer memory (the reference has no multi-GPU code).
+ * bufs[r] (host array, `world` <= 8 entries) is rank r's bucket of `count` floats (a multiple of 4) as mapped into THIS
+ * process (CUDA IPC / symmetric memory), bufs[rank] the local one.  The call sums slice `rank` of all buckets in rank
+ * order and stores the sum into every bucket (reduce-scatter + all-gather in one kernel, peer loads and stores).
+ * The caller orders it against the other ranks: all buckets written before, all slices stored after (a cross-rank
+ * barrier on the same stream on both sides; omnigs-fork_b200/parallel.py uses torch.distributed's symmetric memory).
+ */
+OGS_API int ogs_peer_allreduce_sum(float* const* bufs, int world, int rank, size_t count, void* stream);
+/* One view's increments of the densification statistics as plain [P] arrays (gaussian_mapper.cpp:427-434,
+ * gaussian_model.cpp:839-853): ||dL_dmean2D.xy|| and 1 where radii > 0 (else 0), and the radius as float — what
+ * data-parallel ranks sum / sum / max over views before applying them. */
+OGS_API int ogs_view_stats(int P, const int* radii, const float* dL_dmean2D, float* grad_norm, float* visible,
+                           float* radius, void* stream);
+
+/*
  * Longitude-seam wrap-around (opt-in extension; off by default = reference parity).
  * The reference's live code clamps tile rects at the left/right image edge (auxiliary.h:56-66,
  * forward.cu:678-681), so a Gaussian straddling lon = +-pi is cut at the seam; its dead code

@@ -118,6 +118,11 @@ struct AdamLaunch {
 	AdamGroup group[kAdamMaxGroups];
 };
 int launch_adam(AdamLaunch a, cudaStream_t st);
+int launch_view_stats(int P, const int* radii, const float* dL_dmean2D, float* grad_norm, float* visible, float* radius,
+                      cudaStream_t st);
+// ---- peer_collective.cu
+constexpr int kMaxPeers = 8;
+int launch_peer_allreduce_sum(float* const* bufs, int world, int rank, size_t count, cudaStream_t st);
 int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D,
                          float* xyz_gradient_accum, float* denom, cudaStream_t st);
 

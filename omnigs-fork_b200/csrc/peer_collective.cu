@@ -1,0 +1,77 @@
+// peer_collective.cu — all-reduce(SUM) of the data-parallel gradient bucket over NVLink peer memory.
+//
+// Every rank owns one contiguous slice of the bucket.  One kernel per rank reads that slice from ALL ranks'
+// buffers (its own and the peers', mapped into this process: peer loads over NVLink / NVSwitch), adds them in
+// rank order and stores the sum into ALL ranks' buffers (peer stores).  Per GPU that is (N-1)/N of the bucket in
+// and (N-1)/N out, both directions of the links busy at once — a reduce-scatter and an all-gather in one pass —
+// and because the owner adds in a fixed order, every replica ends with bit-identical sums.
+// Ordering across ranks (everybody's gradients written before anyone reads; everybody's sums written before
+// anyone consumes) is the caller's: parallel.py brackets the launch with the symmetric-memory barrier of
+// torch.distributed on the same stream.  No spin-waits in this kernel.
+#include "launchers.cuh"
+#include <cstdlib>
+
+namespace ogs {
+
+struct PeerBuffers {
+	float* buf[kMaxPeers];
+};
+
+constexpr int kPeerUnroll = 4;   // independent 16-byte peer loads in flight per thread
+
+__global__ void __launch_bounds__(256) peer_allreduce_sum_kernel(const PeerBuffers p, int world, size_t begin4, size_t end4)
+{
+	// float4 units; each block walks chunks of 256 * kPeerUnroll consecutive float4 of this rank's slice [begin4, end4)
+	const size_t stride = (size_t)gridDim.x * blockDim.x * kPeerUnroll;
+	for (size_t base = begin4 + (size_t)blockIdx.x * blockDim.x * kPeerUnroll + threadIdx.x; base < end4; base += stride) {
+		float4 acc[kPeerUnroll];
+#pragma unroll
+		for (int u = 0; u < kPeerUnroll; u++) {
+			const size_t i = base + (size_t)u * blockDim.x;
+			acc[u] = (i < end4) ? reinterpret_cast<const float4*>(p.buf[0])[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+#pragma unroll
+		for (int r = 1; r < kMaxPeers; r++) {
+			if (r < world) {
+				float4 v[kPeerUnroll];
+#pragma unroll
+				for (int u = 0; u < kPeerUnroll; u++) {
+					const size_t i = base + (size_t)u * blockDim.x;
+					v[u] = (i < end4) ? reinterpret_cast<const float4*>(p.buf[r])[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+				}
+#pragma unroll
+				for (int u = 0; u < kPeerUnroll; u++) {
+					acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+				}
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < kMaxPeers; r++) {
+			if (r < world) {
+#pragma unroll
+				for (int u = 0; u < kPeerUnroll; u++) {
+					const size_t i = base + (size_t)u * blockDim.x;
+					if (i < end4) reinterpret_cast<float4*>(p.buf[r])[i] = acc[u];
+				}
+			}
+		}
+	}
+}
+
+int launch_peer_allreduce_sum(float* const* bufs, int world, int rank, size_t count, cudaStream_t st)
+{
+	PeerBuffers p{};
+	for (int r = 0; r < world; r++) p.buf[r] = bufs[r];
+	const size_t n4 = count / 4;                       // the bucket is padded to a multiple of 4 floats
+	const size_t per = (n4 + world - 1) / world;
+	const size_t begin4 = min(n4, per * rank), end4 = min(n4, begin4 + per);
+	if (end4 <= begin4) return OGS_OK;
+	const size_t want = (end4 - begin4 + 256 * kPeerUnroll - 1) / (256 * kPeerUnroll);
+	static const int per_sm = [] { const char* e = getenv("OGS_PEER_BLOCKS_PER_SM"); return e ? atoi(e) : 8; }();
+	const int blocks = (int)min(want, (size_t)kNumSMs * per_sm);
+	peer_allreduce_sum_kernel<<<blocks, 256, 0, st>>>(p, world, begin4, end4);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
+} // namespace ogs

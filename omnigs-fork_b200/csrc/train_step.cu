@@ -282,6 +282,29 @@ __global__ void densify_stats_kernel(int P, const int* __restrict__ radii, const
 	denom[i] += 1.f;
 }
 
+// Per-view increments of the same statistics as three plain arrays (what data-parallel ranks exchange before
+// applying them: sum, sum, max).
+__global__ void view_stats_kernel(int P, const int* __restrict__ radii, const float* __restrict__ dL_dmean2D,
+                                  float* __restrict__ grad_norm, float* __restrict__ visible, float* __restrict__ radius)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	const int r = radii[i];
+	const float gx = dL_dmean2D[3 * (size_t)i], gy = dL_dmean2D[3 * (size_t)i + 1];
+	grad_norm[i] = r > 0 ? sqrtf(gx * gx + gy * gy) : 0.f;
+	visible[i] = r > 0 ? 1.f : 0.f;
+	radius[i] = (float)r;
+}
+
+int launch_view_stats(int P, const int* radii, const float* dL_dmean2D, float* grad_norm, float* visible, float* radius,
+                      cudaStream_t st)
+{
+	if (P == 0) return OGS_OK;
+	view_stats_kernel<<<ceil_div(P, 256), 256, 0, st>>>(P, radii, dL_dmean2D, grad_norm, visible, radius);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
 int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D,
                          float* xyz_gradient_accum, float* denom, cudaStream_t st)
 {

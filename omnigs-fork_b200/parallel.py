@@ -45,6 +45,103 @@ def allreduce_gradients(grads, radii=None, group=None):
     return grads, stats
 
 
+class GradientBucket:
+    """One flat float32 buffer holding, back to back, the five gradient tensors the optimiser consumes
+    (dL_dmeans3D [P,3], dL_dsh [P,M,3], dL_dopacity [P,1], dL_dscales [P,3], dL_drotations [P,4]) and the two
+    summed densification statistics ([P] each).  RasterizeGaussiansBackwardCUDA(..., out=bucket) lets the library
+    write the gradients straight into it, so the data-parallel exchange is ONE all-reduce(SUM) over
+    (59 + 2) floats per Gaussian (plus one small all-reduce(MAX) for the radii) instead of eight collectives:
+    collective launches are latency-bound, and one large message uses the NVLink/NVSwitch bandwidth better."""
+
+    def __init__(self, P, M, device, peer=None):
+        """peer: None = use NVLink peer memory when available (NCCL otherwise), False = always NCCL/gloo."""
+        self.P, self.M = int(P), int(M)
+        self.peer = None
+        sizes = [("dL_dmeans3D", (P, 3)), ("dL_dsh", (P, M, 3)), ("dL_dopacity", (P, 1)), ("dL_dscales", (P, 3)),
+                 ("dL_drotations", (P, 4)), ("xyz_gradient_accum", (P,)), ("denom", (P,))]
+        # every section starts 16-byte aligned (the SH rows go through 16-byte bulk copies)
+        offs, total = [], 0
+        for _, shape in sizes:
+            offs.append(total)
+            n = 1
+            for d in shape:
+                n *= int(d)
+            total += -(-n // 4) * 4
+        self.flat = None
+        if peer is not False and is_distributed() and torch.device(device).type == "cuda":
+            self.flat = self._symmetric(total, device)
+        if self.flat is None:
+            self.flat = torch.empty((total,), dtype=torch.float32, device=device)
+        self.tensors = {}
+        for (name, shape), o in zip(sizes, offs):
+            n = 1
+            for d in shape:
+                n *= int(d)
+            self.tensors[name] = self.flat[o:o + n].view(shape)
+        self.max_radii2D = torch.empty((P,), dtype=torch.float32, device=device)
+
+    def __getitem__(self, name):
+        return self.tensors[name]
+
+    def _symmetric(self, total, device):
+        """Allocate the bucket in torch.distributed symmetric memory and map every peer's copy into this process.
+        Returns None (-> NCCL path) when that is not possible on this system."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            world = dist.get_world_size()
+            if world > 8:
+                return None
+            flat = symm_mem.empty(total, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(flat, dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != world or any(p == 0 or p % 16 for p in ptrs):
+                return None
+            self.peer = dict(handle=hdl, ptrs=ptrs, rank=dist.get_rank(), world=world)
+            return flat
+        except Exception:   # no symmetric memory on this build / topology
+            self.peer = None
+            return None
+
+
+def allreduce_bucket(bucket, dL_dmeans2D, radii, group=None):
+    """Fill the statistics slots of `bucket` from this rank's view and sum the whole bucket over ranks in one
+    collective.  Returns (dict of the five summed gradients, stats dict) like allreduce_gradients."""
+    if bucket.flat.is_cuda:
+        import ctypes
+        from ._lib import load_library, check
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        check(load_library().ogs_view_stats(
+            bucket.P, ptr(radii.contiguous()), ptr(dL_dmeans2D.contiguous()), ptr(bucket["xyz_gradient_accum"]),
+            ptr(bucket["denom"]), ptr(bucket.max_radii2D),
+            ctypes.c_void_p(torch.cuda.current_stream(bucket.flat.device).cuda_stream)))
+    else:   # gloo tests on CPU tensors
+        vis = radii > 0
+        torch.where(vis, dL_dmeans2D[:, :2].norm(dim=-1), dL_dmeans2D.new_zeros(()), out=bucket["xyz_gradient_accum"])
+        bucket["denom"].copy_(vis)
+        bucket.max_radii2D.copy_(radii)
+    if is_distributed() and bucket.peer is not None:
+        # reduce-scatter + all-gather in one kernel over peer memory (csrc/peer_collective.cu), bracketed by the
+        # symmetric-memory barrier on this stream: all buckets written before, all slices stored after
+        import ctypes
+        from ._lib import load_library, check
+        pr = bucket.peer
+        w2 = dist.all_reduce(bucket.max_radii2D, op=dist.ReduceOp.MAX, group=group, async_op=True)
+        arr = (ctypes.c_void_p * pr["world"])(*pr["ptrs"])
+        stream = ctypes.c_void_p(torch.cuda.current_stream(bucket.flat.device).cuda_stream)
+        pr["handle"].barrier(channel=0)
+        check(load_library().ogs_peer_allreduce_sum(arr, pr["world"], pr["rank"], bucket.flat.numel(), stream))
+        pr["handle"].barrier(channel=1)
+        w2.wait()
+    elif is_distributed():
+        w1 = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        w2 = dist.all_reduce(bucket.max_radii2D, op=dist.ReduceOp.MAX, group=group, async_op=True)
+        w1.wait()
+        w2.wait()
+    grads = {n: bucket[n] for n in OPTIMISED}
+    stats = {"xyz_gradient_accum": bucket["xyz_gradient_accum"], "denom": bucket["denom"], "max_radii2D": bucket.max_radii2D}
+    return grads, stats
+
+
 def tile_row_counts(ranges, W, H):
     """Instances per tile row from a frame's `ranges` [T,2] (e.g. of the previous frame of a sequence)."""
     gx, gy = (W + 15) // 16, (H + 15) // 16

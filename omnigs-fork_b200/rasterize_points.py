@@ -130,7 +130,7 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
 def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                    cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                    dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                   imageBuffer, camera_type=PINHOLE, reduce_accumulators=None):
+                                   imageBuffer, camera_type=PINHOLE, reduce_accumulators=None, out=None):
     """reference src/rasterize_points.cu:166-285.
 
     Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
@@ -140,6 +140,9 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
     [P,12] float32 render-backward accumulators of this rank (a view into geomBuffer) between the two
     backward kernels, e.g. ``lambda t: dist.all_reduce(t)``; the per-Gaussian backward then runs on the
     sums, so every rank ends with the full-frame gradients after exchanging 48 B/Gaussian.
+
+    ``out`` (extension for data-parallel training): a ``parallel.GradientBucket``; the five optimiser-facing
+    gradients are then written into its flat buffer (and returned as views of it) instead of fresh tensors.
     """
     _require_cuda(means3D, "means3D")
     lib = load_library()
@@ -151,14 +154,16 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
     # the library writes every element (zeros for culled rows): no zero-fill needed
     # (the reference zero-fills 81 floats per Gaussian here, :200-208,246-247)
     alloc = torch.zeros if P == 0 else torch.empty
-    dL_dmeans3D = alloc((P, 3), **opts)
+    dL_dmeans3D = alloc((P, 3), **opts) if out is None else out["dL_dmeans3D"]
     dL_dmeans2D = alloc((P, 3), **opts)
     dL_dcolors = alloc((P, NUM_CHANNELS), **opts)
-    dL_dopacity = alloc((P, 1), **opts)
+    dL_dopacity = alloc((P, 1), **opts) if out is None else out["dL_dopacity"]
     dL_dcov3D = alloc((P, 6), **opts)
-    dL_dsh = alloc((P, M, 3), **opts)
-    dL_dscales = alloc((P, 3), **opts)
-    dL_drotations = alloc((P, 4), **opts)
+    dL_dsh = alloc((P, M, 3), **opts) if out is None else out["dL_dsh"]
+    dL_dscales = alloc((P, 3), **opts) if out is None else out["dL_dscales"]
+    dL_drotations = alloc((P, 4), **opts) if out is None else out["dL_drotations"]
+    if out is not None and (out.P != P or out.M != M):
+        raise RuntimeError("gradient bucket was built for a different P / M")
     if P != 0:
         if camera_type not in (PINHOLE, LONLAT):
             raise RuntimeError("[CudaRasterizer]Invalid camera_type")

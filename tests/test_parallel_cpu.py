@@ -59,6 +59,43 @@ def test_allreduce_gradients_world2_gloo(tmp_path):
     assert torch.equal(got["stats"]["max_radii2D"], torch.maximum(r0, r1).float())
 
 
+def _bucket_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grads, radii = _make(rank)
+    bucket = par.GradientBucket(257, 16, "cpu")
+    for n in par.OPTIMISED:          # what the library does through RasterizeGaussiansBackwardCUDA(..., out=bucket)
+        bucket[n].copy_(grads[n])
+    summed, stats = par.allreduce_bucket(bucket, grads["dL_dmeans2D"], radii)
+    if rank == 0:
+        torch.save({"grads": {k: v.clone() for k, v in summed.items()}, "stats": {k: v.clone() for k, v in stats.items()}}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucket_allreduce_matches_per_tensor_allreduce_world2_gloo(tmp_path):
+    out = str(tmp_path / "b0.pt")
+    mp.spawn(_bucket_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    (g0, r0), (g1, r1) = _make(0), _make(1)
+    for n in par.OPTIMISED:
+        assert torch.allclose(got["grads"][n], g0[n] + g1[n], atol=1e-6), n
+    acc = sum(torch.where(r > 0, g["dL_dmeans2D"][:, :2].norm(dim=-1), torch.zeros(r.shape)) for g, r in ((g0, r0), (g1, r1)))
+    assert torch.allclose(got["stats"]["xyz_gradient_accum"], acc, atol=1e-6)
+    assert torch.equal(got["stats"]["denom"], (r0 > 0).float() + (r1 > 0).float())
+    assert torch.equal(got["stats"]["max_radii2D"], torch.maximum(r0, r1).float())
+
+
+def test_bucket_sections_are_aligned_views_of_one_buffer():
+    b = par.GradientBucket(1001, 16, "cpu")
+    base = b.flat.data_ptr()
+    for n, t in b.tensors.items():
+        assert t.is_contiguous() and (t.data_ptr() - base) % 16 == 0, n
+        assert base <= t.data_ptr() < base + b.flat.numel() * 4
+    assert b["dL_dsh"].shape == (1001, 16, 3) and b["dL_dopacity"].shape == (1001, 1)
+
+
 def test_allreduce_is_identity_on_one_rank():
     grads, radii = _make(0)
     ref = {k: v.clone() for k, v in grads.items()}
