@@ -69,7 +69,14 @@ class GradientBucket:
             total += -(-n // 4) * 4
         self.flat = None
         if peer is not False and is_distributed() and torch.device(device).type == "cuda":
-            self.flat = self._symmetric(total, device)
+            flat = self._symmetric(total, device)
+            # every rank must take the same path (the peer kernel is bracketed by cross-rank barriers)
+            ok = torch.tensor([1 if flat is not None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                self.flat = flat
+            else:
+                self.peer = None
         if self.flat is None:
             self.flat = torch.empty((total,), dtype=torch.float32, device=device)
         self.tensors = {}
