@@ -299,6 +299,9 @@ OGS_API int ogs_densify_stats(
  * barrier on the same stream on both sides; omnigs-fork_b200/parallel.py uses torch.distributed's symmetric memory).
  */
 OGS_API int ogs_peer_allreduce_sum(float* const* bufs, int world, int rank, size_t count, void* stream);
+/* Same contract through the bucket's NVLink multicast address (NVSwitch in-switch reduction: multimem.ld_reduce /
+ * multimem.st on slice `rank`); `multicast` is the multicast mapping of the symmetric buffer. */
+OGS_API int ogs_multimem_allreduce_sum(float* multicast, int world, int rank, size_t count, void* stream);
 /* One view's increments of the densification statistics as plain [P] arrays (gaussian_mapper.cpp:427-434,
  * gaussian_model.cpp:839-853): ||dL_dmean2D.xy|| and 1 where radii > 0 (else 0), and the radius as float — what
  * data-parallel ranks sum / sum / max over views before applying them. */

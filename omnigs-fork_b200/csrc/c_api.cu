@@ -665,6 +665,14 @@ OGS_API int ogs_densify_stats(
 	return launch_densify_stats(P, radii, dL_dmean2D, max_radii2D, xyz_gradient_accum, denom, (cudaStream_t)stream);
 }
 
+OGS_API int ogs_multimem_allreduce_sum(float* multicast, int world, int rank, size_t count, void* stream)
+{
+	if (world < 1 || rank < 0 || rank >= world) return fail(OGS_ERR_INVALID_ARG, "0 <= rank < world");
+	if (!multicast || (reinterpret_cast<uintptr_t>(multicast) & 15u) || (count & 3u))
+		return fail(OGS_ERR_INVALID_ARG, "multicast pointer must be 16-byte aligned, count a multiple of 4 floats");
+	return launch_multimem_allreduce_sum(multicast, world, rank, count, (cudaStream_t)stream);
+}
+
 OGS_API int ogs_view_stats(int P, const int* radii, const float* dL_dmean2D, float* grad_norm, float* visible,
                            float* radius, void* stream)
 {

@@ -123,6 +123,7 @@ int launch_view_stats(int P, const int* radii, const float* dL_dmean2D, float* g
 // ---- peer_collective.cu
 constexpr int kMaxPeers = 8;
 int launch_peer_allreduce_sum(float* const* bufs, int world, int rank, size_t count, cudaStream_t st);
+int launch_multimem_allreduce_sum(float* multicast, int world, int rank, size_t count, cudaStream_t st);
 int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D,
                          float* xyz_gradient_accum, float* denom, cudaStream_t st);
 

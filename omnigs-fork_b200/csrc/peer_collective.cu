@@ -58,6 +58,45 @@ __global__ void __launch_bounds__(256) peer_allreduce_sum_kernel(const PeerBuffe
 	}
 }
 
+// NVLink SHARP variant: the bucket's multicast address reaches all ranks' copies at once.  multimem.ld_reduce has the
+// switch add the N copies of an element and return the sum (one inbound copy per element instead of N - 1),
+// multimem.st broadcasts the result to every rank (one outbound copy).  Each rank handles its own slice.
+__global__ void __launch_bounds__(256) multimem_allreduce_sum_kernel(float* mc, size_t begin4, size_t end4)
+{
+	const size_t stride = (size_t)gridDim.x * blockDim.x * kPeerUnroll;
+	for (size_t base = begin4 + (size_t)blockIdx.x * blockDim.x * kPeerUnroll + threadIdx.x; base < end4; base += stride) {
+		float4 acc[kPeerUnroll];
+#pragma unroll
+		for (int u = 0; u < kPeerUnroll; u++) {
+			const size_t i = base + (size_t)u * blockDim.x;
+			if (i < end4)
+				asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+				             : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w)
+				             : "l"(reinterpret_cast<float4*>(mc) + i) : "memory");
+		}
+#pragma unroll
+		for (int u = 0; u < kPeerUnroll; u++) {
+			const size_t i = base + (size_t)u * blockDim.x;
+			if (i < end4)
+				asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+				             :: "l"(reinterpret_cast<float4*>(mc) + i), "f"(acc[u].x), "f"(acc[u].y), "f"(acc[u].z), "f"(acc[u].w) : "memory");
+		}
+	}
+}
+
+int launch_multimem_allreduce_sum(float* multicast, int world, int rank, size_t count, cudaStream_t st)
+{
+	const size_t n4 = count / 4;
+	const size_t per = (n4 + world - 1) / world;
+	const size_t begin4 = min(n4, per * rank), end4 = min(n4, begin4 + per);
+	if (end4 <= begin4) return OGS_OK;
+	const size_t want = (end4 - begin4 + 256 * kPeerUnroll - 1) / (256 * kPeerUnroll);
+	const int blocks = (int)min(want, (size_t)kNumSMs * 8);
+	multimem_allreduce_sum_kernel<<<blocks, 256, 0, st>>>(multicast, begin4, end4);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
 int launch_peer_allreduce_sum(float* const* bufs, int world, int rank, size_t count, cudaStream_t st)
 {
 	PeerBuffers p{};

@@ -103,7 +103,15 @@ class GradientBucket:
             ptrs = [int(p) for p in hdl.buffer_ptrs]
             if len(ptrs) != world or any(p == 0 or p % 16 for p in ptrs):
                 return None
-            self.peer = dict(handle=hdl, ptrs=ptrs, rank=dist.get_rank(), world=world)
+            mc = 0
+            try:
+                mc = int(hdl.multicast_ptr) if hdl.has_multicast_support(torch.device(device).type, torch.device(device).index or 0) else 0
+            except Exception:
+                try:
+                    mc = int(hdl.multicast_ptr)
+                except Exception:
+                    mc = 0
+            self.peer = dict(handle=hdl, ptrs=ptrs, rank=dist.get_rank(), world=world, multicast=mc)
             return flat
         except Exception:   # no symmetric memory on this build / topology
             self.peer = None
@@ -136,7 +144,12 @@ def allreduce_bucket(bucket, dL_dmeans2D, radii, group=None):
         arr = (ctypes.c_void_p * pr["world"])(*pr["ptrs"])
         stream = ctypes.c_void_p(torch.cuda.current_stream(bucket.flat.device).cuda_stream)
         pr["handle"].barrier(channel=0)
-        check(load_library().ogs_peer_allreduce_sum(arr, pr["world"], pr["rank"], bucket.flat.numel(), stream))
+        if pr.get("multicast") and pr.get("use_multimem", pr["world"] > 2):
+            # NVSwitch in-switch reduction: one inbound copy per element instead of world - 1
+            check(load_library().ogs_multimem_allreduce_sum(ctypes.c_void_p(pr["multicast"]), pr["world"], pr["rank"],
+                                                            bucket.flat.numel(), stream))
+        else:
+            check(load_library().ogs_peer_allreduce_sum(arr, pr["world"], pr["rank"], bucket.flat.numel(), stream))
         pr["handle"].barrier(channel=1)
         w2.wait()
     elif is_distributed():

@@ -28,9 +28,6 @@ for it in range(3):
         assert err <= 1e-6 * world, (n, err)
     assert float((stats["xyz_gradient_accum"] - acc_ref).abs().max()) <= 1e-6 * world
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-import ctypes
-lib = h.pkg.load_library()
-arr = (ctypes.c_void_p * world)(*b.peer["ptrs"])
 def kernel_only():
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     b.peer["handle"].barrier(channel=0)
@@ -38,9 +35,30 @@ def kernel_only():
     b.peer["handle"].barrier(channel=1)
 def kernel_bare():
     lib.ogs_peer_allreduce_sum(arr, world, rank, b.flat.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-for name, fn in (("peer (stats + barriers + kernel + max-allreduce)", lambda: par.allreduce_bucket(b, m2d, radii)),
+import ctypes
+lib = h.pkg.load_library()
+arr = (ctypes.c_void_p * world)(*b.peer["ptrs"])
+def set_mm(v):
+    b.peer["use_multimem"] = v
+if rank == 0: print("multicast pointer:", hex(b.peer.get("multicast") or 0))
+if b.peer.get("multicast"):
+    set_mm(True)
+    b.flat.copy_(src); par.allreduce_bucket(b, m2d, radii); torch.cuda.synchronize()
+    for n in par.OPTIMISED:
+        o = b[n].data_ptr() - b.flat.data_ptr()
+        sec = ref.view(-1)[o // 4: o // 4 + b[n].numel()].view(b[n].shape)
+        assert float((b[n] - sec).abs().max()) <= 2e-6 * world, n
+    if rank == 0: print("multimem all-reduce matches NCCL")
+def mm_only():
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    b.peer["handle"].barrier(channel=0)
+    lib.ogs_multimem_allreduce_sum(ctypes.c_void_p(b.peer["multicast"]), world, rank, b.flat.numel(), st)
+    b.peer["handle"].barrier(channel=1)
+extra = (("multimem barriers + kernel", mm_only),) if b.peer.get("multicast") else ()
+set_mm(False)
+for name, fn in (("peer (stats + barriers + kernel + max-allreduce)", lambda: par.allreduce_bucket(b, m2d, radii)),) + extra + (
                  ("peer barriers + kernel", kernel_only),
-                 ("nccl", lambda: dist.all_reduce(ref))):
+                 ("nccl", lambda: dist.all_reduce(ref)),):
     for _ in range(3): fn()
     dist.barrier(); torch.cuda.synchronize(); e0.record()
     for _ in range(20): fn()
