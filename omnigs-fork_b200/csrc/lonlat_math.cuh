@@ -313,6 +313,53 @@ OGS_D V3 sh_to_rgb(int deg, float3 mean, float3 campos, ShPtr sh, unsigned& clam
 	return { result.x < 0.0f ? 0.0f : result.x, result.y < 0.0f ? 0.0f : result.y, result.z < 0.0f ? 0.0f : result.z };
 }
 
+// The same evaluation with every operation pinned to the order of the reference's compiled computeColorFromSH
+// (its sm_100 SASS): dir = (p - c) / sqrt(dot), every term is  result = fma(coef, sh_k, result)  with
+// coef = (C * a) * b  built from plain multiplies; 2zz = zz + zz; 3xx - yy = fma(xx, 3, -yy);
+// 4zz - xx - yy = fma(zz, 4, -xx) - yy; 2zz - 3xx - 3yy = fma(yy, -3, fma(xx, -3, zz + zz)); xx - 3yy = fma(yy, -3, xx).
+// The colours enter the image directly, so this makes the image bit-identical to the reference's, not merely <= 1e-5.
+template <typename ShPtr>
+OGS_D V3 sh_to_rgb_p(int deg, float3 mean, float3 campos, ShPtr sh, unsigned& clamp_mask)
+{
+	const float dx = __fsub_rn(mean.x, campos.x), dy = __fsub_rn(mean.y, campos.y), dz = __fsub_rn(mean.z, campos.z);
+	const float len = __fsqrt_rn(dot3p(dx, dx, dy, dy, dz, dz));
+	const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
+	V3 c = sh(0);
+	V3 r = { __fmul_rn(c.x, kSH_C0), __fmul_rn(c.y, kSH_C0), __fmul_rn(c.z, kSH_C0) };
+	auto acc = [&r, &sh](float t, int k) {
+		const V3 s = sh(k);
+		r.x = __fmaf_rn(t, s.x, r.x); r.y = __fmaf_rn(t, s.y, r.y); r.z = __fmaf_rn(t, s.z, r.z);
+	};
+	if (deg > 0) {
+		acc(-__fmul_rn(kSH_C1, y), 1);
+		acc(__fmul_rn(kSH_C1, z), 2);
+		acc(-__fmul_rn(kSH_C1, x), 3);
+		if (deg > 1) {
+			const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+			const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+			const float zz2 = __fadd_rn(zz, zz), xx_yy = __fsub_rn(xx, yy);
+			acc(__fmul_rn(kSH_C2[0], xy), 4);
+			acc(__fmul_rn(kSH_C2[1], yz), 5);
+			acc(__fmul_rn(kSH_C2[2], __fsub_rn(__fsub_rn(zz2, xx), yy)), 6);
+			acc(__fmul_rn(kSH_C2[3], xz), 7);
+			acc(__fmul_rn(kSH_C2[4], xx_yy), 8);
+			if (deg > 2) {
+				const float u = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);   // 4zz - xx - yy
+				acc(__fmul_rn(__fmul_rn(kSH_C3[0], y), __fmaf_rn(xx, 3.0f, -yy)), 9);
+				acc(__fmul_rn(__fmul_rn(kSH_C3[1], xy), z), 10);
+				acc(__fmul_rn(__fmul_rn(kSH_C3[2], y), u), 11);
+				acc(__fmul_rn(__fmul_rn(kSH_C3[3], z), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2))), 12);
+				acc(__fmul_rn(__fmul_rn(kSH_C3[4], x), u), 13);
+				acc(__fmul_rn(__fmul_rn(kSH_C3[5], z), xx_yy), 14);
+				acc(__fmul_rn(__fmul_rn(kSH_C3[6], x), __fmaf_rn(yy, -3.0f, xx)), 15);
+			}
+		}
+	}
+	r.x = __fadd_rn(r.x, 0.5f); r.y = __fadd_rn(r.y, 0.5f); r.z = __fadd_rn(r.z, 0.5f);
+	clamp_mask = (r.x < 0 ? 1u : 0u) | (r.y < 0 ? 2u : 0u) | (r.z < 0 ? 4u : 0u);
+	return { r.x < 0.0f ? 0.0f : r.x, r.y < 0.0f ? 0.0f : r.y, r.z < 0.0f ? 0.0f : r.z };
+}
+
 // d|v|^-1 v / dv applied to dv (auxiliary.h:134-144)
 OGS_D float3 dnormvdv(float3 v, float3 dv)
 {

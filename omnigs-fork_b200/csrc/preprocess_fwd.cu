@@ -27,6 +27,10 @@ namespace ogs {
 
 constexpr int kPreThreads = 128;
 
+// Out of line on purpose: inlined, its expf/logf bodies change the instruction selection (FMA contraction) of the
+// surrounding, bit-compared projection and SH code.
+__device__ __noinline__ float alpha_cutoff_power_call(float opacity) { return alpha_cutoff_power(opacity); }
+
 // kMode: 0 SH rows by plain loads, 1 SH rows [P,16,3] by per-row bulk copies,
 //        2 raw parameters with split SH by per-CTA bulk copies, 3 raw parameters by plain loads.
 // kPinhole: the perspective camera (camera_type 1; forward.cu:232-340) instead of the equirectangular one.
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 #pragma unroll
 				for (int k = 0; k < kRawRestFloats; k++) shr[3 + k] = s_sh[tid * kRawRestFloats + k];
 				auto sh = [&shr](int k) { return V3{ shr[3 * k], shr[3 * k + 1], shr[3 * k + 2] }; };
-				c = sh_to_rgb(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
+				c = sh_to_rgb_p(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
 			} else if constexpr (kMode == 3) {
 				const float* dc = a.features_dc + (size_t)idx * 3;
 				const float* rest = a.features_rest + (size_t)idx * (a.M - 1) * 3;
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 					const float* p = k == 0 ? dc : rest + 3 * (k - 1);
 					return V3{ p[0], p[1], p[2] };
 				};
-				c = sh_to_rgb(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
+				c = sh_to_rgb_p(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
 			} else if constexpr (kBulkSH) {
 				float shr[kShRowFloats];
 				const float4* row = reinterpret_cast<const float4*>(&s_sh[tid * kShPitchFloats]);
@@ -211,11 +215,11 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 					shr[4 * k] = q.x; shr[4 * k + 1] = q.y; shr[4 * k + 2] = q.z; shr[4 * k + 3] = q.w;
 				}
 				auto sh = [&shr](int k) { return V3{ shr[3 * k], shr[3 * k + 1], shr[3 * k + 2] }; };
-				c = sh_to_rgb(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
+				c = sh_to_rgb_p(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
 			} else {
 				const float* shp = a.shs + (size_t)idx * a.M * 3;
 				auto sh = [shp](int k) { return V3{ shp[3 * k], shp[3 * k + 1], shp[3 * k + 2] }; };
-				c = sh_to_rgb(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
+				c = sh_to_rgb_p(a.D, p_orig, float3{ sCam[0], sCam[1], sCam[2] }, sh, cmask);
 			}
 			rgb = { c.x, c.y, c.z };
 		} else {
@@ -229,7 +233,11 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 		float opacity = a.opacities[idx];
 		if (kRaw) opacity = sigmoid_act(opacity);   // getOpacityActivation, gaussian_model.cpp:74-77
 		a.g1[idx] = make_float4(conic.z, opacity, rgb.x, rgb.y);
-		a.gb[idx] = make_float2(rgb.z, alpha_cutoff_power(opacity));
+#if defined(OGS_VAR_OLDTAU)
+		a.gb[idx] = make_float2(rgb.z, (opacity > 0.f) ? (-logf(255.0f * opacity) - 1e-3f) : -INFINITY);
+#else
+		a.gb[idx] = make_float2(rgb.z, alpha_cutoff_power_call(opacity));
+#endif
 		if (emits) {
 			a.depth[idx] = r;
 			a.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));

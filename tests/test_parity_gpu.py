@@ -172,6 +172,12 @@ def test_against_reference_rasterizer(case):
     assert torch.equal(so["point_list"], sr["point_list"])
     assert torch.equal(so["point_list_keys"], sr["point_list_keys"])
     assert float((fo[1] - fr[1]).abs().max()) <= IMG_TOL
+    if d["camera_type"] == 3 and mode != "colors":
+        # beyond the stated tolerance: SH colours and blend are pinned to the reference's operation order, so the
+        # lonlat image is bit-identical
+        assert torch.equal(bits(so["rgb"][vis]), bits(sr["rgb"][vis]))
+    if d["camera_type"] == 3:
+        assert torch.equal(bits(fo[1]), bits(fr[1]))
     assert float((so["accum_alpha"] - sr["accum_alpha"]).abs().max()) <= IMG_TOL
     assert torch.equal(so["n_contrib"], sr["n_contrib"])
     if d["camera_type"] == 1:
