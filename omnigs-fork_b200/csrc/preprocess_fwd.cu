@@ -27,8 +27,7 @@ namespace ogs {
 
 constexpr int kPreThreads = 128;
 
-// Out of line on purpose: inlined, its expf/logf bodies change the instruction selection (FMA contraction) of the
-// surrounding, bit-compared projection and SH code.
+// Out of line: keeps the expf/logf bodies of the ulp walk out of the (long, register-hungry) projection code.
 __device__ __noinline__ float alpha_cutoff_power_call(float opacity) { return alpha_cutoff_power(opacity); }
 
 // kMode: 0 SH rows by plain loads, 1 SH rows [P,16,3] by per-row bulk copies,
@@ -233,11 +232,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 		float opacity = a.opacities[idx];
 		if (kRaw) opacity = sigmoid_act(opacity);   // getOpacityActivation, gaussian_model.cpp:74-77
 		a.g1[idx] = make_float4(conic.z, opacity, rgb.x, rgb.y);
-#if defined(OGS_VAR_OLDTAU)
-		a.gb[idx] = make_float2(rgb.z, (opacity > 0.f) ? (-logf(255.0f * opacity) - 1e-3f) : -INFINITY);
-#else
 		a.gb[idx] = make_float2(rgb.z, alpha_cutoff_power_call(opacity));
-#endif
 		if (emits) {
 			a.depth[idx] = r;
 			a.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)by0 | ((uint32_t)by1 << 16));

@@ -5,8 +5,8 @@
 //     with I = rendered * mask, optionally cropped at the bottom (gaussian_mapper.cpp:391-413).
 //     SSIM is the reference's: 11x11 Gaussian window (sigma 1.5), zero padding, per channel, mean over all
 //     elements (include/loss_utils.h:58-131, built there from five grouped conv2d calls and autograd).
-//     Forward kernel: one CTA per 16x16 pixel block and channel stages the 26x26 halo of both images in shared
-//     memory, runs the separable window over the five moment maps, evaluates the SSIM map and its three
+//     Forward kernel: one CTA per 32x32 pixel block and channel stages the 42x42 halo of both images in shared
+//     memory, runs the separable window (register-tiled, four outputs per thread) over the five moment maps, evaluates the SSIM map and its three
 //     partial derivatives (w.r.t. mu1, sigma1^2, sigma12) and accumulates the two loss sums.
 //     Backward kernel: the window is self-adjoint, so dL/dI is the same separable filter applied to the three
 //     derivative maps:  dSSIM/dI(p) = (w * dm_dmu1)(p) + 2 I(p) (w * dm_dsigma1sq)(p) + gt(p) (w * dm_dsigma12)(p).
@@ -18,9 +18,12 @@
 
 namespace ogs {
 
-constexpr int kLossTile = 16;
+constexpr int kLossTile = 32;                  // output pixels per CTA edge
+constexpr int kLossThreads = 256;
 constexpr int kWin = 11, kHalf = 5;
-constexpr int kHalo = kLossTile + 2 * kHalf;   // 26
+constexpr int kHalo = kLossTile + 2 * kHalf;   // 42
+constexpr int kHaloPitch = 44;                 // 16-byte aligned rows; a 4-output group reads columns 4g .. 4g+15 <= 43
+constexpr int kGroups = kLossTile / 4;         // 4 horizontally (H pass) / vertically (V pass) adjacent outputs per thread
 
 struct LossArgs {
 	int W, H, H_used;          // rows >= H_used are cropped away (skip_bottom_ratio)
@@ -45,21 +48,24 @@ OGS_D float masked_pixel(const LossArgs& a, int ch, int x, int y)
 	return v;
 }
 
-__global__ void __launch_bounds__(kLossTile * kLossTile) ssim_l1_fwd_kernel(const LossArgs a)
+// Both kernels run the separable 11-tap window register-tiled: a thread produces FOUR adjacent outputs per pass
+// from 14 inputs (128-bit shared loads in the horizontal pass), so an output costs 3.5 shared loads per map instead
+// of 11 (the first version was bound by shared-memory bandwidth: ncu L1/shared 88-91 %).
+__global__ void __launch_bounds__(kLossThreads) ssim_l1_fwd_kernel(const LossArgs a)
 {
-	__shared__ float s_x[kHalo][kHalo + 1], s_y[kHalo][kHalo + 1];
-	__shared__ float s_h[5][kHalo][kLossTile];
-	__shared__ float s_red[2][8];
-	const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kLossTile + tx;
+	__shared__ __align__(16) float s_x[kHalo][kHaloPitch], s_y[kHalo][kHaloPitch];
+	__shared__ __align__(16) float s_h[5][kHalo][kLossTile];
+	__shared__ float s_red[2][kLossThreads / 32];
+	const int tid = threadIdx.x;
 	const int ch = blockIdx.z;
 	const int x0 = blockIdx.x * kLossTile - kHalf, y0 = blockIdx.y * kLossTile - kHalf;
 	const size_t HW = (size_t)a.H * a.W;
 
-	for (int i = tid; i < kHalo * kHalo; i += kLossTile * kLossTile) {
-		const int r = i / kHalo, c = i % kHalo;
+	for (int i = tid; i < kHalo * kHaloPitch; i += kLossThreads) {
+		const int r = i / kHaloPitch, c = i % kHaloPitch;
 		const int x = x0 + c, y = y0 + r;
 		float vx = 0.f, vy = 0.f;   // zero padding outside the (cropped) image
-		if (x >= 0 && x < a.W && y >= 0 && y < a.H_used) {
+		if (c < kHalo && x >= 0 && x < a.W && y >= 0 && y < a.H_used) {
 			vx = masked_pixel(a, ch, x, y);
 			vy = a.gt[ch * HW + (size_t)y * a.W + x];
 		}
@@ -67,46 +73,87 @@ __global__ void __launch_bounds__(kLossTile * kLossTile) ssim_l1_fwd_kernel(cons
 		s_y[r][c] = vy;
 	}
 	__syncthreads();
-	// horizontal pass: 26 rows x 16 columns, five moment maps
-	for (int i = tid; i < kHalo * kLossTile; i += kLossTile * kLossTile) {
-		const int r = i / kLossTile, c = i % kLossTile;
-		float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+	// horizontal pass: 42 rows x 8 groups of 4 columns, five moment maps
+	for (int item = tid; item < kHalo * kGroups; item += kLossThreads) {
+		const int r = item / kGroups, g = item % kGroups;
+		float vx[16], vy[16];
 #pragma unroll
-		for (int k = 0; k < kWin; k++) {
-			const float w = a.w[k], vx = s_x[r][c + k], vy = s_y[r][c + k];
-			m1 += w * vx; m2 += w * vy;
-			e11 += w * vx * vx; e22 += w * vy * vy; e12 += w * vx * vy;
+		for (int q = 0; q < 4; q++) {
+			const float4 fx = *reinterpret_cast<const float4*>(&s_x[r][4 * g + 4 * q]);
+			const float4 fy = *reinterpret_cast<const float4*>(&s_y[r][4 * g + 4 * q]);
+			vx[4 * q] = fx.x; vx[4 * q + 1] = fx.y; vx[4 * q + 2] = fx.z; vx[4 * q + 3] = fx.w;
+			vy[4 * q] = fy.x; vy[4 * q + 1] = fy.y; vy[4 * q + 2] = fy.z; vy[4 * q + 3] = fy.w;
 		}
-		s_h[0][r][c] = m1; s_h[1][r][c] = m2; s_h[2][r][c] = e11; s_h[3][r][c] = e22; s_h[4][r][c] = e12;
+		float o[5][4];
+#pragma unroll
+		for (int m = 0; m < 5; m++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) o[m][j] = 0.f;
+#pragma unroll
+		for (int i = 0; i < 14; i++) {
+			const float xx = vx[i] * vx[i], yy = vy[i] * vy[i], xy = vx[i] * vy[i];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int k = i - j;   // tap index of input i for output j
+				if (k >= 0 && k < kWin) {
+					const float w = a.w[k];
+					o[0][j] += w * vx[i]; o[1][j] += w * vy[i];
+					o[2][j] += w * xx; o[3][j] += w * yy; o[4][j] += w * xy;
+				}
+			}
+		}
+#pragma unroll
+		for (int m = 0; m < 5; m++)
+			*reinterpret_cast<float4*>(&s_h[m][r][4 * g]) = make_float4(o[m][0], o[m][1], o[m][2], o[m][3]);
 	}
 	__syncthreads();
-	const int x = blockIdx.x * kLossTile + tx, y = blockIdx.y * kLossTile + ty;
-	float l1 = 0.f, ssim = 0.f;
-	if (x < a.W && y < a.H_used) {
-		float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+	// vertical pass: column c, output rows 4 rg .. 4 rg + 3
+	const int c = tid % kLossTile, rg = tid / kLossTile;
+	float o[5][4];
 #pragma unroll
-		for (int k = 0; k < kWin; k++) {
-			const float w = a.w[k];
-			mu1 += w * s_h[0][ty + k][tx]; mu2 += w * s_h[1][ty + k][tx];
-			e11 += w * s_h[2][ty + k][tx]; e22 += w * s_h[3][ty + k][tx]; e12 += w * s_h[4][ty + k][tx];
+	for (int m = 0; m < 5; m++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) o[m][j] = 0.f;
+#pragma unroll
+	for (int i = 0; i < 14; i++) {
+		float v[5];
+#pragma unroll
+		for (int m = 0; m < 5; m++) v[m] = s_h[m][4 * rg + i][c];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int k = i - j;
+			if (k >= 0 && k < kWin) {
+				const float w = a.w[k];
+#pragma unroll
+				for (int m = 0; m < 5; m++) o[m][j] += w * v[m];
+			}
 		}
-		// loss_utils.h:93-108
-		const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
-		const float sigma1_sq = e11 - mu1_sq, sigma2_sq = e22 - mu2_sq, sigma12 = e12 - mu1_mu2;
-		const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-		const float A = mu1_sq + mu2_sq + C1, B = sigma1_sq + sigma2_sq + C2;
-		const float C = 2.f * mu1_mu2 + C1, D = 2.f * sigma12 + C2;
-		const float invAB = 1.f / (A * B);
-		ssim = C * D * invAB;
-		// partial derivatives of the map (sigma's dependence on mu1 folded into dm_dmu1)
-		const float dm_dmu1 = 2.f * invAB * (mu2 * (D - C) - mu1 * C * D / A + mu1 * C * D / B);
-		const float dm_ds1 = -C * D * invAB / B;
-		const float dm_ds12 = 2.f * C * invAB;
-		const size_t i = (size_t)y * a.W + x;
-		a.dmaps[(0 * 3 + ch) * HW + i] = dm_dmu1;
-		a.dmaps[(1 * 3 + ch) * HW + i] = dm_ds1;
-		a.dmaps[(2 * 3 + ch) * HW + i] = dm_ds12;
-		l1 = fabsf(s_x[ty + kHalf][tx + kHalf] - s_y[ty + kHalf][tx + kHalf]);
+	}
+	float l1 = 0.f, ssim = 0.f;
+	const int x = blockIdx.x * kLossTile + c;
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		const int ly = 4 * rg + j, y = blockIdx.y * kLossTile + ly;
+		if (x < a.W && y < a.H_used) {
+			const float mu1 = o[0][j], mu2 = o[1][j], e11 = o[2][j], e22 = o[3][j], e12 = o[4][j];
+			// loss_utils.h:93-108
+			const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
+			const float sigma1_sq = e11 - mu1_sq, sigma2_sq = e22 - mu2_sq, sigma12 = e12 - mu1_mu2;
+			const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+			const float A = mu1_sq + mu2_sq + C1, B = sigma1_sq + sigma2_sq + C2;
+			const float C = 2.f * mu1_mu2 + C1, D = 2.f * sigma12 + C2;
+			const float invAB = 1.f / (A * B);
+			ssim += C * D * invAB;
+			// partial derivatives of the map (sigma's dependence on mu1 folded into dm_dmu1)
+			const float dm_dmu1 = 2.f * invAB * (mu2 * (D - C) - mu1 * C * D / A + mu1 * C * D / B);
+			const float dm_ds1 = -C * D * invAB / B;
+			const float dm_ds12 = 2.f * C * invAB;
+			const size_t i = (size_t)y * a.W + x;
+			a.dmaps[(0 * 3 + ch) * HW + i] = dm_dmu1;
+			a.dmaps[(1 * 3 + ch) * HW + i] = dm_ds1;
+			a.dmaps[(2 * 3 + ch) * HW + i] = dm_ds12;
+			l1 += fabsf(s_x[ly + kHalf][c + kHalf] - s_y[ly + kHalf][c + kHalf]);
+		}
 	}
 	l1 = warp_sum(l1);
 	ssim = warp_sum(ssim);
@@ -114,16 +161,16 @@ __global__ void __launch_bounds__(kLossTile * kLossTile) ssim_l1_fwd_kernel(cons
 	__syncthreads();
 	if (tid < 2) {
 		double t = 0.0;
-		for (int w = 0; w < 8; w++) t += (double)s_red[tid][w];
+		for (int w = 0; w < kLossThreads / 32; w++) t += (double)s_red[tid][w];
 		atomicAdd(&a.sums[tid], t);
 	}
 }
 
-__global__ void __launch_bounds__(kLossTile * kLossTile) ssim_l1_bwd_kernel(const LossArgs a)
+__global__ void __launch_bounds__(kLossThreads) ssim_l1_bwd_kernel(const LossArgs a)
 {
-	__shared__ float s_d[3][kHalo][kHalo + 1];
-	__shared__ float s_h[3][kHalo][kLossTile];
-	const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kLossTile + tx;
+	__shared__ __align__(16) float s_d[3][kHalo][kHaloPitch];
+	__shared__ __align__(16) float s_h[3][kHalo][kLossTile];
+	const int tid = threadIdx.x;
 	const int ch = blockIdx.z;
 	const int x0 = blockIdx.x * kLossTile - kHalf, y0 = blockIdx.y * kLossTile - kHalf;
 	const size_t HW = (size_t)a.H * a.W;
@@ -135,47 +182,77 @@ __global__ void __launch_bounds__(kLossTile * kLossTile) ssim_l1_bwd_kernel(cons
 		a.loss_out[1] = (float)l1;
 		a.loss_out[2] = (float)ssim;
 	}
-	for (int i = tid; i < kHalo * kHalo; i += kLossTile * kLossTile) {
-		const int r = i / kHalo, c = i % kHalo;
+	for (int i = tid; i < kHalo * kHaloPitch; i += kLossThreads) {
+		const int r = i / kHaloPitch, c = i % kHaloPitch;
 		const int x = x0 + c, y = y0 + r;
-		const bool in = x >= 0 && x < a.W && y >= 0 && y < a.H_used;
+		const bool in = c < kHalo && x >= 0 && x < a.W && y >= 0 && y < a.H_used;
 		const size_t p = (size_t)y * a.W + x;
 #pragma unroll
 		for (int m = 0; m < 3; m++) s_d[m][r][c] = in ? a.dmaps[(m * 3 + ch) * HW + p] : 0.f;
 	}
 	__syncthreads();
-	for (int i = tid; i < kHalo * kLossTile; i += kLossTile * kLossTile) {
-		const int r = i / kLossTile, c = i % kLossTile;
-		float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+	for (int item = tid; item < kHalo * kGroups; item += kLossThreads) {
+		const int r = item / kGroups, g = item % kGroups;
+		float o[3][4];
 #pragma unroll
-		for (int k = 0; k < kWin; k++) {
-			const float w = a.w[k];
-			h0 += w * s_d[0][r][c + k]; h1 += w * s_d[1][r][c + k]; h2 += w * s_d[2][r][c + k];
+		for (int m = 0; m < 3; m++) {
+			float v[16];
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const float4 f = *reinterpret_cast<const float4*>(&s_d[m][r][4 * g + 4 * q]);
+				v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+			}
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				float t = 0.f;
+#pragma unroll
+				for (int k = 0; k < kWin; k++) t += a.w[k] * v[j + k];
+				o[m][j] = t;
+			}
+			*reinterpret_cast<float4*>(&s_h[m][r][4 * g]) = make_float4(o[m][0], o[m][1], o[m][2], o[m][3]);
 		}
-		s_h[0][r][c] = h0; s_h[1][r][c] = h1; s_h[2][r][c] = h2;
 	}
 	__syncthreads();
-	const int x = blockIdx.x * kLossTile + tx, y = blockIdx.y * kLossTile + ty;
-	if (x >= a.W || y >= a.H) return;
-	const size_t i = (size_t)y * a.W + x;
-	float grad = 0.f;
-	if (y < a.H_used) {
-		float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+	const int c = tid % kLossTile, rg = tid / kLossTile;
+	float o[3][4];
 #pragma unroll
-		for (int k = 0; k < kWin; k++) {
-			const float w = a.w[k];
-			c0 += w * s_h[0][ty + k][tx]; c1 += w * s_h[1][ty + k][tx]; c2 += w * s_h[2][ty + k][tx];
+	for (int m = 0; m < 3; m++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) o[m][j] = 0.f;
+#pragma unroll
+	for (int i = 0; i < 14; i++) {
+		float v[3];
+#pragma unroll
+		for (int m = 0; m < 3; m++) v[m] = s_h[m][4 * rg + i][c];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int k = i - j;
+			if (k >= 0 && k < kWin) {
+#pragma unroll
+				for (int m = 0; m < 3; m++) o[m][j] += a.w[k] * v[m];
+			}
 		}
-		const float I = masked_pixel(a, ch, x, y), g = a.gt[ch * HW + i];
-		const float dssim = c0 + 2.f * I * c1 + g * c2;
-		const float diff = I - g;
-		const float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
-		const float inv = (float)(1.0 / count);
-		grad = (1.f - a.lambda_dssim) * sgn * inv - a.lambda_dssim * dssim * inv;
-		if (a.mask_channels == 1) grad *= a.mask[i];
-		else if (a.mask_channels == 3) grad *= a.mask[ch * HW + i];
 	}
-	a.dL_dpix[ch * HW + i] = grad;
+	const int x = blockIdx.x * kLossTile + c;
+	if (x >= a.W) return;
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		const int y = blockIdx.y * kLossTile + 4 * rg + j;
+		if (y >= a.H) continue;
+		const size_t i = (size_t)y * a.W + x;
+		float grad = 0.f;
+		if (y < a.H_used) {
+			const float I = masked_pixel(a, ch, x, y), g = a.gt[ch * HW + i];
+			const float dssim = o[0][j] + 2.f * I * o[1][j] + g * o[2][j];
+			const float diff = I - g;
+			const float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
+			const float inv = (float)(1.0 / count);
+			grad = (1.f - a.lambda_dssim) * sgn * inv - a.lambda_dssim * dssim * inv;
+			if (a.mask_channels == 1) grad *= a.mask[i];
+			else if (a.mask_channels == 3) grad *= a.mask[ch * HW + i];
+		}
+		a.dL_dpix[ch * HW + i] = grad;
+	}
 }
 
 int launch_photometric_loss(int W, int H, int H_used, float lambda_dssim, const float* rendered, const float* gt,
@@ -197,9 +274,9 @@ int launch_photometric_loss(int W, int H, int H_used, float lambda_dssim, const 
 	a.dmaps = workspace + 4;   // behind the two 8-byte sums
 	a.loss_out = loss_out; a.dL_dpix = dL_dpix;
 	OGS_CUDA_TRY(cudaMemsetAsync(a.sums, 0, 2 * sizeof(double), st));
-	const dim3 grid(ceil_div(W, kLossTile), ceil_div(H, kLossTile), 3), block(kLossTile, kLossTile);
-	ssim_l1_fwd_kernel<<<grid, block, 0, st>>>(a);
-	ssim_l1_bwd_kernel<<<grid, block, 0, st>>>(a);
+	const dim3 grid(ceil_div(W, kLossTile), ceil_div(H, kLossTile), 3);
+	ssim_l1_fwd_kernel<<<grid, kLossThreads, 0, st>>>(a);
+	ssim_l1_bwd_kernel<<<grid, kLossThreads, 0, st>>>(a);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }
