@@ -397,7 +397,7 @@ def main():
                               "stage_ms": stage_ms}
     if world == 1:
         line["train_step"] = training_iteration_bench(h, scene, views, dev, K, Wm, None)
-    line["gpu_launches"] = K * (12 + 2)   # fwd: preprocess, hist, 4+2 onesweep, scan, ranges, emit, render; bwd: 2
+    line["gpu_launches"] = K * (11 + 2)   # fwd: preprocess, hist, 4 + 2 onesweep (the first tile pass emits), scan, ranges, render; bwd: 2
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port_baseline(scene, views[Wm], dL_np)
     print(json.dumps(line))

@@ -9,16 +9,18 @@
 //   of a Gaussian share them, so those passes commute with the duplication step:
 //     1. stable-sort the P Gaussians by depth bits            (P-sized, 4 x 8-bit onesweep passes)
 //     2. emit tile instances in that order, row-major inside each rect (load-balanced expansion)
-//     3. stable-sort the R instances by tile id only           (ceil(bit/9) <= 2 onesweep passes)
+//     3. stable-sort the R instances by tile id only           (ceil(bit/9) <= 2 onesweep passes; the first one
+//        generates its input with the emission logic instead of loading it)
 //   Equal (tile, depth) keys end in ascending Gaussian index, as with the reference (stability).
 //   Tile ranges never need the sorted keys: the per-tile instance counts come from a 2-D
 //   difference array that preprocess fills with 4 atomics per Gaussian; their prefix sum IS
 //   `ranges`, and the radix digit histograms are its marginals.
 //
-// HBM traffic at R instances: 8R (emit) + 16R + 12R (two passes) = 36R bytes, against
+// HBM traffic at R instances: 8R (first pass, which emits its own input) + 12R (second pass) = 20R bytes, against
 // 12R + (8 + 24*6)R = 164R for the reference's data flow.
 #include "ogs_common.cuh"
 #include "launchers.cuh"
+#include <cstdlib>
 
 namespace ogs {
 
@@ -93,10 +95,23 @@ struct OnesweepSmem {
 	uint32_t vals[kSortItemsPerBlock];
 	uint32_t tile_hist[kMaxBins];                    // digit counts of this tile (published early)
 	uint32_t warp_tmp[8];
-	uint32_t tile;
 };
 
 constexpr int kLookbackBatch = 8;
+
+// Load-balanced emission of tile instances (see emit_instances below): staging area for one block of
+// kEmitPerBlock consecutive output slots.  The fused first tile-sort pass overlays it on OnesweepSmem.
+constexpr int kEmitPerBlock = 2048;
+static_assert(kEmitPerBlock == kSortItemsPerBlock, "the fused emit + sort pass produces one sort tile per block");
+struct EmitSmem {
+	uint32_t off[kEmitPerBlock + 2];
+	uint32_t gid[kEmitPerBlock + 1];
+	uint2 rect[kEmitPerBlock + 1];
+	uint32_t src[kEmitPerBlock];      // slot -> local source index (after the max-scan)
+	uint32_t warp_max[kSortThreads / 32];
+	uint32_t first, last;
+};
+constexpr size_t kOnesweepSmemBytes = sizeof(OnesweepSmem) > sizeof(EmitSmem) ? sizeof(OnesweepSmem) : sizeof(EmitSmem);
 
 // Decoupled look-back for one counter: sum the predecessors' published values back to the nearest
 // inclusive one.  Status words of kLookbackBatch predecessors are fetched together, so the walk
@@ -131,20 +146,116 @@ OGS_D uint32_t lookback_sum(const uint32_t* __restrict__ status, int tile, size_
 	return excl;
 }
 
-template <int BITS>
+
+// Slot -> (tile id, Gaussian id) for the kEmitPerBlock output slots [o0, o1) of one block.  Output slot o belongs to
+// the depth-ordered Gaussian i with emit_offset[i] <= o < emit_offset[i+1]; inside a Gaussian, slots walk its tile
+// rect row-major (the order of duplicateWithKeys, rasterizer_impl.cu:127-138).  After this call em.src / em.off /
+// em.gid / em.rect are ready and emit_slot() evaluates any slot of the block.
+OGS_D void emit_prepare(EmitSmem& em, uint32_t block, uint32_t o0, uint32_t o1,
+                        const uint32_t* __restrict__ emit_offset, const uint32_t* __restrict__ order,
+                        const uint2* __restrict__ rect, const uint32_t* __restrict__ first_src)
+{
+	constexpr int kPerThread = kEmitPerBlock / kSortThreads;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	// sources owning the first and the last slot of this block (table written by gather_scan_kernel)
+	if (tid == 0) em.first = first_src[block];
+	if (tid == 1) em.last = first_src[block + 1];   // owner of slot min(o1, R-1): may start exactly at o1
+#pragma unroll
+	for (int k = 0; k < kPerThread; k++) em.src[tid + k * kSortThreads] = 0u;
+	__syncthreads();
+	const uint32_t first = em.first, last = em.last;
+	// every source in [first, last) owns >= 1 slot of this block (zero-count Gaussians sort to the end
+	// of the depth order), so ns <= kEmitPerBlock + 1 and the head marks below never collide
+	const uint32_t ns = last - first + 1;
+	for (uint32_t i = tid; i < ns; i += kSortThreads) {
+		const uint32_t g = order[first + i];
+		const uint32_t off = emit_offset[first + i];
+		em.off[i] = off;
+		em.gid[i] = g;
+		em.rect[i] = rect[g];
+		if (i > 0 && off < o1) em.src[off - o0] = i;   // head of source i (source 0 starts at or before slot 0)
+	}
+	__syncthreads();
+	// inclusive max-scan of the head marks: slot -> source index
+	uint32_t v[kPerThread];
+	uint32_t run = 0;
+#pragma unroll
+	for (int k = 0; k < kPerThread; k++) {
+		run = max(run, em.src[tid * kPerThread + k]);
+		v[k] = run;
+	}
+	uint32_t incl = run;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl = max(incl, u);
+	}
+	if (lane == 31) em.warp_max[warp] = incl;
+	const uint32_t prev_lane = __shfl_up_sync(0xffffffffu, incl, 1);
+	__syncthreads();
+	uint32_t carry = (lane > 0) ? prev_lane : 0u;
+	for (int w = 0; w < warp; w++) carry = max(carry, em.warp_max[w]);
+#pragma unroll
+	for (int k = 0; k < kPerThread; k++) em.src[tid * kPerThread + k] = max(v[k], carry);
+	__syncthreads();
+}
+OGS_D void emit_slot(const EmitSmem& em, uint32_t o, uint32_t o0, int gx, uint32_t& tile_key, uint32_t& gid)
+{
+	const uint32_t src = em.src[o - o0];
+	const uint2 rc = em.rect[src];
+	const uint32_t x0 = rc.x & 0xFFFFu, x1 = rc.x >> 16, y0 = rc.y & 0xFFFFu;
+	const uint32_t w = x1 - x0;
+	const uint32_t local = o - em.off[src];
+	const uint32_t q = local / w;
+	uint32_t x = x0 + (local - q * w);
+	if (x >= (uint32_t)gx) x -= (uint32_t)gx;   // only rects that wrap around the longitude seam (opt-in mode)
+	tile_key = (y0 + q) * (uint32_t)gx + x;
+	gid = em.gid[src];
+}
+
+// kEmit: the pass generates its (tile key, Gaussian id) pairs itself (emit_prepare / emit_slot) instead of loading
+// them: the first tile-sort pass then needs no materialised unsorted list (saves writing and re-reading 8 R bytes).
+struct EmitSource {
+	const uint32_t* emit_offset;
+	const uint32_t* order;
+	const uint2* rect;
+	const uint32_t* first_src;
+	int gx;
+};
+
+template <int BITS, bool kEmit = false>
 __global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
 	uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
 	uint32_t n, int shift,
-	const uint32_t* __restrict__ digit_counts, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket)
+	const uint32_t* __restrict__ digit_counts, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket,
+	const EmitSource es)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
+	__shared__ uint32_t s_tile;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr int nbins = 1 << BITS;
 	constexpr uint32_t mask = (uint32_t)nbins - 1u;
 
-	if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+	uint32_t key[kSortItems];
+	uint32_t val[kSortItems];
+	if constexpr (kEmit) {
+		// the emission staging area overlays the sort's shared memory; it is dead once the pairs are in registers
+		__syncthreads();
+		EmitSmem& em = *reinterpret_cast<EmitSmem*>(smem_raw);
+		const uint32_t o0 = s_tile * (uint32_t)kSortItemsPerBlock, o1 = min(n, o0 + (uint32_t)kSortItemsPerBlock);
+		emit_prepare(em, s_tile, o0, o1, es.emit_offset, es.order, es.rect, es.first_src);
+#pragma unroll
+		for (int k = 0; k < kSortItems; k++) {
+			const uint32_t idx = o0 + warp * (32 * kSortItems) + k * 32 + lane;
+			key[k] = 0xFFFFFFFFu;
+			val[k] = 0u;
+			if (idx < n) emit_slot(em, idx, o0, es.gx, key[k], val[k]);
+		}
+		__syncthreads();
+	}
 	for (int w = 0; w < kSortThreads / 32; w++)
 		for (int b = tid; b < nbins; b += kSortThreads) sm.warp_hist[w][b] = 0;
 	// global digit starts: exclusive scan of the pass histogram
@@ -155,18 +266,19 @@ __global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 	__syncthreads();
 	block_exclusive_scan_512(sm.global_base, nbins, sm.warp_tmp);
 
-	const uint32_t tile = sm.tile;
+	const uint32_t tile = s_tile;
 	const uint32_t tile_base = tile * (uint32_t)kSortItemsPerBlock;
 	const uint32_t tile_count = min((uint32_t)kSortItemsPerBlock, n - tile_base);
 
 	// ---- load (warp-striped); count digits and publish the tile's counts before the (slow) ranking ----
-	uint32_t key[kSortItems];
 	uint32_t rank[kSortItems];
 	const uint32_t warp_base = tile_base + warp * (32 * kSortItems);
+	if constexpr (!kEmit) {
 #pragma unroll
-	for (int k = 0; k < kSortItems; k++) {
-		uint32_t idx = warp_base + k * 32 + lane;
-		key[k] = (idx < n) ? keys_in[idx] : 0xFFFFFFFFu;
+		for (int k = 0; k < kSortItems; k++) {
+			uint32_t idx = warp_base + k * 32 + lane;
+			key[k] = (idx < n) ? keys_in[idx] : 0xFFFFFFFFu;
+		}
 	}
 #pragma unroll
 	for (int k = 0; k < kSortItems; k++) {
@@ -177,11 +289,12 @@ __global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 	for (int b = tid; b < nbins; b += kSortThreads)
 		st_release(&status[(size_t)tile * nbins + b], (tile == 0 ? kFlagInclusive : kFlagPartial) | sm.tile_hist[b]);
 	// values travel with the keys: issue their loads now, they are consumed after the look-back
-	uint32_t val[kSortItems];
+	if constexpr (!kEmit) {
 #pragma unroll
-	for (int k = 0; k < kSortItems; k++) {
-		uint32_t idx = warp_base + k * 32 + lane;
-		val[k] = (idx < n) ? (vals_in ? vals_in[idx] : idx) : 0u;
+		for (int k = 0; k < kSortItems; k++) {
+			uint32_t idx = warp_base + k * 32 + lane;
+			val[k] = (idx < n) ? (vals_in ? vals_in[idx] : idx) : 0u;
+		}
 	}
 #pragma unroll
 	for (int k = 0; k < kSortItems; k++) {
@@ -257,8 +370,6 @@ __global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 // out[i] = sum_{j<i} counts[order[j]] for i in [0, n]; out has n+1 entries.
 // Also fills first_src[b] = index i of the source that owns output slot min(b*kEmitPerBlock, R-1)
 // for b in [0, ceil(R/kEmitPerBlock)], so the emission needs no search (R = *total).
-constexpr int kEmitPerBlock = 2048;
-
 struct ScanSmem {
 	uint32_t warp_tmp[8];
 	uint32_t tile;
@@ -402,86 +513,26 @@ __global__ void __launch_bounds__(1024) tile_ranges_kernel(
 	for (int i = tid; i < kMaxTilePasses * kMaxBins; i += nthreads) tile_hist[i] = s_hist[i];
 }
 
-// ------------------------------------------------------------------ load-balanced emission
-// Output slot o in [0, R) belongs to the depth-ordered Gaussian i with emit_offset[i] <= o <
-// emit_offset[i+1]; inside a Gaussian, slots walk its tile rect row-major (the order of
-// duplicateWithKeys, rasterizer_impl.cu:127-138).  Each block produces kEmitPerBlock consecutive
-// slots, so work is even no matter how many tiles a single (e.g. polar) Gaussian covers, and all
-// stores are fully coalesced.
-constexpr int kEmitThreads = 256;
-constexpr int kEmitPerThread = kEmitPerBlock / kEmitThreads;
-
-__global__ void __launch_bounds__(kEmitThreads) emit_instances_kernel(
+// ------------------------------------------------------------------ load-balanced emission (stand-alone)
+// Materialises the unsorted (tile key, Gaussian id) list.  Each block produces kEmitPerBlock consecutive slots, so work
+// is even no matter how many tiles a single (e.g. polar) Gaussian covers, and all stores are fully coalesced.  The
+// frame path does not launch it any more (the first tile-sort pass emits on the fly, onesweep_pass_kernel<B, true>);
+// it remains for OGS_FUSED_EMIT=0 A/B measurements.
+__global__ void __launch_bounds__(kSortThreads) emit_instances_kernel(
 	const uint32_t* __restrict__ emit_offset /*P+1*/, const uint32_t* __restrict__ order /*P*/,
 	const uint2* __restrict__ rect, const uint32_t* __restrict__ first_src, uint32_t R, int gx,
 	uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ values)
 {
-	__shared__ uint32_t s_off[kEmitPerBlock + 2];
-	__shared__ uint32_t s_gid[kEmitPerBlock + 1];
-	__shared__ uint2 s_rect[kEmitPerBlock + 1];
-	__shared__ uint32_t s_src[kEmitPerBlock];      // slot -> local source index (after the max-scan)
-	__shared__ uint32_t s_warp_max[kEmitThreads / 32];
-	__shared__ uint32_t s_first, s_last;
-
+	__shared__ EmitSmem em;
 	const uint32_t o0 = blockIdx.x * (uint32_t)kEmitPerBlock;
 	if (o0 >= R) return;
 	const uint32_t o1 = min(R, o0 + (uint32_t)kEmitPerBlock);
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-	// sources owning the first and the last slot of this block (table written by gather_scan_kernel)
-	if (tid == 0) s_first = first_src[blockIdx.x];
-	if (tid == 1) s_last = first_src[blockIdx.x + 1];   // owner of slot min(o1, R-1): may start exactly at o1
-#pragma unroll
-	for (int k = 0; k < kEmitPerThread; k++) s_src[tid + k * kEmitThreads] = 0u;
-	__syncthreads();
-	const uint32_t first = s_first, last = s_last;
-	// every source in [first, last) owns >= 1 slot of this block (zero-count Gaussians sort to the end
-	// of the depth order), so ns <= kEmitPerBlock + 1 and the head marks below never collide
-	const uint32_t ns = last - first + 1;
-	for (uint32_t i = tid; i < ns; i += kEmitThreads) {
-		const uint32_t g = order[first + i];
-		const uint32_t off = emit_offset[first + i];
-		s_off[i] = off;
-		s_gid[i] = g;
-		s_rect[i] = rect[g];
-		if (i > 0 && off < o1) s_src[off - o0] = i;   // head of source i (source 0 starts at or before slot 0)
-	}
-	__syncthreads();
-
-	// inclusive max-scan of the head marks: slot -> source index
-	uint32_t v[kEmitPerThread];
-	uint32_t run = 0;
-#pragma unroll
-	for (int k = 0; k < kEmitPerThread; k++) {
-		run = max(run, s_src[tid * kEmitPerThread + k]);
-		v[k] = run;
-	}
-	uint32_t incl = run;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) {
-		const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-		if (lane >= o) incl = max(incl, u);
-	}
-	if (lane == 31) s_warp_max[warp] = incl;
-	const uint32_t prev_lane = __shfl_up_sync(0xffffffffu, incl, 1);
-	__syncthreads();
-	uint32_t carry = (lane > 0) ? prev_lane : 0u;
-	for (int w = 0; w < warp; w++) carry = max(carry, s_warp_max[w]);
-#pragma unroll
-	for (int k = 0; k < kEmitPerThread; k++) s_src[tid * kEmitPerThread + k] = max(v[k], carry);
-	__syncthreads();
-
-	for (uint32_t o = o0 + tid; o < o1; o += kEmitThreads) {
-		const uint32_t src = s_src[o - o0];
-		const uint2 rc = s_rect[src];
-		const uint32_t x0 = rc.x & 0xFFFFu, x1 = rc.x >> 16, y0 = rc.y & 0xFFFFu;
-		const uint32_t w = x1 - x0;
-		const uint32_t local = o - s_off[src];
-		const uint32_t q = local / w;
-		uint32_t x = x0 + (local - q * w);
-		if (x >= (uint32_t)gx) x -= (uint32_t)gx;   // only rects that wrap around the longitude seam (opt-in mode)
-		tile_keys[o] = (y0 + q) * (uint32_t)gx + x;
-		values[o] = s_gid[src];
+	emit_prepare(em, blockIdx.x, o0, o1, emit_offset, order, rect, first_src);
+	for (uint32_t o = o0 + threadIdx.x; o < o1; o += kSortThreads) {
+		uint32_t key, gid;
+		emit_slot(em, o, o0, gx, key, gid);
+		tile_keys[o] = key;
+		values[o] = gid;
 	}
 }
 
@@ -517,9 +568,11 @@ TileSortPlan make_tile_sort_plan(int W, int H)
 static cudaError_t ensure_onesweep_smem()
 {
 	// per device/context attribute, cheap host call: set on every use (several devices per process)
-	const int bytes = (int)sizeof(OnesweepSmem);
+	const int bytes = (int)kOnesweepSmemBytes;
 	cudaError_t e = cudaSuccess;
-#define OGS_SET(B) if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+#define OGS_SET(B)                                                                                                          \
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_kernel<B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_kernel<B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 	OGS_SET(1) OGS_SET(2) OGS_SET(3) OGS_SET(4) OGS_SET(5) OGS_SET(6) OGS_SET(7) OGS_SET(8) OGS_SET(9)
 #undef OGS_SET
 	return e;
@@ -541,9 +594,9 @@ int launch_depth_order(const GeomState& g, int P, cudaStream_t st)
 		const uint32_t* vin = p == 0 ? nullptr : g.sort_val[p & 1];
 		uint32_t* kout = g.sort_key[(p + 1) & 1];
 		uint32_t* vout = g.sort_val[(p + 1) & 1];
-		onesweep_pass_kernel<8><<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(
+		onesweep_pass_kernel<8><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(
 			kin, vin, kout, vout, n, 8 * p, g.depth_hist + 256 * p,
-			g.depth_status + (size_t)p * tiles * 256, tickets + p);
+			g.depth_status + (size_t)p * tiles * 256, tickets + p, EmitSource{});
 	}
 	// 4 passes: result back in buffer 0
 	OGS_CUDA_TRY(cudaGetLastError());
@@ -572,19 +625,25 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 	unsigned int* scan_ticket = reinterpret_cast<unsigned int*>(g.scalars + 2) + 4;
 	gather_scan_kernel<<<ceil_div(P, kSortItemsPerBlock), kSortThreads, 0, st>>>(
 		g.tiles_touched, g.sort_val[0], (uint32_t)P, g.emit_offset, g.scan_status, scan_ticket, b.first_src, g.scalars);
-	emit_instances_kernel<<<(unsigned)((R + kEmitPerBlock - 1) / kEmitPerBlock), kEmitThreads, 0, st>>>(
-		g.emit_offset, g.sort_val[0], g.rect, b.first_src, n, gx, b.key[0], b.val[0]);
+	// OGS_FUSED_EMIT=0 materialises the unsorted list first (A/B measurements); default: pass 0 emits on the fly
+	static const bool fused = [] { const char* e = getenv("OGS_FUSED_EMIT"); return e ? atoi(e) != 0 : true; }();
+	if (!fused)
+		emit_instances_kernel<<<(unsigned)((R + kEmitPerBlock - 1) / kEmitPerBlock), kSortThreads, 0, st>>>(
+			g.emit_offset, g.sort_val[0], g.rect, b.first_src, n, gx, b.key[0], b.val[0]);
 	prof_end(OGS_PROF_EMIT, st);
 	prof_begin(OGS_PROF_TILE_SORT, st);
 	const int tiles = (int)((R + kSortItemsPerBlock - 1) / kSortItemsPerBlock);
+	const EmitSource es{ g.emit_offset, g.sort_val[0], g.rect, b.first_src, gx };
 	size_t status_off = 0;
 	for (int p = 0; p < plan.passes; p++) {
 		const bool last = (p == plan.passes - 1);
+#define OGS_SORT_ARGS                                                                                          \
+	b.key[p & 1], b.val[p & 1], last ? nullptr : b.key[(p + 1) & 1], b.val[(p + 1) & 1], n, plan.shift[p],     \
+		img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p, es
 #define OGS_SORT_CASE(B)                                                                                      \
 	case B:                                                                                                   \
-		onesweep_pass_kernel<B><<<tiles, kSortThreads, sizeof(OnesweepSmem), st>>>(                           \
-			b.key[p & 1], b.val[p & 1], last ? nullptr : b.key[(p + 1) & 1], b.val[(p + 1) & 1], n,           \
-			plan.shift[p], img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p);               \
+		if (p == 0 && fused) onesweep_pass_kernel<B, true><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(OGS_SORT_ARGS); \
+		else onesweep_pass_kernel<B, false><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(OGS_SORT_ARGS);  \
 		break;
 		switch (plan.bits[p]) {
 			OGS_SORT_CASE(1) OGS_SORT_CASE(2) OGS_SORT_CASE(3) OGS_SORT_CASE(4) OGS_SORT_CASE(5)
@@ -592,6 +651,7 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 		default: return fail(OGS_ERR_INVALID_ARG, "bad radix digit width");
 		}
 #undef OGS_SORT_CASE
+#undef OGS_SORT_ARGS
 		status_off += (size_t)tiles << plan.bits[p];
 	}
 	prof_end(OGS_PROF_TILE_SORT, st);
