@@ -184,3 +184,27 @@ def test_training_iterations_match_reference_composition():
     assert torch.equal(pc.denom_, den)
     assert float((pc.max_radii2D_ - mr).abs().max()) <= 1.0
     assert float((pc.xyz_gradient_accum_ - acc).abs().max()) <= 1e-4 * float(acc.abs().max())
+
+
+def test_gradient_bucket_and_view_statistics_single_rank():
+    """parallel.GradientBucket: the backward writes the optimiser-facing gradients straight into the flat bucket, and
+    allreduce_bucket fills the per-view statistics slots with one kernel (sum / sum / max semantics over ranks)."""
+    par = importlib.import_module("omnigs-fork_b200.parallel")
+    scene = sm.make_scene(20011, 320, 160, 0.04, 51)     # P not a multiple of 4: every section still 16-byte aligned
+    d = h.torch_inputs(scene, sm.random_view(52))
+    dL = torch.from_numpy(sm.make_grad_image(scene.W, scene.H, 53)).cuda()
+    fwd = h.run_forward(h.pkg, d)
+    plain = h.run_backward(h.pkg, d, fwd, dL)
+    bucket = par.GradientBucket(scene.P, 16, "cuda")
+    assert bucket.peer is None                                    # single process: no peer memory involved
+    g = h.run_backward(h.pkg, d, fwd, dL, out=bucket)
+    for n, a, b in zip(h.GRAD_NAMES, g, plain):
+        if n in par.OPTIMISED:
+            assert a.data_ptr() == bucket[n].data_ptr(), n        # written in place, no copy
+        scale = float(b.abs().max()) + 1e-30
+        assert float((a - b).abs().max()) / scale < (3e-4 if n in ("dL_dcov3D", "dL_dscales", "dL_drotations") else 1e-5), n
+    grads, stats = par.allreduce_bucket(bucket, g[0], fwd[2])
+    vis = fwd[2] > 0
+    assert torch.equal(stats["denom"], vis.float()) and torch.equal(stats["max_radii2D"], fwd[2].float())
+    ref_norm = torch.where(vis, g[0][:, :2].norm(dim=-1), torch.zeros((), device="cuda"))
+    assert float((stats["xyz_gradient_accum"] - ref_norm).abs().max()) <= 1e-6 * float(ref_norm.max())
