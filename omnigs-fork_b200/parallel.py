@@ -118,9 +118,9 @@ class GradientBucket:
             return None
 
 
-def allreduce_bucket(bucket, dL_dmeans2D, radii, group=None):
-    """Fill the statistics slots of `bucket` from this rank's view and sum the whole bucket over ranks in one
-    collective.  Returns (dict of the five summed gradients, stats dict) like allreduce_gradients."""
+def fill_view_stats(bucket, dL_dmeans2D, radii):
+    """Write one view's densification-statistics increments into the bucket's slots (one kernel on the GPU):
+    ||dL_dmeans2D.xy|| and 1 where radii > 0, and the radius as float."""
     if bucket.flat.is_cuda:
         import ctypes
         from ._lib import load_library, check
@@ -134,9 +134,15 @@ def allreduce_bucket(bucket, dL_dmeans2D, radii, group=None):
         torch.where(vis, dL_dmeans2D[:, :2].norm(dim=-1), dL_dmeans2D.new_zeros(()), out=bucket["xyz_gradient_accum"])
         bucket["denom"].copy_(vis)
         bucket.max_radii2D.copy_(radii)
+
+
+def exchange_bucket(bucket, group=None):
+    """Sum the bucket (gradients + summed statistics) and take the maximum of the radii over ranks, in place.
+    One kernel over NVLink peer memory / the multicast address when the bucket lives in symmetric memory
+    (csrc/peer_collective.cu), NCCL / gloo all-reduce otherwise.  A no-op on a single rank."""
     if is_distributed() and bucket.peer is not None:
-        # reduce-scatter + all-gather in one kernel over peer memory (csrc/peer_collective.cu), bracketed by the
-        # symmetric-memory barrier on this stream: all buckets written before, all slices stored after
+        # reduce-scatter + all-gather in one kernel, bracketed by the symmetric-memory barrier on this stream:
+        # all buckets written before, all slices stored after
         import ctypes
         from ._lib import load_library, check
         pr = bucket.peer
@@ -157,6 +163,15 @@ def allreduce_bucket(bucket, dL_dmeans2D, radii, group=None):
         w2 = dist.all_reduce(bucket.max_radii2D, op=dist.ReduceOp.MAX, group=group, async_op=True)
         w1.wait()
         w2.wait()
+
+
+def allreduce_bucket(bucket, dL_dmeans2D, radii, group=None):
+    """One view per rank and step: fill the statistics slots of `bucket` from this rank's view and sum the whole
+    bucket over ranks in one collective.  Returns (dict of the five summed gradients, stats dict) like
+    allreduce_gradients.  (Several views per rank: fill_view_stats + local accumulation + exchange_bucket,
+    see tools/bench_dp_views.py.)"""
+    fill_view_stats(bucket, dL_dmeans2D, radii)
+    exchange_bucket(bucket, group)
     grads = {n: bucket[n] for n in OPTIMISED}
     stats = {"xyz_gradient_accum": bucket["xyz_gradient_accum"], "denom": bucket["denom"], "max_radii2D": bucket.max_radii2D}
     return grads, stats
