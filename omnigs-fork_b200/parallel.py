@@ -57,6 +57,7 @@ class GradientBucket:
         """peer: None = use NVLink peer memory when available (NCCL otherwise), False = always NCCL/gloo."""
         self.P, self.M = int(P), int(M)
         self.peer = None
+        self.peer_error = None
         sizes = [("dL_dmeans3D", (P, 3)), ("dL_dsh", (P, M, 3)), ("dL_dopacity", (P, 1)), ("dL_dscales", (P, 3)),
                  ("dL_drotations", (P, 4)), ("xyz_gradient_accum", (P,)), ("denom", (P,))]
         # every section starts 16-byte aligned (the SH rows go through 16-byte bulk copies)
@@ -113,8 +114,9 @@ class GradientBucket:
                     mc = 0
             self.peer = dict(handle=hdl, ptrs=ptrs, rank=dist.get_rank(), world=world, multicast=mc)
             return flat
-        except Exception:   # no symmetric memory on this build / topology
+        except Exception as e:   # no symmetric memory on this build / topology: remember why, use NCCL
             self.peer = None
+            self.peer_error = repr(e)
             return None
 
 

@@ -1,5 +1,7 @@
+"""25 timed forward+backward frames at C2 after 5 warm-up frames (ncu target for the frame kernels)."""
 import sys, os, time
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import _harness as h
 sm = h.scene_mod
