@@ -266,7 +266,8 @@ OGS_API int ogs_lonlat_backward_raw(
  * window, sigma 1.5, zero padding, mean over all elements), forward AND backward: writes
  * loss_out[3] = {loss, L1, SSIM} (device) and dL_dpix [3,H,W] = dloss/drendered.  mask is NULL, [1,H,W]
  * (mask_channels 1) or [3,H,W] (3).  rows_used < H drops the bottom rows from the loss as
- * skip_bottom_ratio does (gaussian_mapper.cpp:395-407); their dL_dpix is 0.  workspace: 8-byte aligned,
+ * skip_bottom_ratio does (gaussian_mapper.cpp:395-407); their dL_dpix is 0.  With lambda == 0 the SSIM term has no
+ * weight and is not evaluated (one streaming L1 pass; loss_out[2] = 0).  workspace: 8-byte aligned,
  * ogs_photometric_loss_workspace_bytes(W, H) bytes.
  *
  * ogs_adam_step: one launch of torch::optim::Adam::step over up to 8 parameter groups (the reference's

@@ -458,11 +458,18 @@ __global__ void __launch_bounds__(1024) tile_ranges_kernel(
 
 	for (int i = tid; i < kMaxTilePasses * kMaxBins; i += nthreads) s_hist[i] = 0;
 	// column prefix (down the rows)
+	// (eight independent loads in flight per thread: the chain is L2-latency bound, not the adds)
 	for (int x = tid; x < pitch; x += nthreads) {
 		int run = 0;
-		for (int y = 0; y <= gy; y++) {
-			run += tile_diff[y * pitch + x];
-			tile_diff[y * pitch + x] = run;
+		for (int y0 = 0; y0 <= gy; y0 += 8) {
+			int v[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++) v[k] = (y0 + k <= gy) ? __ldcg(&tile_diff[(y0 + k) * pitch + x]) : 0;
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				run += v[k];
+				if (y0 + k <= gy) tile_diff[(y0 + k) * pitch + x] = run;
+			}
 		}
 	}
 	__syncthreads();

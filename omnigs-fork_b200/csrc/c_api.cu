@@ -171,6 +171,10 @@ namespace {
 struct Readback {
 	unsigned long long* pinned = nullptr;
 	cudaEvent_t event = nullptr;
+	// tile_ranges (one CTA, latency bound) depends only on the per-Gaussian forward, like the depth order: it runs on
+	// this side stream beside the depth-order passes (fork / join with the two events)
+	cudaStream_t side = nullptr;
+	cudaEvent_t fork = nullptr, join = nullptr;
 };
 constexpr int kMaxDevices = 64;
 std::mutex g_rb_mutex;
@@ -186,6 +190,9 @@ int get_readback(Readback** out)
 		std::lock_guard<std::mutex> lock(g_rb_mutex);
 		OGS_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&rb.pinned), 64));
 		OGS_CUDA_TRY(cudaEventCreateWithFlags(&rb.event, cudaEventDisableTiming));
+		OGS_CUDA_TRY(cudaStreamCreateWithFlags(&rb.side, cudaStreamNonBlocking));
+		OGS_CUDA_TRY(cudaEventCreateWithFlags(&rb.fork, cudaEventDisableTiming));
+		OGS_CUDA_TRY(cudaEventCreateWithFlags(&rb.join, cudaEventDisableTiming));
 	}
 	*out = &rb;
 	return OGS_OK;
@@ -301,12 +308,27 @@ int forward_stage1_impl(
 	if (int rc = get_readback(&rb)) return rc;
 	OGS_CUDA_TRY(cudaMemcpyAsync(rb->pinned, g.scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	OGS_CUDA_TRY(cudaEventRecord(rb->event, st));
+	// OGS_SIDE_STREAM=0 keeps tile_ranges on the caller's stream behind the depth order (A/B knob)
+	static const bool side = [] { const char* e = getenv("OGS_SIDE_STREAM"); return e ? atoi(e) != 0 : true; }();
+	const cudaStream_t st_ranges = side ? rb->side : st;
+	if (side) {
+		OGS_CUDA_TRY(cudaEventRecord(rb->fork, st));
+		OGS_CUDA_TRY(cudaStreamWaitEvent(rb->side, rb->fork, 0));
+		prof_begin(OGS_PROF_TILE_RANGES, st_ranges);
+		if (int rc = launch_tile_ranges(img, W, H, st_ranges)) return rc;
+		prof_end(OGS_PROF_TILE_RANGES, st_ranges);
+		OGS_CUDA_TRY(cudaEventRecord(rb->join, rb->side));
+	}
 	prof_begin(OGS_PROF_DEPTH_ORDER, st);
 	if (int rc = launch_depth_order(g, P, st)) return rc;
 	prof_end(OGS_PROF_DEPTH_ORDER, st);
-	prof_begin(OGS_PROF_TILE_RANGES, st);
-	if (int rc = launch_tile_ranges(img, W, H, st)) return rc;
-	prof_end(OGS_PROF_TILE_RANGES, st);
+	if (side) {
+		OGS_CUDA_TRY(cudaStreamWaitEvent(st, rb->join, 0));
+	} else {
+		prof_begin(OGS_PROF_TILE_RANGES, st);
+		if (int rc = launch_tile_ranges(img, W, H, st)) return rc;
+		prof_end(OGS_PROF_TILE_RANGES, st);
+	}
 	OGS_CUDA_TRY(cudaEventSynchronize(rb->event));
 	const unsigned long long total = *rb->pinned;
 	if (total >= (1ull << 30)) {

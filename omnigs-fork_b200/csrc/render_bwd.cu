@@ -63,6 +63,13 @@ OGS_D void warp_transpose_reduce9(const float (&v)[8], float v8, float& z, float
 	for (int o = 16; o > 0; o >>= 1) z8 += __shfl_xor_sync(full, z8, o);
 }
 
+OGS_D float ex2_approx(float x)
+{
+	float r;
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 						// power >= the Gaussian's cut-off (eb.y) IS the forward's alpha >= 1/255 decision, so the gradient
 						// arithmetic itself is free to use ex2.approx (2 instructions instead of expf's 9): gradients are
 						// tolerance-bound, not bit-compared
-						G = __expf(power);
+						G = ex2_approx(power * 1.4426950408889634f);   // ex2.approx.ftz: no denormal rescaling (power >= cut-off > -6)
 						alpha = fminf(0.99f, __fmul_rn(eb.z, G));
 					}
 					if (valid) {

@@ -255,6 +255,48 @@ __global__ void __launch_bounds__(kLossThreads) ssim_l1_bwd_kernel(const LossArg
 	}
 }
 
+// lambda_dssim == 0: the SSIM term has no weight, so the loss is the L1 term alone — one streaming pass that writes
+// dL/dI = sign(I - gt) / count (times the mask) and adds up |I - gt| (a double per CTA into sums[0]).
+constexpr int kL1Threads = 256;
+__global__ void __launch_bounds__(kL1Threads) l1_only_kernel(const LossArgs a)
+{
+	__shared__ double s_red[kL1Threads / 32];
+	const size_t HW = (size_t)a.H * a.W, total = 3 * HW;
+	const float inv = (float)(1.0 / (3.0 * (double)a.W * (double)a.H_used));
+	double acc = 0.0;
+	for (size_t e = (size_t)blockIdx.x * kL1Threads + threadIdx.x; e < total; e += (size_t)gridDim.x * kL1Threads) {
+		const int ch = (int)(e / HW);
+		const size_t i = e - (size_t)ch * HW;
+		float grad = 0.f;
+		if (i < (size_t)a.H_used * a.W) {
+			float m = 1.f;
+			if (a.mask_channels == 1) m = a.mask[i];
+			else if (a.mask_channels == 3) m = a.mask[e];
+			const float diff = a.rendered[e] * m - a.gt[e];
+			acc += (double)fabsf(diff);
+			const float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
+			grad = sgn * inv * m;
+		}
+		a.dL_dpix[e] = grad;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double t = 0.0;
+		for (int w = 0; w < kL1Threads / 32; w++) t += s_red[w];
+		atomicAdd(&a.sums[0], t);
+	}
+}
+__global__ void l1_only_finish_kernel(const LossArgs a)
+{
+	const float l1 = (float)(a.sums[0] / (3.0 * (double)a.W * (double)a.H_used));
+	a.loss_out[0] = l1;
+	a.loss_out[1] = l1;
+	a.loss_out[2] = 0.f;   // SSIM is not evaluated when it has no weight
+}
+
 int launch_photometric_loss(int W, int H, int H_used, float lambda_dssim, const float* rendered, const float* gt,
                             const float* mask, int mask_channels, float* workspace, float* loss_out, float* dL_dpix,
                             cudaStream_t st)
@@ -274,6 +316,12 @@ int launch_photometric_loss(int W, int H, int H_used, float lambda_dssim, const 
 	a.dmaps = workspace + 4;   // behind the two 8-byte sums
 	a.loss_out = loss_out; a.dL_dpix = dL_dpix;
 	OGS_CUDA_TRY(cudaMemsetAsync(a.sums, 0, 2 * sizeof(double), st));
+	if (lambda_dssim == 0.f) {
+		l1_only_kernel<<<kNumSMs * 8, kL1Threads, 0, st>>>(a);
+		l1_only_finish_kernel<<<1, 1, 0, st>>>(a);
+		OGS_CUDA_TRY(cudaGetLastError());
+		return OGS_OK;
+	}
 	const dim3 grid(ceil_div(W, kLossTile), ceil_div(H, kLossTile), 3);
 	ssim_l1_fwd_kernel<<<grid, kLossThreads, 0, st>>>(a);
 	ssim_l1_bwd_kernel<<<grid, kLossThreads, 0, st>>>(a);

@@ -103,6 +103,17 @@ def test_photometric_loss_matches_libtorch_composition(W, H, mask_ch, rows):
     if rows is not None:
         assert float(dL[:, rows:].abs().max()) == 0.0
 
+    # lambda = 0: the L1-only pass (SSIM not evaluated)
+    loss_out0, dL0 = tr.photometric_loss(rendered, gt, 0.0, mask, rows)
+    x0 = rendered.clone().requires_grad_(True)
+    loss0, Ll10, _ = ref.photometric_loss(x0, gt, 0.0, mask, rows)
+    loss0.backward()
+    out0 = loss_out0.cpu().tolist()
+    assert abs(out0[0] - float(Ll10.detach())) <= 1e-6 * abs(float(Ll10.detach())) + 1e-7 and out0[1] == out0[0] and out0[2] == 0.0
+    assert float((dL0 - x0.grad).abs().max()) <= 1e-6 * float(x0.grad.abs().max())
+    if rows is not None:
+        assert float(dL0[:, rows:].abs().max()) == 0.0
+
 
 def test_adam_step_matches_torch_optim_adam():
     g = torch.Generator(device="cuda").manual_seed(1)

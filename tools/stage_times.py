@@ -17,4 +17,11 @@ acc = np.zeros(8); buf = (ctypes.c_float * 8)()
 for _ in range(10):
     f = h.run_forward(h.pkg, d); h.run_backward(h.pkg, d, f, dL); lib.ogs_profile_read(buf, 8); acc += np.array(list(buf))
 lib.ogs_profile_enable(0)
-print(cfg, "R", f[0], " ".join(f"{n}={v/10:.3f}" for n, v in zip(names, acc)), f"sum={acc.sum()/10:.3f}")
+# whole frames without the per-stage events (stages on the side stream overlap, so their sum is not the frame)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize(); e0.record()
+for _ in range(20):
+    f = h.run_forward(h.pkg, d); h.run_backward(h.pkg, d, f, dL)
+e1.record(); torch.cuda.synchronize()
+frame_ms = e0.elapsed_time(e1) / 20
+print(cfg, "R", f[0], " ".join(f"{n}={v/10:.3f}" for n, v in zip(names, acc)), f"sum={acc.sum()/10:.3f} frame={frame_ms:.3f}")
