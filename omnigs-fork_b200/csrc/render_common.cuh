@@ -95,6 +95,13 @@ struct __align__(16) StagedEntry {
 	float4 a, b, c;
 };
 
+OGS_D float4 lds_f4(uint32_t shared_addr)
+{
+	float4 r;
+	asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(shared_addr) : "memory");
+	return r;
+}
+
 // Stable block-wide compaction slot for `keep` flags (list order must be preserved: blending is
 // order dependent).  Returns this thread's slot (valid when keep) and the block total.
 // Uses one __syncthreads; s_warp_cnt must hold kRenderThreads/32 words.

@@ -47,14 +47,16 @@ __global__ void __launch_bounds__(kRenderThreads, 5) render_fwd_kernel(
 	const int rounds = (n + kBatch - 1) / kBatch;
 	const float wrap_W = (n > 0 && scalars[7] != 0ull) ? (float)W : 0.f;   // > 0: seam wrap-around mode of this frame
 
-	bool done = !inside;
+	// a pixel's own cut-off in `power`: -inf while it blends, +inf once it is finished (forward.cu:441-445) or outside
+	float lane_cut = inside ? -INFINITY : INFINITY;
+	const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_e);
 	float T = 1.0f;
 	uint32_t last_contributor = 0;
 	float C[3] = { 0.f, 0.f, 0.f };
 
 	for (int round = 0; round < rounds; round++) {
 		// all pixels of the tile saturated -> stop (forward.cu:399-401); also guards smem reuse
-		if (__syncthreads_count(done) == kRenderThreads) break;
+		if (__syncthreads_count(lane_cut > 0.f) == kRenderThreads) break;
 
 		// ---- gather one entry per thread, tile-level cull ----
 		const int i = round * kBatch + threadIdx.x;
@@ -90,26 +92,28 @@ __global__ void __launch_bounds__(kRenderThreads, 5) render_fwd_kernel(
 				hit = gaussian_touches_box(ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, sx0, sy0, sx1, sy1);
 			}
 			unsigned m = __ballot_sync(0xffffffffu, hit);
-			if (__all_sync(0xffffffffu, done)) break;
+			if (__all_sync(0xffffffffu, lane_cut > 0.f)) break;
 			while (m) {
-				const StagedEntry* e = &s_e[base + __ffs(m) - 1];
+				// one 32-bit shared address per entry (a generic pointer costs an S2R + LEA per iteration)
+				const uint32_t e = s_base + (uint32_t)(base + __ffs(m) - 1) * (uint32_t)sizeof(StagedEntry);
 				m &= m - 1;
-				if (done) continue;
-				const float4 ea = e->a;
-				const float4 eb = e->b;
+				const float4 ea = lds_f4(e);
+				const float4 eb = lds_f4(e + 16);
 				// forward.cu:424-455, arithmetic pinned to the reference's compiled order
 				float dx, dy;
 				const float power = pair_power(ea.x, ea.y, ea.z, ea.w, eb.x, pixf, dx, dy);
 				if (power > 0.0f) continue;
-				if (power < eb.y) continue; // below the Gaussian's alpha cut-off: alpha would be < 1/255 (skips expf)
+				// below the Gaussian's alpha cut-off alpha would be < 1/255 (skips expf); a finished pixel's cut-off is
+				// +inf, so it drops out here without a test of its own
+				if (power < fmaxf(eb.y, lane_cut)) continue;
 				const float alpha = fminf(0.99f, __fmul_rn(eb.z, expf(power)));
 				if (alpha < kAlphaMin) continue;
 				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-				if (test_T < 0.0001f) {
-					done = true;
+				if (test_T < 0.0001f) {   // finished (forward.cu:441-445); the asm keeps this one predicated move
+					asm volatile("mov.f32 %0, 0f7F800000;" : "=f"(lane_cut));
 					continue;
 				}
-				const float4 ec = e->c;
+				const float4 ec = lds_f4(e + 32);
 				C[0] = __fmaf_rn(T, __fmul_rn(alpha, ec.x), C[0]);
 				C[1] = __fmaf_rn(T, __fmul_rn(alpha, ec.y), C[1]);
 				C[2] = __fmaf_rn(T, __fmul_rn(alpha, ec.z), C[2]);
