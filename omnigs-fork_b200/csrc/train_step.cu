@@ -261,32 +261,52 @@ constexpr int kL1Threads = 256;
 __global__ void __launch_bounds__(kL1Threads) l1_only_kernel(const LossArgs a)
 {
 	__shared__ double s_red[kL1Threads / 32];
-	const size_t HW = (size_t)a.H * a.W, total = 3 * HW;
+	const size_t HW = (size_t)a.H * a.W, used = (size_t)a.H_used * a.W;
 	const float inv = (float)(1.0 / (3.0 * (double)a.W * (double)a.H_used));
-	double acc = 0.0;
-	for (size_t e = (size_t)blockIdx.x * kL1Threads + threadIdx.x; e < total; e += (size_t)gridDim.x * kL1Threads) {
-		const int ch = (int)(e / HW);
-		const size_t i = e - (size_t)ch * HW;
-		float grad = 0.f;
-		if (i < (size_t)a.H_used * a.W) {
-			float m = 1.f;
-			if (a.mask_channels == 1) m = a.mask[i];
-			else if (a.mask_channels == 3) m = a.mask[e];
-			const float diff = a.rendered[e] * m - a.gt[e];
-			acc += (double)fabsf(diff);
-			const float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
-			grad = sgn * inv * m;
+	// 128-bit accesses when the channel planes, the crop line and the four base pointers are 16-byte aligned
+	const bool vec = (HW % 4 == 0) && (used % 4 == 0) &&
+	                 ((reinterpret_cast<uintptr_t>(a.rendered) | reinterpret_cast<uintptr_t>(a.gt) |
+	                   reinterpret_cast<uintptr_t>(a.mask) | reinterpret_cast<uintptr_t>(a.dL_dpix)) % 16 == 0);
+	float acc = 0.f;   // per-thread partial (a few hundred terms); doubles from the warp reduction on
+	auto element = [&](float I, float g, float m, float& grad) {
+		const float diff = I * m - g;
+		acc += fabsf(diff);
+		grad = ((diff > 0.f) ? inv : ((diff < 0.f) ? -inv : 0.f)) * m;
+	};
+	for (int ch = 0; ch < 3; ch++) {
+		const float* I = a.rendered + ch * HW;
+		const float* G = a.gt + ch * HW;
+		const float* M = a.mask_channels == 0 ? nullptr : (a.mask_channels == 1 ? a.mask : a.mask + ch * HW);
+		float* D = a.dL_dpix + ch * HW;
+		const size_t stride = (size_t)gridDim.x * kL1Threads, first = (size_t)blockIdx.x * kL1Threads + threadIdx.x;
+		if (vec) {
+			for (size_t q = first; q < HW / 4; q += stride) {
+				float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (4 * q < used) {
+					const float4 x = reinterpret_cast<const float4*>(I)[q], g = reinterpret_cast<const float4*>(G)[q];
+					const float4 m = M ? reinterpret_cast<const float4*>(M)[q] : make_float4(1.f, 1.f, 1.f, 1.f);
+					element(x.x, g.x, m.x, d.x); element(x.y, g.y, m.y, d.y);
+					element(x.z, g.z, m.z, d.z); element(x.w, g.w, m.w, d.w);
+				}
+				reinterpret_cast<float4*>(D)[q] = d;
+			}
+		} else {
+			for (size_t i = first; i < HW; i += stride) {
+				float d = 0.f;
+				if (i < used) element(I[i], G[i], M ? M[i] : 1.f, d);
+				D[i] = d;
+			}
 		}
-		a.dL_dpix[e] = grad;
 	}
+	double t = (double)acc;
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+	for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		double t = 0.0;
-		for (int w = 0; w < kL1Threads / 32; w++) t += s_red[w];
-		atomicAdd(&a.sums[0], t);
+		double sum = 0.0;
+		for (int w = 0; w < kL1Threads / 32; w++) sum += s_red[w];
+		atomicAdd(&a.sums[0], sum);
 	}
 }
 __global__ void l1_only_finish_kernel(const LossArgs a)
