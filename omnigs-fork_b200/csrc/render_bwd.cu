@@ -80,6 +80,9 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 	const float* __restrict__ dL_dpixels, float* __restrict__ grad_acc /*[P,12]*/)
 {
 	__shared__ StagedEntry s_e[kBwdBatch];
+	// per (slot, thread): dL/dpixel (r, g, b) and -T_final * (bg . dL/dpixel) — read once per contributing pair with one
+	// conflict-free 128-bit load instead of living in 16 registers
+	__shared__ float4 s_pix[kBwdSlots][kBwdThreads];
 	__shared__ int s_warp_cnt[kBwdThreads / 32];
 	__shared__ int s_max_contrib;
 
@@ -94,14 +97,16 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 	const int half_x0 = tile_x * kTile, half_y0 = tile_y * kTile + 8 * warp;
 
 	const uint2 range = ranges[tile];
+	uint32_t pix_addr = (uint32_t)__cvta_generic_to_shared(&s_pix[0][tid]);
+	asm volatile("" : "+r"(pix_addr));   // opaque: one register for the whole kernel instead of S2R + LEA per use
 
 	// per-pixel state (backward.cu:717-740), one set per slot
 	// accum_rec holds the colour accumulated behind the NEXT Gaussian to be visited: the reference's
 	// update accum_rec = last_alpha*last_color + (1-last_alpha)*accum_rec (backward.cu:797) is applied
 	// right after a Gaussian is processed instead of right before the next one (same expression, same
 	// values, no last_alpha / last_color registers).
-	float T[kBwdSlots], neg_Tfinal_bg[kBwdSlots];
-	float accum_rec[kBwdSlots][3], dL_dpixel[kBwdSlots][3];
+	float T[kBwdSlots];
+	float accum_rec[kBwdSlots][3];
 	int last_contributor[kBwdSlots];
 	const float px0f = (float)(half_x0 + (lane & (kSubW - 1))), py0f = (float)(half_y0 + (lane / kSubW));
 	const float bg[3] = { bg_color[0], bg_color[1], bg_color[2] };
@@ -116,14 +121,15 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 		T[s] = T_final;
 		last_contributor[s] = inside ? (int)n_contrib[pix_id] : 0;   // 0 => no list position passes the test
 		my_max = max(my_max, last_contributor[s]);
-		float bg_dot = 0.f;
+		float bg_dot = 0.f, dLp[3];
 #pragma unroll
 		for (int ch = 0; ch < 3; ch++) {
 			accum_rec[s][ch] = 0.f;
-			dL_dpixel[s][ch] = inside ? dL_dpixels[ch * HW + pix_id] : 0.f;
-			bg_dot += bg[ch] * dL_dpixel[s][ch];
+			dLp[ch] = inside ? dL_dpixels[ch * HW + pix_id] : 0.f;
+			bg_dot += bg[ch] * dLp[ch];
 		}
-		neg_Tfinal_bg[s] = -T_final * bg_dot;   // (-T_final / (1 - alpha)) * bg_dot = this * 1/(1 - alpha)
+		// (-T_final / (1 - alpha)) * bg_dot = .w * 1/(1 - alpha)
+		s_pix[s][tid] = make_float4(dLp[0], dLp[1], dLp[2], -T_final * bg_dot);
 	}
 
 	// entries at list positions >= max(n_contrib) of the tile were blended by no pixel
@@ -236,6 +242,8 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 						any_valid = true;
 						// backward.cu:784-840; one reciprocal (rcp.approx, 1 ulp; 1 - alpha >= 0.01) replaces the two
 						// divisions by (1 - alpha)
+						const float4 pix = lds_f4(pix_addr + (uint32_t)(s * kBwdThreads * sizeof(float4)));
+						const float dL_dpixel[3] = { pix.x, pix.y, pix.z };
 						const float inv = rcp_approx(1.f - alpha);
 						T[s] = T[s] * inv;
 						const float dchannel_dcolor = alpha * T[s];
@@ -243,14 +251,14 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 						const float col[3] = { ec.x, ec.y, ec.z };
 #pragma unroll
 						for (int ch = 0; ch < 3; ch++) {
-							dL_dalpha += (col[ch] - accum_rec[s][ch]) * dL_dpixel[s][ch];
+							dL_dalpha += (col[ch] - accum_rec[s][ch]) * dL_dpixel[ch];
 							accum_rec[s][ch] = alpha * col[ch] + (1.f - alpha) * accum_rec[s][ch];
 						}
-						r[6] += dchannel_dcolor * dL_dpixel[s][0];
-						r[7] += dchannel_dcolor * dL_dpixel[s][1];
-						r8 += dchannel_dcolor * dL_dpixel[s][2];
+						r[6] += dchannel_dcolor * dL_dpixel[0];
+						r[7] += dchannel_dcolor * dL_dpixel[1];
+						r8 += dchannel_dcolor * dL_dpixel[2];
 						dL_dalpha *= T[s];
-						dL_dalpha += neg_Tfinal_bg[s] * inv;
+						dL_dalpha += pix.w * inv;
 
 						const float u = (eb.z * dL_dalpha) * G;   // dL/dG * G
 						const float udx = u * dx, udy = u * dy;
