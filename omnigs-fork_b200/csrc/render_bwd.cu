@@ -33,10 +33,9 @@ constexpr int kBwdPerThread = kBwdBatch / kBwdThreads;
 
 // Sum v[0..7] and v8 over the 32 lanes.  On return lane L holds in `z` the total of value (L>>2)
 // (replicated over the 4 lanes of a quad) and every lane holds the total of v8 in `z8`.
-OGS_D void warp_transpose_reduce9(const float (&v)[8], float v8, float& z, float& z8)
+OGS_D void warp_transpose_reduce9(const float (&v)[8], float v8, int lane, float& z, float& z8)
 {
 	const unsigned full = 0xffffffffu;
-	const int lane = threadIdx.x & 31;
 	const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
 	float w[4], u[2];
 #pragma unroll
@@ -97,6 +96,13 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 	const int half_x0 = tile_x * kTile, half_y0 = tile_y * kTile + 8 * warp;
 
 	const uint2 range = ranges[tile];
+	// this lane's element of a Gaussian's accumulator row (see the reduction at the end of a visit); opaque so that the
+	// pointer stays in registers instead of being rebuilt from %tid for every visit
+	const bool ninth = (lane == 1), red_lane = (lane & 3) == 0 || ninth;
+	float* lane_acc = grad_acc + (ninth ? 8 : (lane >> 2));
+	asm volatile("" : "+l"(lane_acc));
+	int lane_bits = lane;   // same for the butterfly's lane-bit selects
+	asm volatile("" : "+r"(lane_bits));
 	uint32_t pix_addr = (uint32_t)__cvta_generic_to_shared(&s_pix[0][tid]);
 	asm volatile("" : "+r"(pix_addr));   // opaque: one register for the whole kernel instead of S2R + LEA per use
 
@@ -109,6 +115,10 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 	float accum_rec[kBwdSlots][3];
 	int last_contributor[kBwdSlots];
 	const float px0f = (float)(half_x0 + (lane & (kSubW - 1))), py0f = (float)(half_y0 + (lane / kSubW));
+	// the second column / row of sub-blocks (exact integers); opaque so that they stay in two registers instead of being
+	// re-added for every slot of every visit
+	float px1f = px0f + (float)kSubW, py1f = py0f + (float)kSubH;
+	asm volatile("" : "+f"(px1f), "+f"(py1f));
 	const float bg[3] = { bg_color[0], bg_color[1], bg_color[2] };
 	int my_max = 0;
 #pragma unroll
@@ -221,13 +231,13 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 
 				float r[8] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
 				float r8 = 0.f;
-				bool any_valid = false;
+				int any_valid = 0;
 #pragma unroll
 				for (int s = 0; s < kBwdSlots; s++) {
 					if (!((m[s] >> bit) & 1u)) continue;   // warp-uniform
 					// backward.cu:766-782: same guards (and the same pinned arithmetic) as the forward
 					float dx, dy;
-					const float2 pixf = { px0f + (float)(kSubW * (s & 1)), py0f + (float)(kSubH * (s >> 1)) };   // exact
+					const float2 pixf = { (s & 1) ? px1f : px0f, (s >> 1) ? py1f : py0f };
 					const float power = pair_power(ea.x, ea.y, ea.z, ea.w, eb.x, pixf, dx, dy);
 					bool valid = (list_pos < last_contributor[s]) && !(power > 0.0f) && !(power < eb.y);
 					float G = 0.f, alpha = 0.f;
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 						alpha = fminf(0.99f, __fmul_rn(eb.z, G));
 					}
 					if (valid) {
-						any_valid = true;
+						any_valid = 1;
 						// backward.cu:784-840; one reciprocal (rcp.approx, 1 ulp; 1 - alpha >= 0.01) replaces the two
 						// divisions by (1 - alpha)
 						const float4 pix = lds_f4(pix_addr + (uint32_t)(s * kBwdThreads * sizeof(float4)));
@@ -251,8 +261,11 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 						const float col[3] = { ec.x, ec.y, ec.z };
 #pragma unroll
 						for (int ch = 0; ch < 3; ch++) {
-							dL_dalpha += (col[ch] - accum_rec[s][ch]) * dL_dpixel[ch];
-							accum_rec[s][ch] = alpha * col[ch] + (1.f - alpha) * accum_rec[s][ch];
+							// accum_rec' = alpha c + (1 - alpha) accum_rec (backward.cu:797) = accum_rec + alpha (c - accum_rec):
+							// the difference is needed anyway, so the update is one FMA
+							const float d = col[ch] - accum_rec[s][ch];
+							dL_dalpha = fmaf(d, dL_dpixel[ch], dL_dalpha);
+							accum_rec[s][ch] = fmaf(alpha, d, accum_rec[s][ch]);
 						}
 						r[6] += dchannel_dcolor * dL_dpixel[0];
 						r[7] += dchannel_dcolor * dL_dpixel[1];
@@ -270,13 +283,12 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 						r[5] += G * dL_dalpha;
 					}
 				}
-				if (!__any_sync(0xffffffffu, any_valid)) continue;
+				if (!__any_sync(0xffffffffu, any_valid != 0)) continue;
 				float z, z8;
-				warp_transpose_reduce9(r, r8, z, z8);
+				warp_transpose_reduce9(r, r8, lane_bits, z, z8);
 				// lanes 0,4,..,28 hold sums 0..7, lane 1 takes the ninth: one 9-lane L2 reduction
-				const bool ninth = (lane == 1);
-				if ((lane & 3) == 0 || ninth)
-					red_add(grad_acc + (size_t)__float_as_uint(ec.w) * 12 + (ninth ? 8 : (lane >> 2)), ninth ? z8 : z);
+				if (red_lane)
+					red_add(lane_acc + (size_t)__float_as_uint(ec.w) * 12, (lane_bits == 1) ? z8 : z);
 			}
 		}
 	}
