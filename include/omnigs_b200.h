@@ -40,7 +40,9 @@
  *     rotations are (w,x,y,z) and are NOT normalised by the kernels (forward.cu:203);
  *   - the three byte buffers are opaque: their layout is private to this library (it is NOT the
  *     reference's layout) and only has to survive from forward to backward of the same frame;
- *   - `stream` is a cudaStream_t (NULL = legacy default stream);
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream).  All work is ordered on it: stage 1 forks one small
+ *     kernel (the tile ranges) onto a library-owned non-blocking stream beside the depth-order passes and joins it
+ *     back with events before returning, so the caller sees ordinary stream semantics (OGS_SIDE_STREAM=0 disables it);
  *   - all calls return 0 on success or a negative OGS_ERR_* code; ogs_last_error() gives text.
  *     Like the reference, kernels are launched asynchronously; only stage 1 blocks (for the
  *     num_rendered read-back, as the reference does at rasterizer_impl.cu:627-628).

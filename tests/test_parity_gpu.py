@@ -511,3 +511,32 @@ def test_band_gradients_sum_to_full_frame_gradients():
     g_sum = h.run_backward(h.pkg, d, fwds[-1], dL, reduce_accumulators=add_others)
     for n, a, b in zip(h.GRAD_NAMES, g_sum, g_full):
         assert_own_runs_close(n, a, b, 2e-5)
+
+
+def test_caller_streams_and_side_stream_ordering():
+    """The library forks tile_ranges onto its own side stream and joins it back (csrc/c_api.cu): frames issued back
+    to back on the caller's current stream — default or not, alternating, with no host synchronisation in between —
+    must give the same bits as a lone frame."""
+    scene = sm.make_scene(60000, 640, 320, 0.02, 41)
+    d = h.torch_inputs(scene, sm.random_view(42))
+    dL = torch.from_numpy(sm.make_grad_image(scene.W, scene.H, 43)).cuda()
+    base_f = h.run_forward(h.pkg, d)
+    base_g = h.run_backward(h.pkg, d, base_f, dL)
+    base_s = h.ours_state(d, base_f)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    runs = []
+    for i in range(6):
+        st = streams[i % 2]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            f = h.run_forward(h.pkg, d)
+            g = h.run_backward(h.pkg, d, f, dL)
+            runs.append((f, g, h.ours_state(d, f)))
+    torch.cuda.synchronize()
+    for f, g, s in runs:
+        assert f[0] == base_f[0]
+        assert torch.equal(f[1], base_f[1]) and torch.equal(f[2], base_f[2])
+        for k in ("ranges", "point_list", "n_contrib"):
+            assert np.array_equal(_np(s[k]), _np(base_s[k])), k
+        assert_grads_close(g, base_g)
