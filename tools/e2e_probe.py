@@ -21,6 +21,28 @@ vbuf = torch.empty(19, device="cuda")
 copy_stream, gt_ready = torch.cuda.Stream(), torch.cuda.Event()
 loss_host, loss_ready = torch.empty(3).pin_memory(), torch.cuda.Event()
 
+gt_bufs = [gt_dev, torch.empty_like(gt_dev)]
+gt_events = [torch.cuda.Event(), torch.cuda.Event()]
+loss_done = torch.cuda.Event()
+
+def step_prefetch(s):
+    """Target image of step s+1 copied while step s runs (double-buffered), pose copy, L1 pass, deferred loss read."""
+    cur, nxt = s & 1, (s + 1) & 1
+    vbuf.copy_(view_host[s], non_blocking=True)
+    d["viewmatrix"], d["campos"] = vbuf[:16].view(4, 4), vbuf[16:19]
+    d["projmatrix"] = d["viewmatrix"]
+    fwd = h.run_forward(h.pkg, d)
+    torch.cuda.current_stream().wait_event(gt_events[cur])
+    loss_out, g_in = tr.photometric_loss(fwd[1], gt_bufs[cur], 0.0)
+    loss_done.record()
+    # the other buffer was last read by the previous step's loss, which is behind us on this stream
+    copy_stream.wait_event(loss_done)
+    with torch.cuda.stream(copy_stream):
+        gt_bufs[nxt].copy_(gt_host, non_blocking=True); gt_events[nxt].record()
+    h.run_backward(h.pkg, d, fwd, g_in)
+    loss_ready.synchronize(); _ = float(loss_host[0])
+    loss_host.copy_(loss_out, non_blocking=True); loss_ready.record()
+
 def step(s, pose_copy, gt_copy, loss, readback):
     if pose_copy:
         vbuf.copy_(view_host[s], non_blocking=True)
@@ -57,3 +79,10 @@ for name, args in [("frame only", (False, False, False, None)), ("+ pose H2D", (
     for s in range(5, 55): step(s, *args)
     e1.record(); torch.cuda.synchronize()
     print(f"{name:32s} {e0.elapsed_time(e1) / 50:.3f} ms/step")
+gt_events[0].record(); gt_events[1].record(); loss_ready.record()
+for s in range(5): step_prefetch(s)
+torch.cuda.synchronize()
+e0.record()
+for s in range(5, 55): step_prefetch(s)
+e1.record(); torch.cuda.synchronize()
+print(f"{'prefetched target (under bwd)':32s} {e0.elapsed_time(e1) / 50:.3f} ms/step")
