@@ -333,19 +333,19 @@ __global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 	}
 	__syncthreads();
 
-	// ---- decoupled look-back (one thread per digit, batched status loads) ----
-	for (int b = tid; b < nbins; b += kSortThreads) {
-		if (tile != 0) {
-			const uint32_t excl = lookback_sum(status, (int)tile, (size_t)nbins, (size_t)b);
-			st_release(&status[(size_t)tile * nbins + b], kFlagInclusive | (excl + sm.bin_start[b]));
-			sm.global_base[b] += excl; // digit start + keys of this digit in earlier tiles
-		}
+	// this thread's digit totals (needed for the inclusive status after bin_start has become the local starts)
+	constexpr int kDigitsPerThread = (nbins + kSortThreads - 1) / kSortThreads;
+	uint32_t digit_total[kDigitsPerThread];
+#pragma unroll
+	for (int q = 0; q < kDigitsPerThread; q++) {
+		const int b = tid + q * kSortThreads;
+		digit_total[q] = (b < nbins) ? sm.bin_start[b] : 0u;
 	}
 	__syncthreads();
 	block_exclusive_scan_512(sm.bin_start, nbins, sm.warp_tmp); // totals -> tile-local starts
-	for (int b = tid; b < nbins; b += kSortThreads) sm.global_base[b] -= sm.bin_start[b];
 
-	// ---- stage into digit order, then coalesced scatter ----
+	// ---- stage into digit order: needs nothing from other tiles, so it runs BEFORE the look-back — the predecessors'
+	// status words have that much longer to arrive and the threads without a digit wait that much less ----
 #pragma unroll
 	for (int k = 0; k < kSortItems; k++) {
 		uint32_t idx = warp_base + k * 32 + lane;
@@ -354,6 +354,21 @@ __global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 			uint32_t pos = sm.bin_start[d] + sm.warp_hist[warp][d] + rank[k];
 			sm.keys[pos] = key[k];
 			sm.vals[pos] = val[k];
+		}
+	}
+
+	// ---- decoupled look-back (one thread per digit, batched status loads) ----
+#pragma unroll
+	for (int q = 0; q < kDigitsPerThread; q++) {
+		const int b = tid + q * kSortThreads;
+		if (b < nbins) {
+			uint32_t excl = 0;
+			if (tile != 0) {
+				excl = lookback_sum(status, (int)tile, (size_t)nbins, (size_t)b);
+				st_release(&status[(size_t)tile * nbins + b], kFlagInclusive | (excl + digit_total[q]));
+			}
+			// digit start + keys of this digit in earlier tiles - tile-local start: slot j of the staged tile goes to base + j
+			sm.global_base[b] += excl - sm.bin_start[b];
 		}
 	}
 	__syncthreads();
