@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 	uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
 	uint32_t n, int shift,
 	const uint32_t* __restrict__ digit_counts, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket,
-	const EmitSource es)
+	const EmitSource es, const bool counts_are_starts)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
@@ -258,13 +258,13 @@ __global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
 	}
 	for (int w = 0; w < kSortThreads / 32; w++)
 		for (int b = tid; b < nbins; b += kSortThreads) sm.warp_hist[w][b] = 0;
-	// global digit starts: exclusive scan of the pass histogram
+	// global digit starts: the exclusive scan of the pass histogram (already scanned when counts_are_starts)
 	for (int b = tid; b < nbins; b += kSortThreads) {
 		sm.global_base[b] = digit_counts[b];
 		sm.tile_hist[b] = 0;
 	}
 	__syncthreads();
-	block_exclusive_scan_512(sm.global_base, nbins, sm.warp_tmp);
+	if (!counts_are_starts) block_exclusive_scan_512(sm.global_base, nbins, sm.warp_tmp);
 
 	const uint32_t tile = s_tile;
 	const uint32_t tile_base = tile * (uint32_t)kSortItemsPerBlock;
@@ -532,7 +532,30 @@ __global__ void __launch_bounds__(1024) tile_ranges_kernel(
 		run += c;
 	}
 	__syncthreads();
-	for (int i = tid; i < kMaxTilePasses * kMaxBins; i += nthreads) tile_hist[i] = s_hist[i];
+	// the sort passes want digit STARTS (exclusive prefix of the counts): one warp per pass scans its kMaxBins counts
+	// here once instead of every one of the passes' thousands of CTAs doing it
+	if (warp < kMaxTilePasses) {
+		constexpr int kPerLane = kMaxBins / 32;
+		uint32_t* hp = s_hist + warp * kMaxBins;
+		uint32_t v[kPerLane], sum = 0;
+#pragma unroll
+		for (int k = 0; k < kPerLane; k++) {
+			v[k] = hp[lane * kPerLane + k];
+			sum += v[k];
+		}
+		uint32_t incl = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += u;
+		}
+		uint32_t run = incl - sum;
+#pragma unroll
+		for (int k = 0; k < kPerLane; k++) {
+			tile_hist[warp * kMaxBins + lane * kPerLane + k] = run;
+			run += v[k];
+		}
+	}
 }
 
 // ------------------------------------------------------------------ load-balanced emission (stand-alone)
@@ -618,7 +641,7 @@ int launch_depth_order(const GeomState& g, int P, cudaStream_t st)
 		uint32_t* vout = g.sort_val[(p + 1) & 1];
 		onesweep_pass_kernel<8><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(
 			kin, vin, kout, vout, n, 8 * p, g.depth_hist + 256 * p,
-			g.depth_status + (size_t)p * tiles * 256, tickets + p, EmitSource{});
+			g.depth_status + (size_t)p * tiles * 256, tickets + p, EmitSource{}, false);
 	}
 	// 4 passes: result back in buffer 0
 	OGS_CUDA_TRY(cudaGetLastError());
@@ -661,7 +684,7 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 		const bool last = (p == plan.passes - 1);
 #define OGS_SORT_ARGS                                                                                          \
 	b.key[p & 1], b.val[p & 1], last ? nullptr : b.key[(p + 1) & 1], b.val[(p + 1) & 1], n, plan.shift[p],     \
-		img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p, es
+		img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p, es, true
 #define OGS_SORT_CASE(B)                                                                                      \
 	case B:                                                                                                   \
 		if (p == 0 && fused) onesweep_pass_kernel<B, true><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(OGS_SORT_ARGS); \

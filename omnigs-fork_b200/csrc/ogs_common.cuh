@@ -81,7 +81,7 @@ struct ImageState {              // per pixel / per tile
 	uint2* ranges;               // T
 	int* tile_diff;              // (gy+1)*(gx+1) 2-D difference array of tile coverage counts
 	uint32_t* tile_count;        // T
-	uint32_t* tile_hist;         // kMaxTilePasses x kMaxBins digit counts for the tile sort
+	uint32_t* tile_hist;         // kMaxTilePasses x kMaxBins digit STARTS (exclusive prefix of the counts) for the tile sort
 	static size_t bytes(int W, int H);
 	static ImageState carve(char* base, int W, int H);
 };
