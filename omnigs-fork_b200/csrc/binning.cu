@@ -206,8 +206,13 @@ OGS_D void emit_slot(const EmitSmem& em, uint32_t o, uint32_t o0, int gx, uint32
 	const uint32_t x0 = rc.x & 0xFFFFu, x1 = rc.x >> 16, y0 = rc.y & 0xFFFFu;
 	const uint32_t w = x1 - x0;
 	const uint32_t local = o - em.off[src];
-	const uint32_t q = local / w;
-	uint32_t x = x0 + (local - q * w);
+	// q = local / w without the ~35-instruction integer division: local < 2^30 and q < 2^16, so the float quotient is
+	// off by at most one and a two-sided correction makes it exact
+	uint32_t q = __float2uint_rz(__uint2float_rz(local) * rcp_approx(__uint2float_rz(w)));
+	int rem = (int)(local - q * w);
+	if (rem < 0) { q--; rem += (int)w; }
+	else if (rem >= (int)w) { q++; rem -= (int)w; }
+	uint32_t x = x0 + (uint32_t)rem;
 	if (x >= (uint32_t)gx) x -= (uint32_t)gx;   // only rects that wrap around the longitude seam (opt-in mode)
 	tile_key = (y0 + q) * (uint32_t)gx + x;
 	gid = em.gid[src];
