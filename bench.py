@@ -196,6 +196,9 @@ def main():
     distributed = world > 1 and args.impl == "ours"
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries the one JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     scene = sm.make_config_scene(WORKLOAD)
