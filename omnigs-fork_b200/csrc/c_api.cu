@@ -187,12 +187,23 @@ int get_readback(Readback** out)
 	if (dev < 0 || dev >= kMaxDevices) return fail(OGS_ERR_NO_DEVICE, "device ordinal out of range");
 	Readback& rb = g_rb[dev];
 	if (!rb.pinned) {
+		// all-or-nothing: a slot is published only when every resource exists (a failed call is retried from scratch)
 		std::lock_guard<std::mutex> lock(g_rb_mutex);
-		OGS_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&rb.pinned), 64));
-		OGS_CUDA_TRY(cudaEventCreateWithFlags(&rb.event, cudaEventDisableTiming));
-		OGS_CUDA_TRY(cudaStreamCreateWithFlags(&rb.side, cudaStreamNonBlocking));
-		OGS_CUDA_TRY(cudaEventCreateWithFlags(&rb.fork, cudaEventDisableTiming));
-		OGS_CUDA_TRY(cudaEventCreateWithFlags(&rb.join, cudaEventDisableTiming));
+		Readback fresh;
+		cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&fresh.pinned), 64);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fresh.event, cudaEventDisableTiming);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&fresh.side, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fresh.fork, cudaEventDisableTiming);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fresh.join, cudaEventDisableTiming);
+		if (e != cudaSuccess) {
+			if (fresh.join) cudaEventDestroy(fresh.join);
+			if (fresh.fork) cudaEventDestroy(fresh.fork);
+			if (fresh.side) cudaStreamDestroy(fresh.side);
+			if (fresh.event) cudaEventDestroy(fresh.event);
+			if (fresh.pinned) cudaFreeHost(fresh.pinned);
+			return fail_cuda(e);
+		}
+		rb = fresh;
 	}
 	*out = &rb;
 	return OGS_OK;

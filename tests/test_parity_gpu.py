@@ -540,3 +540,21 @@ def test_caller_streams_and_side_stream_ordering():
         for k in ("ranges", "point_list", "n_contrib"):
             assert np.array_equal(_np(s[k]), _np(base_s[k])), k
         assert_grads_close(g, base_g)
+
+
+def test_more_than_2_30_tile_instances_are_rejected():
+    """Maximum size: the tile sort carries 30-bit counts in its status words, so a frame with num_rendered >= 2^30 is
+    refused in stage 1 (OGS_ERR_TOO_MANY) before any R-sized buffer is asked for — the reference overflows its int
+    num_rendered at 2^31 instead (rasterizer_impl.cu:627-632).  32768 + 8 Gaussians that each cover all 32768 tiles of a
+    4096x2048 frame."""
+    P = 32768 + 8
+    scene = sm.make_scene(P, 4096, 2048, 0.02, 11)
+    scene.means3D[:] = (0.01, -3.0, 0.02)
+    scene.scales[:] = (4.0, 4.0, 4.0)
+    d = h.torch_inputs(scene, sm.identity_view())
+    with pytest.raises(h.pkg.OgsError, match="2\\^30"):
+        h.run_forward(h.pkg, d)
+    # the library stays usable afterwards
+    small = sm.make_scene(2000, 160, 80, 0.03, 12)
+    fwd = h.run_forward(h.pkg, h.torch_inputs(small, sm.identity_view()))
+    assert fwd[0] > 0 and bool(torch.isfinite(fwd[1]).all())
