@@ -17,8 +17,12 @@
 
 namespace ogs {
 
-// 5 resident CTAs per SM (48 registers) measured best of 3..8 (0.558 ms at C2; 4: 0.598, 6: 0.562, 8: 0.577)
-__global__ void __launch_bounds__(kRenderThreads, 5) render_fwd_kernel(
+// resident CTAs per SM: with the 52-instruction blend loop 6 (40 registers) measures best at C2 (4: 0.547, 5: 0.504,
+// 6: 0.495 ms); with the earlier 60-instruction loop it was 5 (4: 0.598, 5: 0.558, 6: 0.562, 8: 0.577)
+#ifndef OGS_FWD_MINBLOCKS
+#define OGS_FWD_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float2* __restrict__ gb,
 	const unsigned long long* __restrict__ scalars, const float* __restrict__ bg_color,
