@@ -229,7 +229,10 @@ struct EmitSource {
 };
 
 template <int BITS, bool kEmit = false>
-__global__ void __launch_bounds__(kSortThreads, 5) onesweep_pass_kernel(
+#ifndef OGS_SORT_MINBLOCKS
+#define OGS_SORT_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(kSortThreads, OGS_SORT_MINBLOCKS) onesweep_pass_kernel(
 	const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
 	uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
 	uint32_t n, int shift,

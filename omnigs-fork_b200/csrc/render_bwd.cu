@@ -28,7 +28,10 @@ namespace ogs {
 
 constexpr int kBwdThreads = 64;                 // two warps per tile
 constexpr int kBwdSlots = 4;                    // pixels per lane (one per 8x4 sub-block)
-constexpr int kBwdBatch = 128;                  // list entries staged per round
+#ifndef OGS_BWD_BATCH
+#define OGS_BWD_BATCH 128
+#endif
+constexpr int kBwdBatch = OGS_BWD_BATCH;        // list entries staged per round
 constexpr int kBwdPerThread = kBwdBatch / kBwdThreads;
 
 // Sum v[0..7] and v8 over the 32 lanes.  On return lane L holds in `z` the total of value (L>>2)

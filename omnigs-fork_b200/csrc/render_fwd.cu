@@ -17,10 +17,11 @@
 
 namespace ogs {
 
-// resident CTAs per SM: with the 52-instruction blend loop 6 (40 registers) measures best at C2 (4: 0.547, 5: 0.504,
-// 6: 0.495 ms); with the earlier 60-instruction loop it was 5 (4: 0.598, 5: 0.558, 6: 0.562, 8: 0.577)
+// resident CTAs per SM: with the 52-instruction blend loop 8 (32 registers, full occupancy) measures best at C2
+// (4: 0.547, 5: 0.504, 6: 0.495, 8: 0.486 ms); with the earlier 60-instruction loop it was 5 (4: 0.598, 5: 0.558,
+// 6: 0.562, 8: 0.577)
 #ifndef OGS_FWD_MINBLOCKS
-#define OGS_FWD_MINBLOCKS 6
+#define OGS_FWD_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
