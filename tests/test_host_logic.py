@@ -55,3 +55,22 @@ def test_rasterizer_module_argument_rules():
 def test_config_table_matches_baseline():
     assert sm.CONFIGS["C2"]["P"] == 1_000_000 and (sm.CONFIGS["C2"]["W"], sm.CONFIGS["C2"]["H"]) == (2048, 1024)
     assert sm.CONFIGS["C1"]["P"] == 100_000 and (sm.CONFIGS["C1"]["W"], sm.CONFIGS["C1"]["H"]) == (1024, 512)
+
+
+def test_bench_algorithmic_bytes_match_the_survey_yardstick():
+    """bench.py's roofline numerator is SURVEY.md section 8(d)'s fixed yardstick; its worked C2 example (V = P = 1e6, D = 3,
+    M = 16, N = 2048 x 1024, T = 8192, K = 6, R = 2.3e7) gives 0.311 + (0.008 + 0.296 + 3.496 + 0.184) + 0.962 + 1.042 +
+    0.559 = 6.86 GB."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    B = bench.alg_bytes(P=10**6, V=10**6, R=23 * 10**6, N=2048 * 1024, T=8192, D=3, M=16, K=6)
+    gb = {k: v / 1e9 for k, v in B.items()}
+    assert abs(gb["preprocess_fwd"] - 0.311) < 1e-3
+    assert abs(gb["binning"] - (0.008 + 0.296 + 3.496 + 0.184)) < 2e-3
+    assert abs(gb["render_fwd"] - 0.962) < 1e-3
+    assert abs(gb["render_bwd"] - 1.042) < 1e-3
+    assert abs(gb["preprocess_bwd"] - 0.559) < 1e-3
+    assert abs(sum(gb.values()) - 6.86) < 0.01
