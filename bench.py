@@ -8,7 +8,8 @@ Prints ONE JSON line (rank 0).  `value` = whole-job training views/s with every 
 (fwd + bwd through the public RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA boundary, plus
 the NCCL gradient all-reduce when N > 1); `ms_per_step` is the BASELINE "fwd+bwd ms/frame".
 `e2e` adds, per step, the pinned host->device copy of the view (pose + target image) and the
-device->host read of the loss.  `--impl reference` times the reference's own rasterizer
+device->host read of the loss.  `roofline_frame` carries the per-stage device times and `frame_ms`, the
+per-frame distribution SURVEY.md 8(d) asks for (forward, backward, both: p10 / median / p90 over 50 frames).  `--impl reference` times the reference's own rasterizer
 (oracle/_ref/omnigs_ref.so: its sources rebuilt for sm_100) through its own entry points on the same
 scene; if that library is absent it falls back to the CPU oracle port.
 """
@@ -425,6 +426,29 @@ def main():
         acc += np.array(list(buf))
     lib.ogs_profile_enable(0)
     stage_ms = dict(zip(stage_names, (acc / reps).tolist()))
+
+    # per-frame distribution (forward, backward and both; median with p10 / p90), CUDA events around the
+    # two boundary calls of every frame, one pose per frame
+    n_dist = min(K, 50)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_dist)]
+    for s in range(n_dist):
+        d["viewmatrix"], d["campos"] = view_dev[Wm + s]
+        d["projmatrix"] = d["viewmatrix"]
+        evs[s][0].record()
+        fwd = h.run_forward(mod, d)
+        evs[s][1].record()
+        h.run_backward(mod, d, fwd, dL)
+        evs[s][2].record()
+    torch.cuda.synchronize()
+
+    def spread(v):
+        v = sorted(v)
+        n = len(v)
+        return {"p10": v[int(0.1 * (n - 1))], "p50": statistics.median(v), "p90": v[int(0.9 * (n - 1) + 0.5)]}
+
+    frame_ms = {"forward": spread([e[0].elapsed_time(e[1]) for e in evs]),
+                "backward": spread([e[1].elapsed_time(e[2]) for e in evs]),
+                "forward_backward": spread([e[0].elapsed_time(e[2]) for e in evs]), "frames": n_dist}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -452,7 +476,7 @@ def main():
     total_alg = sum(B.values())
     line["roofline_frame"] = {"alg_bytes": total_alg, "achieved": total_alg / ms_per_step / 1e6, "peak": peak,
                               "unit": "GB/s", "frac": total_alg / ms_per_step / 1e6 / peak, "stages": per_stage,
-                              "stage_ms": stage_ms}
+                              "stage_ms": stage_ms, "frame_ms": frame_ms}
     if world == 1:
         line["train_step"] = training_iteration_bench(h, scene, views, dev, K, Wm, None)
     line["gpu_launches"] = K * (11 + 2)   # fwd: preprocess, hist, 4 + 2 onesweep (the first tile pass emits), scan, ranges, render; bwd: 2
