@@ -152,8 +152,10 @@ def exchange_bucket(bucket, group=None):
         arr = (ctypes.c_void_p * pr["world"])(*pr["ptrs"])
         stream = ctypes.c_void_p(torch.cuda.current_stream(bucket.flat.device).cuda_stream)
         pr["handle"].barrier(channel=0)
-        if pr.get("multicast") and pr.get("use_multimem", pr["world"] > 2):
-            # NVSwitch in-switch reduction: one inbound copy per element instead of world - 1
+        if pr.get("multicast") and pr.get("use_multimem", pr["world"] > 4):
+            # NVSwitch in-switch reduction: one inbound copy per element instead of world - 1.  Measured on the 244 MB
+            # bucket: peer loads/stores win up to four ranks (2: 0.36 ms; 4: 0.575 against 0.598), the multicast path
+            # beyond (8: 0.63 against 0.74)
             check(load_library().ogs_multimem_allreduce_sum(ctypes.c_void_p(pr["multicast"]), pr["world"], pr["rank"],
                                                             bucket.flat.numel(), stream))
         else:
