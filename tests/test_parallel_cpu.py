@@ -122,3 +122,40 @@ def test_band_rows_balances_instances_and_covers_all_rows():
         loads = [int(counts[a:b].sum()) for a, b in bands]
         assert max(loads) <= 1.6 * sum(loads) / world + counts.max()
     assert par.band_rows([5, 5], 4)[-1][1] == 2   # more ranks than rows: trailing bands may be empty
+
+
+def _multiview_worker(rank, world, port, out, views):
+    """One step = `views` views: every rank accumulates its own views into the step's bucket and ONE exchange sums the
+    ranks (the flow of tools/bench_dp_views.py / BASELINE configs[2])."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    bucket = par.GradientBucket(257, 16, "cpu")
+    work = par.GradientBucket(257, 16, "cpu", peer=False)
+    for k, v in enumerate(par.views_for_rank(views, rank, world)):
+        grads, radii = _make(v)
+        tgt = bucket if k == 0 else work
+        for n in par.OPTIMISED:
+            tgt[n].copy_(grads[n])
+        par.fill_view_stats(tgt, grads["dL_dmeans2D"], radii)
+        if k > 0:
+            bucket.flat += work.flat
+            torch.maximum(bucket.max_radii2D, work.max_radii2D, out=bucket.max_radii2D)
+    par.exchange_bucket(bucket)
+    if rank == 0:
+        torch.save({"flat": bucket.flat.clone(), "max_radii2D": bucket.max_radii2D.clone(),
+                    "sh": bucket["dL_dsh"].clone(), "acc": bucket["xyz_gradient_accum"].clone(), "denom": bucket["denom"].clone()}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_multi_view_step_accumulates_locally_and_exchanges_once_world2_gloo(tmp_path):
+    out, views = str(tmp_path / "mv.pt"), 4
+    mp.spawn(_multiview_worker, args=(2, _free_port(), out, views), nprocs=2, join=True)
+    got = torch.load(out)
+    per_view = [_make(v) for v in range(views)]
+    assert torch.allclose(got["sh"], sum(g["dL_dsh"] for g, _ in per_view), atol=1e-5)
+    acc = sum(torch.where(r > 0, g["dL_dmeans2D"][:, :2].norm(dim=-1), torch.zeros(r.shape)) for g, r in per_view)
+    assert torch.allclose(got["acc"], acc, atol=1e-5)
+    assert torch.equal(got["denom"], sum((r > 0).float() for _, r in per_view))
+    assert torch.equal(got["max_radii2D"], torch.stack([r for _, r in per_view]).max(dim=0).values.float())
