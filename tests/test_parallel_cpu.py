@@ -159,3 +159,20 @@ def test_multi_view_step_accumulates_locally_and_exchanges_once_world2_gloo(tmp_
     assert torch.allclose(got["acc"], acc, atol=1e-5)
     assert torch.equal(got["denom"], sum((r > 0).float() for _, r in per_view))
     assert torch.equal(got["max_radii2D"], torch.stack([r for _, r in per_view]).max(dim=0).values.float())
+
+
+def test_band_rows_properties_hold_for_arbitrary_row_loads():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(min_value=0, max_value=10**6), min_size=1, max_size=300), st.integers(min_value=1, max_value=8))
+    def check(counts, world):
+        bands = par.band_rows(counts, world)
+        gy = len(counts)
+        assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == gy
+        assert all(0 <= a <= b <= gy for a, b in bands)
+        assert all(x[1] == y[0] for x, y in zip(bands, bands[1:]))          # contiguous, disjoint, covering
+        if gy >= world:
+            assert all(b > a for a, b in bands)                              # nobody idles while rows are left
+
+    check()
