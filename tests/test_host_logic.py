@@ -74,3 +74,31 @@ def test_bench_algorithmic_bytes_match_the_survey_yardstick():
     assert abs(gb["render_bwd"] - 1.042) < 1e-3
     assert abs(gb["preprocess_bwd"] - 0.559) < 1e-3
     assert abs(sum(gb.values()) - 6.86) < 0.01
+
+
+def test_emit_slot_float_division_is_exact_with_its_correction():
+    """binning.cu emit_slot(): q = local / w is evaluated as trunc(float_rz(local) * rcp.approx(float(w))) followed by a
+    two-sided correction.  Restated in float32 numpy with the reciprocal off by -1 / 0 / +1 ulp (rcp.approx's error
+    bound) on adversarial slots (remainders next to 0 and w - 1, local up to 2^30, q up to 2^16): always exact."""
+    rng = np.random.default_rng(1)
+    n = 1_500_000
+    w = rng.integers(1, 65536, n).astype(np.int64)
+    q = rng.integers(0, 65536, n).astype(np.int64)
+    r = np.where(rng.random(n) < 0.5, rng.integers(0, 3, n), w - 1 - rng.integers(0, 3, n)).astype(np.int64)
+    r = np.clip(r, 0, w - 1)
+    local = q * w + r
+    keep = local < (1 << 30)
+    w, q, local = w[keep], q[keep], local[keep]
+
+    def f32_rz(x):   # __uint2float_rz
+        f = x.astype(np.float32)
+        return np.where(f.astype(np.int64) > x, np.nextafter(f, np.float32(0)), f).astype(np.float32)
+
+    lf, wf = f32_rz(local), f32_rz(w)
+    rc = (np.float32(1) / wf).astype(np.float32)
+    for rcp in (rc, np.nextafter(rc, np.float32(np.inf)), np.nextafter(rc, np.float32(0))):
+        qq = np.floor((lf * rcp).astype(np.float32)).astype(np.int64)
+        rem = local - qq * w
+        qq = np.where(rem < 0, qq - 1, np.where(rem >= w, qq + 1, qq))
+        rem = local - qq * w
+        assert np.array_equal(qq, q) and bool(((rem >= 0) & (rem < w)).all())
