@@ -60,10 +60,10 @@ extern "C" {
 #define OGS_OK 0
 #define OGS_ERR_INVALID_ARG (-1)   /* NULL/negative/inconsistent argument                      */
 #define OGS_ERR_CUDA (-2)          /* a CUDA runtime call failed (see ogs_last_error)            */
-#define OGS_ERR_TOO_MANY (-3)      /* num_rendered >= 2^30 or image larger than 2^16 tiles/axis  */
+#define OGS_ERR_TOO_MANY (-3)      /* num_rendered >= 2^31 (the reference's int) or image larger than 2^16 tiles/axis  */
 #define OGS_ERR_NO_DEVICE (-4)     /* no usable sm_100 device                                    */
 
-#define OGS_ABI_VERSION 1
+#define OGS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define OGS_API __attribute__((visibility("default")))
@@ -104,6 +104,28 @@ OGS_API int ogs_lonlat_forward_stage2(
 	int P, int W, int H, int64_t num_rendered, const float* background,
 	char* geom_buffer, char* binning_buffer, char* img_buffer,
 	float* out_color, void* stream);
+/* The two halves of stage 2: ..._bin = emission + sort (rasterizer_impl.cu:632-679, needs no colours),
+ * ..._blend = renderCUDA (forward.cu:346-467).  stage2 == bin followed by blend; bin may be repeated on the same buffers. */
+OGS_API int ogs_lonlat_forward_bin(
+	int P, int W, int H, int64_t num_rendered, char* geom_buffer, char* binning_buffer, char* img_buffer, void* stream);
+OGS_API int ogs_lonlat_forward_blend(
+	int P, int W, int H, int64_t num_rendered, const float* background,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, float* out_color, void* stream);
+/*
+ * Stage 1 without colours, and the colours on their own (data-parallel training): the SH
+ * coefficients are the only parameters the geometry, the depth order and the tile sort do not read, so a trainer can
+ * start a step with ..._stage1_geometry + ..._bin while the previous step's SH gradients are still being exchanged and
+ * applied, then call ..._forward_colors (computeColorFromSH at its call site, forward.cu:688-692, for every Gaussian
+ * with radii > 0; bit-identical colours and clamp masks) and ..._blend.
+ */
+OGS_API int ogs_lonlat_forward_stage1_geometry(
+	int P, int W, int H,
+	const float* means3D, const float* opacities, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* campos,
+	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, void* stream);
+OGS_API int ogs_lonlat_forward_colors(
+	int P, int D, int M, const float* means3D, const float* shs, const float* campos, const int* radii,
+	char* geom_buffer, void* stream);
 
 /*
  * Backward (rasterizer_impl.cu:701-795): render backward (backward.cu:672-843) then the fused
@@ -146,6 +168,52 @@ OGS_API int ogs_lonlat_backward_finish(
 	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
 	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream);
 OGS_API size_t ogs_grad_acc_offset(int P);
+/* The same two halves on caller-owned accumulators (grad_acc: [P,12] float, 16-byte aligned, e.g. in symmetric memory
+ * so that the band ranks can sum it with ogs_peer_allreduce / ogs_multimem_allreduce instead of NCCL). */
+OGS_API int ogs_lonlat_backward_render_into(
+	int P, int64_t num_rendered, int W, int H, const float* background,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, const float* dL_dpix, float* grad_acc, void* stream);
+OGS_API int ogs_lonlat_backward_finish_from(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* campos, const int* radii, char* geom_buffer,
+	const float* grad_acc,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream);
+
+/*
+ * One view of a multi-view / data-parallel training step (the reference trains one view per step
+ * and has no multi-GPU code, so this is an extension whose oracle is "the sum of the reference's per-view gradients").
+ * Like ogs_lonlat_backward, except that
+ *   - the four geometry gradients the optimiser consumes (dL_dmean3D [P,3], dL_dopacity [P], dL_dscale [P,3],
+ *     dL_drot [P,4]) are WRITTEN when accumulate == 0 (first view of the step) and ADDED TO otherwise;
+ *   - the view's densification statistics (gaussian_mapper.cpp:427-434, gaussian_model.cpp:839-853) go the same way
+ *     into stat_grad_norm (sum of |dL_dmean2D.xy|), stat_visible (count) and stat_max_radius (max radius, as float);
+ *     pass all three or none;
+ *   - instead of dL_dsh [P,M,3] the call leaves dL_drgb_view [P,3]: dL/dcolour with the clamped channels zeroed
+ *     (zeros for culled Gaussians).  Row k of dL/dsh is b_k(direction) * dL/dRGB per view (backward.cu:60-150), so
+ *     a step's dL/dsh is rebuilt ONCE from all its views' factors by ogs_sh_gradient_from_views: 12 bytes per
+ *     Gaussian and view cross NVLink instead of 192.
+ * dL_dmean2D [P,3] is optional.
+ */
+OGS_API int ogs_lonlat_backward_view(
+	int P, int D, int M, int64_t num_rendered, int W, int H, const float* background,
+	const float* means3D, const float* shs, const float* scales, float scale_modifier, const float* rotations,
+	const float* viewmatrix, const float* campos, const int* radii,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, const float* dL_dpix,
+	int accumulate, float* dL_dmean3D, float* dL_dopacity, float* dL_dscale, float* dL_drot,
+	float* dL_drgb_view, float* stat_grad_norm, float* stat_visible, float* stat_max_radius,
+	float* dL_dmean2D, void* stream);
+/*
+ * dL_dsh [P,16,3] (or, for the raw-parameter trainer, dL_dfeatures_dc [P,1,3] + dL_dfeatures_rest [P,15,3]; give one
+ * of the two forms) = sum over the step's views, in view order, of b(direction from campos_views[v]) (x) dL_drgb_views[v].
+ * Bit-identical to adding up the per-view dL_dsh tensors of ogs_lonlat_backward in that order.  campos_views is a
+ * device array [n_views,3]; dL_drgb_views a HOST array of n_views <= 16 device pointers, which may point into peer
+ * GPUs' memory (the kernel then reads the factors over NVLink: transfer and rebuild are one pass).
+ */
+OGS_API int ogs_sh_gradient_from_views(
+	int P, int D, int M, int n_views, const float* means3D, const float* campos_views, const float* const* dL_drgb_views,
+	float* dL_dsh, float* dL_dfeatures_dc, float* dL_dfeatures_rest, void* stream);
 
 /* markAllVisible (rasterizer_impl.cu:82-90): present[i] = true for i < P (1 byte per flag). */
 OGS_API int ogs_mark_all_visible(int P, uint8_t* present, void* stream);
@@ -178,27 +246,6 @@ OGS_API int ogs_export_binning(
 	const char* geom_buffer, const char* binning_buffer, const char* img_buffer,
 	uint32_t* point_list /*[R]*/, uint64_t* point_list_keys /*[R]*/, uint32_t* ranges /*[T,2]*/,
 	float* final_T /*[H*W]*/, uint32_t* n_contrib /*[H*W]*/, void* stream);
-
-/*
- * Host-buffer convenience call used for end-to-end measurement: per-view inputs
- * (viewmatrix, campos, dL_dpix) are HOST pointers copied in, the image is copied back to
- * out_color_host, all inside the call; the scene parameters stay resident on the device.
- * Equivalent to stage1 + stage2 + backward with the copies around them; synchronises on return.
- * binning_buffer/binning_capacity: a device scratch the caller owns; if num_rendered needs more
- * the call fails with OGS_ERR_INVALID_ARG after writing the required size to *binning_needed.
- */
-OGS_API int ogs_lonlat_train_view_host(
-	int P, int D, int M, int W, int H,
-	const float* background,
-	const float* means3D, const float* shs, const float* opacities,
-	const float* scales, float scale_modifier, const float* rotations,
-	const float* viewmatrix_host, const float* campos_host, const float* dL_dpix_host,
-	float* view_scratch /*device, >= 19 floats*/, float* dL_dpix_dev /*device [3,H,W]*/,
-	int* radii, char* geom_buffer, char* binning_buffer, size_t binning_capacity, char* img_buffer,
-	float* out_color_dev, float* out_color_host,
-	float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
-	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
-	int64_t* num_rendered_host, size_t* binning_needed, void* stream);
 
 /*
  * Perspective camera (camera_type = 1): CudaRasterizer::Rasterizer::forward / backward /
@@ -305,6 +352,15 @@ OGS_API int ogs_peer_allreduce_sum(float* const* bufs, int world, int rank, size
 /* Same contract through the bucket's NVLink multicast address (NVSwitch in-switch reduction: multimem.ld_reduce /
  * multimem.st on slice `rank`); `multicast` is the multicast mapping of the symmetric buffer. */
 OGS_API int ogs_multimem_allreduce_sum(float* multicast, int world, int rank, size_t count, void* stream);
+/* Both with a second section: the first count_sum floats are summed, the count_max floats behind them (non-negative
+ * values such as radii, which order like their bit patterns) are max-reduced — one call replaces the all-reduce(SUM)
+ * plus the separate all-reduce(MAX) of the densification statistics. */
+OGS_API int ogs_peer_allreduce(float* const* bufs, int world, int rank, size_t count_sum, size_t count_max, void* stream);
+OGS_API int ogs_multimem_allreduce(float* multicast, int world, int rank, size_t count_sum, size_t count_max, void* stream);
+/* Latitude bands: store pixel rows [y0, y1) of the three planes of `src` ([3,H,W], this rank's
+ * render) into every rank's image images[r] ([3,H,W] in symmetric memory): an all-gather of band rows by peer stores. */
+OGS_API int ogs_band_rows_allgather(float* const* images, int world, int rank, const float* src, int W, int H,
+                                    int y0, int y1, void* stream);
 /* One view's increments of the densification statistics as plain [P] arrays (gaussian_mapper.cpp:427-434,
  * gaussian_model.cpp:839-853): ||dL_dmean2D.xy|| and 1 where radii > 0 (else 0), and the radius as float — what
  * data-parallel ranks sum / sum / max over views before applying them. */

@@ -13,6 +13,9 @@ from ._lib import load_library, library_path, OgsError  # noqa: F401
 from .rasterize_points import (  # noqa: F401
     RasterizeGaussiansCUDA,
     RasterizeGaussiansBackwardCUDA,
+    RasterizeGaussiansBackwardView,
+    RasterizeGaussiansGeometry,
+    RasterizeGaussiansBlend,
     markVisible,
     export_forward_state,
     set_seam_wrap,
@@ -22,7 +25,8 @@ from .rasterize_points import (  # noqa: F401
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians  # noqa: F401
 
 __all__ = [
-    "RasterizeGaussiansCUDA", "RasterizeGaussiansBackwardCUDA", "markVisible", "export_forward_state", "set_seam_wrap",
+    "RasterizeGaussiansCUDA", "RasterizeGaussiansBackwardCUDA", "RasterizeGaussiansBackwardView",
+    "RasterizeGaussiansGeometry", "RasterizeGaussiansBlend", "markVisible", "export_forward_state", "set_seam_wrap",
     "GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians",
     "load_library", "library_path", "OgsError", "LONLAT", "PINHOLE",
 ]

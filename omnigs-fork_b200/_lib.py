@@ -58,8 +58,18 @@ SYMBOLS = {
     "ogs_get_seam_wrap": (_c_int, []),
     "ogs_profile_enable": (_c_int, [_c_int]),
     "ogs_profile_read": (_c_int, [ctypes.POINTER(_c_f), _c_int]),
-    "ogs_lonlat_train_view_host": (_c_int, [_c_int] * 5 + [_p] * 5 + [_c_f] + [_p] * 4 + [_p] * 2 + [_p] * 3 + [_c_sz, _p]
-                                   + [_p] * 2 + [_p] * 8 + [ctypes.POINTER(_c_i64), ctypes.POINTER(_c_sz), _p]),
+    "ogs_lonlat_forward_bin": (_c_int, [_c_int] * 3 + [_c_i64] + [_p] * 3 + [_p]),
+    "ogs_lonlat_forward_blend": (_c_int, [_c_int] * 3 + [_c_i64] + [_p] * 5 + [_p]),
+    "ogs_lonlat_forward_stage1_geometry": (_c_int, [_c_int] * 3 + [_p] * 3 + [_c_f] + [_p] * 4 + [_p] * 3 + [ctypes.POINTER(_c_i64), _p]),
+    "ogs_lonlat_forward_colors": (_c_int, [_c_int] * 3 + [_p] * 5 + [_p]),
+    "ogs_lonlat_backward_render_into": (_c_int, [_c_int, _c_i64, _c_int, _c_int] + [_p] * 6 + [_p]),
+    "ogs_lonlat_backward_finish_from": (_c_int, [_c_int] * 5 + [_p] * 3 + [_c_f] + [_p] * 6 + [_p] + [_p] * 9 + [_p]),
+    "ogs_lonlat_backward_view": (_c_int, [_c_int] * 3 + [_c_i64, _c_int, _c_int] + [_p] * 4 + [_c_f] + [_p] * 4 + [_p] * 4
+                                 + [_c_int] + [_p] * 9 + [_p]),
+    "ogs_sh_gradient_from_views": (_c_int, [_c_int] * 4 + [_p] * 6 + [_p]),
+    "ogs_band_rows_allgather": (_c_int, [_p, _c_int, _c_int, _p] + [_c_int] * 4 + [_p]),
+    "ogs_peer_allreduce": (_c_int, [_p, _c_int, _c_int, _c_sz, _c_sz, _p]),
+    "ogs_multimem_allreduce": (_c_int, [_p, _c_int, _c_int, _c_sz, _c_sz, _p]),
 }
 
 
@@ -78,8 +88,8 @@ def load_library():
         fn = getattr(lib, name)  # AttributeError if the header and the library diverge
         fn.restype = res
         fn.argtypes = args
-    if lib.ogs_abi_version() != 1:
-        raise OgsError(f"ABI version mismatch: library reports {lib.ogs_abi_version()}, host expects 1")
+    if lib.ogs_abi_version() != 2:
+        raise OgsError(f"ABI version mismatch: library reports {lib.ogs_abi_version()}, host expects 2")
     _lib = lib
     return lib
 

@@ -26,9 +26,35 @@ namespace ogs {
 
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = kSortItemsPerBlock / kSortThreads;   // 8 keys per thread
-constexpr uint32_t kFlagPartial = 1u << 30;
-constexpr uint32_t kFlagInclusive = 2u << 30;
-constexpr uint32_t kValueMask = (1u << 30) - 1;
+// Look-back status words.  The reference accepts any int num_rendered (rasterizer_impl.cu:627-632), so an inclusive
+// digit prefix needs 31 bits.  32-bit words (tile sort, depth sort; partial counts <= 2048):
+//   0 = not published, 1 .. 2^31-1 = partial count + 1, bit 31 set = inclusive prefix in the low 31 bits.
+// 64-bit words (emission-offset scan, whose per-tile partial sums are unbounded below 2^31): flag in bits 62-63.
+struct Status32 {
+	typedef uint32_t word;
+	static OGS_D word partial(uint32_t v) { return v + 1u; }
+	static OGS_D word inclusive(uint32_t v) { return 0x80000000u | v; }
+	static OGS_D bool empty(word w) { return w == 0u; }
+	static OGS_D bool is_inclusive(word w) { return (w & 0x80000000u) != 0u; }
+	static OGS_D uint32_t value(word w) { return (w & 0x80000000u) ? (w & 0x7FFFFFFFu) : w - 1u; }
+	static OGS_D word load(const word* p) { return ld_acquire(p); }
+	static OGS_D void store(word* p, word w) { st_release(p, w); }
+};
+struct Status64 {
+	typedef unsigned long long word;
+	static OGS_D word partial(uint32_t v) { return (1ull << 62) | v; }
+	static OGS_D word inclusive(uint32_t v) { return (2ull << 62) | v; }
+	static OGS_D bool empty(word w) { return (w >> 62) == 0ull; }
+	static OGS_D bool is_inclusive(word w) { return (w >> 62) == 2ull; }
+	static OGS_D uint32_t value(word w) { return (uint32_t)w; }
+	static OGS_D word load(const word* p)
+	{
+		word v;
+		asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+		return v;
+	}
+	static OGS_D void store(word* p, word w) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(w) : "memory"); }
+};
 
 // ------------------------------------------------------------------ block-wide exclusive scan
 // Exclusive prefix sum over `n` (<= 2*kSortThreads) smem words, in place; returns nothing.
@@ -117,26 +143,26 @@ constexpr size_t kOnesweepSmemBytes = sizeof(OnesweepSmem) > sizeof(EmitSmem) ? 
 // inclusive one.  Status words of kLookbackBatch predecessors are fetched together, so the walk
 // costs one L2 round trip per batch instead of one per tile (with several hundred CTAs in flight
 // the not-yet-inclusive window is hundreds of tiles long).
-OGS_D uint32_t lookback_sum(const uint32_t* __restrict__ status, int tile, size_t stride, size_t offset)
+template <typename S>
+OGS_D uint32_t lookback_sum(const typename S::word* __restrict__ status, int tile, size_t stride, size_t offset)
 {
 	uint32_t excl = 0;
 	int t = tile - 1;
 	while (true) {
-		uint32_t s[kLookbackBatch];
+		typename S::word s[kLookbackBatch];
 #pragma unroll
 		for (int i = 0; i < kLookbackBatch; i++)
-			s[i] = (t - i >= 0) ? ld_acquire(&status[(size_t)(t - i) * stride + offset]) : kFlagInclusive;
+			s[i] = (t - i >= 0) ? S::load(&status[(size_t)(t - i) * stride + offset]) : S::inclusive(0u);
 		bool done = false;
 		int consumed = kLookbackBatch;
 #pragma unroll
 		for (int i = 0; i < kLookbackBatch; i++) {
 			if (!done && consumed == kLookbackBatch) {
-				const uint32_t flag = s[i] & ~kValueMask;
-				if (flag == 0) {
+				if (S::empty(s[i])) {
 					consumed = i;            // not published yet: poll again from this tile
 				} else {
-					excl += s[i] & kValueMask;
-					if (flag == kFlagInclusive) done = true;
+					excl += S::value(s[i]);
+					if (S::is_inclusive(s[i])) done = true;
 				}
 			}
 		}
@@ -206,7 +232,7 @@ OGS_D void emit_slot(const EmitSmem& em, uint32_t o, uint32_t o0, int gx, uint32
 	const uint32_t x0 = rc.x & 0xFFFFu, x1 = rc.x >> 16, y0 = rc.y & 0xFFFFu;
 	const uint32_t w = x1 - x0;
 	const uint32_t local = o - em.off[src];
-	// q = local / w without the ~35-instruction integer division: local < 2^30 and q < 2^16, so the float quotient is
+	// q = local / w without the ~35-instruction integer division: local < 2^31 and q < 2^16, so the float quotient is
 	// off by at most one and a two-sided correction makes it exact
 	uint32_t q = __float2uint_rz(__uint2float_rz(local) * rcp_approx(__uint2float_rz(w)));
 	int rem = (int)(local - q * w);
@@ -295,7 +321,7 @@ __global__ void __launch_bounds__(kSortThreads, OGS_SORT_MINBLOCKS) onesweep_pas
 	}
 	__syncthreads();
 	for (int b = tid; b < nbins; b += kSortThreads)
-		st_release(&status[(size_t)tile * nbins + b], (tile == 0 ? kFlagInclusive : kFlagPartial) | sm.tile_hist[b]);
+		Status32::store(&status[(size_t)tile * nbins + b], tile == 0 ? Status32::inclusive(sm.tile_hist[b]) : Status32::partial(sm.tile_hist[b]));
 	// values travel with the keys: issue their loads now, they are consumed after the look-back
 	if constexpr (!kEmit) {
 #pragma unroll
@@ -372,8 +398,8 @@ __global__ void __launch_bounds__(kSortThreads, OGS_SORT_MINBLOCKS) onesweep_pas
 		if (b < nbins) {
 			uint32_t excl = 0;
 			if (tile != 0) {
-				excl = lookback_sum(status, (int)tile, (size_t)nbins, (size_t)b);
-				st_release(&status[(size_t)tile * nbins + b], kFlagInclusive | (excl + digit_total[q]));
+				excl = lookback_sum<Status32>(status, (int)tile, (size_t)nbins, (size_t)b);
+				Status32::store(&status[(size_t)tile * nbins + b], Status32::inclusive(excl + digit_total[q]));
 			}
 			// digit start + keys of this digit in earlier tiles - tile-local start: slot j of the staged tile goes to base + j
 			sm.global_base[b] += excl - sm.bin_start[b];
@@ -400,7 +426,7 @@ struct ScanSmem {
 };
 __global__ void __launch_bounds__(kSortThreads) gather_scan_kernel(
 	const uint32_t* __restrict__ counts, const uint32_t* __restrict__ order, uint32_t n,
-	uint32_t* __restrict__ out, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket,
+	uint32_t* __restrict__ out, unsigned long long* __restrict__ status, unsigned int* __restrict__ ticket,
 	uint32_t* __restrict__ first_src, const unsigned long long* __restrict__ total)
 {
 	__shared__ ScanSmem sm;
@@ -436,11 +462,11 @@ __global__ void __launch_bounds__(kSortThreads) gather_scan_kernel(
 	if (tid == 0) {
 		uint32_t excl = 0;
 		if (tile == 0) {
-			st_release(&status[0], kFlagInclusive | tile_total);
+			Status64::store(&status[0], Status64::inclusive(tile_total));
 		} else {
-			st_release(&status[tile], kFlagPartial | tile_total);
-			excl = lookback_sum(status, (int)tile, 1, 0);
-			st_release(&status[tile], kFlagInclusive | (excl + tile_total));
+			Status64::store(&status[tile], Status64::partial(tile_total));
+			excl = lookback_sum<Status64>(status, (int)tile, 1, 0);
+			Status64::store(&status[tile], Status64::inclusive(excl + tile_total));
 		}
 		sm.tile_excl = excl;
 	}
@@ -675,7 +701,11 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 	const TileSortPlan plan = make_tile_sort_plan(W, H);
 	const uint32_t n = (uint32_t)R;
 	prof_begin(OGS_PROF_EMIT, st);
-	unsigned int* scan_ticket = reinterpret_cast<unsigned int*>(g.scalars + 2) + 4;
+	// ticket and look-back words of the emission-offset scan are zeroed HERE (not only in stage 1), so stage 2 may run
+	// again on the same buffers
+	const size_t scan_tiles = (size_t)ceil_div(P, kSortItemsPerBlock);
+	unsigned int* scan_ticket = reinterpret_cast<unsigned int*>(g.scan_status + scan_tiles + 1);
+	OGS_CUDA_TRY(cudaMemsetAsync(g.scan_status, 0, sizeof(unsigned long long) * (scan_tiles + 2), st));
 	gather_scan_kernel<<<ceil_div(P, kSortItemsPerBlock), kSortThreads, 0, st>>>(
 		g.tiles_touched, g.sort_val[0], (uint32_t)P, g.emit_offset, g.scan_status, scan_ticket, b.first_src, g.scalars);
 	// OGS_FUSED_EMIT=0 materialises the unsorted list first (A/B measurements); default: pass 0 emits on the fly

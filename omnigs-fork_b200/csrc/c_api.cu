@@ -104,7 +104,7 @@ GeomState carve_geom(char* base, int P, size_t* total)
 	g.depth_hist = c.take<uint32_t>(4 * 256);
 	g.zero_begin = reinterpret_cast<char*>(g.depth_hist);
 	g.depth_status = c.take<uint32_t>((size_t)4 * tiles * 256);
-	g.scan_status = c.take<uint32_t>((size_t)tiles + 1);
+	g.scan_status = c.take<unsigned long long>((size_t)tiles + 2);   // [tiles + 1] holds the scan's ticket counter
 	g.scalars = c.take<unsigned long long>(8);
 	g.scalars_bytes = 64;
 	c.off = align_up(c.off, kAlign);
@@ -255,7 +255,8 @@ int forward_stage1_impl(
 	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
 	const float* viewmatrix, const float* campos,
 	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, cudaStream_t st,
-	const float* features_dc = nullptr, const float* features_rest = nullptr, const PinholeParams* pin = nullptr)
+	const float* features_dc = nullptr, const float* features_rest = nullptr, const PinholeParams* pin = nullptr,
+	bool defer_colors = false)
 {
 	// raw-parameter mode: features_dc / features_rest given instead of shs; opacities, scales and rotations
 	// are then the stored (pre-activation) tensors
@@ -272,8 +273,11 @@ int forward_stage1_impl(
 	if (!means3D || !opacities || !viewmatrix || !campos || !radii || !geom_buffer)
 		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
 	if (raw) {
-		if (shs || colors_precomp || cov3D_precomp || !features_rest || !scales || !rotations || M < 2)
+		// SH degree 0 models have an empty features_rest_ (M == 1): allowed, as the reference's cat() path allows it
+		if (shs || colors_precomp || cov3D_precomp || (M > 1 && !features_rest) || !scales || !rotations || M < 1)
 			return fail(OGS_ERR_INVALID_ARG, "raw-parameter mode takes features_dc, features_rest, scaling and rotation only");
+	} else if (defer_colors) {
+		if (shs || colors_precomp) return fail(OGS_ERR_INVALID_ARG, "the geometry-only stage takes neither shs nor colors_precomp");
 	} else if ((shs == nullptr) == (colors_precomp == nullptr))
 		return fail(OGS_ERR_INVALID_ARG, "exactly one of shs / colors_precomp must be given");
 	if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
@@ -296,6 +300,7 @@ int forward_stage1_impl(
 	a.means3D = means3D; a.shs = shs; a.colors_precomp = colors_precomp; a.opacities = opacities;
 	a.scales = scales; a.rotations = rotations; a.cov3D_precomp = cov3D_precomp;
 	a.raw = raw ? 1 : 0; a.features_dc = features_dc; a.features_rest = features_rest;
+	a.defer_colors = defer_colors ? 1 : 0;
 	if (pin) {
 		if (!pin->projmatrix) return fail(OGS_ERR_INVALID_ARG, "projmatrix is NULL");
 		if (raw || seam_wrap) return fail(OGS_ERR_INVALID_ARG, "raw-parameter mode and seam wrap-around are lonlat-only");
@@ -322,29 +327,36 @@ int forward_stage1_impl(
 	// OGS_SIDE_STREAM=0 keeps tile_ranges on the caller's stream behind the depth order (A/B knob)
 	static const bool side = [] { const char* e = getenv("OGS_SIDE_STREAM"); return e ? atoi(e) != 0 : true; }();
 	const cudaStream_t st_ranges = side ? rb->side : st;
+	// Work forked onto the side stream must be joined back on EVERY path out of here: the caller may free or reuse the
+	// buffers on `st` as soon as this call returns, error or not.
+	int rc_side = OGS_OK, rc_main = OGS_OK;
 	if (side) {
 		OGS_CUDA_TRY(cudaEventRecord(rb->fork, st));
 		OGS_CUDA_TRY(cudaStreamWaitEvent(rb->side, rb->fork, 0));
 		prof_begin(OGS_PROF_TILE_RANGES, st_ranges);
-		if (int rc = launch_tile_ranges(img, W, H, st_ranges)) return rc;
+		rc_side = launch_tile_ranges(img, W, H, st_ranges);
 		prof_end(OGS_PROF_TILE_RANGES, st_ranges);
-		OGS_CUDA_TRY(cudaEventRecord(rb->join, rb->side));
+		const cudaError_t e = cudaEventRecord(rb->join, rb->side);
+		if (e != cudaSuccess) { cudaStreamSynchronize(rb->side); return fail_cuda(e); }
 	}
 	prof_begin(OGS_PROF_DEPTH_ORDER, st);
-	if (int rc = launch_depth_order(g, P, st)) return rc;
+	rc_main = launch_depth_order(g, P, st);
 	prof_end(OGS_PROF_DEPTH_ORDER, st);
 	if (side) {
-		OGS_CUDA_TRY(cudaStreamWaitEvent(st, rb->join, 0));
-	} else {
+		const cudaError_t e = cudaStreamWaitEvent(st, rb->join, 0);
+		if (e != cudaSuccess) { cudaStreamSynchronize(rb->side); return fail_cuda(e); }
+	} else if (rc_main == OGS_OK) {
 		prof_begin(OGS_PROF_TILE_RANGES, st);
-		if (int rc = launch_tile_ranges(img, W, H, st)) return rc;
+		rc_side = launch_tile_ranges(img, W, H, st);
 		prof_end(OGS_PROF_TILE_RANGES, st);
 	}
+	if (rc_main) return rc_main;
+	if (rc_side) return rc_side;
 	OGS_CUDA_TRY(cudaEventSynchronize(rb->event));
 	const unsigned long long total = *rb->pinned;
-	if (total >= (1ull << 30)) {
+	if (total >= (1ull << 31)) {   // the reference's `int num_rendered` overflows here (rasterizer_impl.cu:627-632)
 		*num_rendered_host = (int64_t)total;
-		return fail(OGS_ERR_TOO_MANY, "num_rendered >= 2^30 tile instances");
+		return fail(OGS_ERR_TOO_MANY, "num_rendered >= 2^31 tile instances");
 	}
 	*num_rendered_host = (int64_t)total;
 	return OGS_OK;
@@ -417,15 +429,32 @@ OGS_API int ogs_lonlat_forward_stage1_band(
 	                           geom_buffer, img_buffer, num_rendered_host, (cudaStream_t)stream);
 }
 
-OGS_API int ogs_lonlat_forward_stage2(
+// Stage 2, first half: emission + tile-id sort (no colours needed).
+OGS_API int ogs_lonlat_forward_bin(
+	int P, int W, int H, int64_t num_rendered, char* geom_buffer, char* binning_buffer, char* img_buffer, void* stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (P < 0 || num_rendered < 0 || !img_buffer) return fail(OGS_ERR_INVALID_ARG, "bad argument to forward bin");
+	if (int rc = check_image(W, H)) return rc;
+	if (num_rendered >= (1ll << 31)) return fail(OGS_ERR_TOO_MANY, "num_rendered >= 2^31 tile instances");
+	if (num_rendered == 0 || P == 0) return OGS_OK;
+	if (!geom_buffer || !binning_buffer) return fail(OGS_ERR_INVALID_ARG, "geom_buffer / binning_buffer is NULL");
+	ImageState img = ImageState::carve(img_buffer, W, H);
+	GeomState g = GeomState::carve(geom_buffer, P);
+	BinningState b = BinningState::carve(binning_buffer, num_rendered, W, H);
+	OGS_CUDA_TRY(cudaMemsetAsync(b.zero_begin, 0, b.zero_bytes, st));
+	return launch_emit_and_tile_sort(g, img, b, P, num_rendered, W, H, st);
+}
+
+// Stage 2, second half: the alpha blend.
+OGS_API int ogs_lonlat_forward_blend(
 	int P, int W, int H, int64_t num_rendered, const float* background,
 	char* geom_buffer, char* binning_buffer, char* img_buffer, float* out_color, void* stream)
 {
 	cudaStream_t st = (cudaStream_t)stream;
 	if (P < 0 || num_rendered < 0 || !background || !img_buffer || !out_color)
-		return fail(OGS_ERR_INVALID_ARG, "bad argument to forward stage 2");
+		return fail(OGS_ERR_INVALID_ARG, "bad argument to forward blend");
 	if (int rc = check_image(W, H)) return rc;
-	if (num_rendered >= (1ll << 30)) return fail(OGS_ERR_TOO_MANY, "num_rendered >= 2^30 tile instances");
 	ImageState img = ImageState::carve(img_buffer, W, H);
 	GeomState g{};
 	BinningState b{};
@@ -436,8 +465,6 @@ OGS_API int ogs_lonlat_forward_stage2(
 	if (num_rendered > 0) {
 		if (!binning_buffer) return fail(OGS_ERR_INVALID_ARG, "binning_buffer is NULL");
 		b = BinningState::carve(binning_buffer, num_rendered, W, H);
-		OGS_CUDA_TRY(cudaMemsetAsync(b.zero_begin, 0, b.zero_bytes, st));
-		if (int rc = launch_emit_and_tile_sort(g, img, b, P, num_rendered, W, H, st)) return rc;
 	}
 	prof_begin(OGS_PROF_RENDER_FWD, st);
 	const int rc = launch_render_fwd(img.ranges, b.point_list, W, H, g.g0, g.g1, g.gb, g.scalars, background,
@@ -446,10 +473,59 @@ OGS_API int ogs_lonlat_forward_stage2(
 	return rc;
 }
 
+OGS_API int ogs_lonlat_forward_stage2(
+	int P, int W, int H, int64_t num_rendered, const float* background,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, float* out_color, void* stream)
+{
+	if (P < 0 || num_rendered < 0 || !background || !img_buffer || !out_color)
+		return fail(OGS_ERR_INVALID_ARG, "bad argument to forward stage 2");
+	if (int rc = ogs_lonlat_forward_bin(P, W, H, num_rendered, geom_buffer, binning_buffer, img_buffer, stream)) return rc;
+	return ogs_lonlat_forward_blend(P, W, H, num_rendered, background, geom_buffer, binning_buffer, img_buffer, out_color, stream);
+}
+
+// Geometry-only stage 1 + deferred colours (data-parallel trainer: the SH gradients of the previous step are still being
+// exchanged while this step's geometry, depth order and tile sort run; colours are evaluated right before the blend).
+OGS_API int ogs_lonlat_forward_stage1_geometry(
+	int P, int W, int H,
+	const float* means3D, const float* opacities, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* campos,
+	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, void* stream)
+{
+	return forward_stage1_impl(P, 0, 0, W, H, 0, 1 << 30, means3D, nullptr, nullptr, opacities, scales, scale_modifier,
+	                           rotations, cov3D_precomp, viewmatrix, campos, radii, geom_buffer, img_buffer,
+	                           num_rendered_host, (cudaStream_t)stream, nullptr, nullptr, nullptr, true);
+}
+
+OGS_API int ogs_lonlat_forward_colors(
+	int P, int D, int M, const float* means3D, const float* shs, const float* campos, const int* radii,
+	char* geom_buffer, void* stream)
+{
+	if (P < 0) return fail(OGS_ERR_INVALID_ARG, "bad P");
+	if (P == 0) return OGS_OK;
+	if (!means3D || !shs || !campos || !radii || !geom_buffer) return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	if (M <= 0 || (D + 1) * (D + 1) > M || D < 0 || D > 3) return fail(OGS_ERR_INVALID_ARG, "SH degree / coefficient count mismatch");
+	GeomState g = GeomState::carve(geom_buffer, P);
+	return launch_sh_colors(P, D, M, means3D, shs, campos, radii, g.g1, g.gb, g.clamped, (cudaStream_t)stream);
+}
+
 // Backward, part 1: zero the packed accumulators and replay the blend (render backward).
+OGS_API int ogs_lonlat_backward_render_into(
+	int P, int64_t num_rendered, int W, int H, const float* background,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, const float* dL_dpix, float* grad_acc, void* stream);
+
 OGS_API int ogs_lonlat_backward_render(
 	int P, int64_t num_rendered, int W, int H, const float* background,
 	char* geom_buffer, char* binning_buffer, char* img_buffer, const float* dL_dpix, void* stream)
+{
+	return ogs_lonlat_backward_render_into(P, num_rendered, W, H, background, geom_buffer, binning_buffer, img_buffer,
+	                                       dL_dpix, nullptr, stream);
+}
+
+// grad_acc: NULL = the accumulators inside geom_buffer; else a caller-owned [P,12] float array (e.g. in symmetric memory,
+// so that latitude-band ranks can sum it with ogs_peer_allreduce / ogs_multimem_allreduce)
+OGS_API int ogs_lonlat_backward_render_into(
+	int P, int64_t num_rendered, int W, int H, const float* background,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, const float* dL_dpix, float* grad_acc, void* stream)
 {
 	cudaStream_t st = (cudaStream_t)stream;
 	if (P < 0 || num_rendered < 0) return fail(OGS_ERR_INVALID_ARG, "bad P / num_rendered");
@@ -461,30 +537,42 @@ OGS_API int ogs_lonlat_backward_render(
 	ImageState img = ImageState::carve(img_buffer, W, H);
 	BinningState b{};
 	if (num_rendered > 0) b = BinningState::carve(binning_buffer, num_rendered, W, H);
-	OGS_CUDA_TRY(cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * (size_t)P, st));
+	if (grad_acc && (reinterpret_cast<uintptr_t>(grad_acc) & 15u)) return fail(OGS_ERR_INVALID_ARG, "grad_acc must be 16-byte aligned");
+	float* acc = grad_acc ? grad_acc : g.grad_acc;
+	OGS_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(float) * 12 * (size_t)P, st));
 	prof_begin(OGS_PROF_RENDER_BWD, st);
 	if (int rc = launch_render_bwd(img.ranges, b.point_list, W, H, background, g.g0, g.g1, g.gb, g.scalars,
-	                               img.final_T, img.n_contrib, dL_dpix, g.grad_acc, st)) return rc;
+	                               img.final_T, img.n_contrib, dL_dpix, acc, st)) return rc;
 	prof_end(OGS_PROF_RENDER_BWD, st);
 	return OGS_OK;
 }
 
 // Backward, part 2: the fused per-Gaussian backward from the (possibly all-reduced) accumulators.
-OGS_API int ogs_lonlat_backward_finish(
+struct FinishExtras {            // multi-view / data-parallel mode and external accumulators (all optional)
+	const float* grad_acc = nullptr;
+	int accumulate = 0;
+	float* dL_drgb_view = nullptr;
+	float* stat_grad_norm = nullptr;
+	float* stat_visible = nullptr;
+	float* stat_max_radius = nullptr;
+};
+static int backward_finish_impl(
 	int P, int D, int M, int W, int H,
 	const float* means3D, const float* shs, const float* scales, float scale_modifier, const float* rotations,
 	const float* cov3D_precomp, const float* viewmatrix, const float* campos, const int* radii, char* geom_buffer,
 	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
-	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream)
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, const FinishExtras& x, cudaStream_t st)
 {
-	cudaStream_t st = (cudaStream_t)stream;
 	if (P < 0) return fail(OGS_ERR_INVALID_ARG, "bad P");
 	if (P == 0) return OGS_OK;
 	if (int rc = check_image(W, H)) return rc;
-	if (!means3D || !viewmatrix || !campos || !radii || !geom_buffer ||
-	    !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot)
+	if (!means3D || !viewmatrix || !campos || !radii || !geom_buffer || !dL_dopacity || !dL_dmean3D || !dL_dscale || !dL_drot)
 		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
-	if (shs && M > 0 && !dL_dsh) return fail(OGS_ERR_INVALID_ARG, "dL_dsh is NULL");
+	if (shs && M > 0 && !dL_dsh && !x.dL_drgb_view) return fail(OGS_ERR_INVALID_ARG, "dL_dsh is NULL");
+	if (x.accumulate && shs && !x.dL_drgb_view)
+		return fail(OGS_ERR_INVALID_ARG, "accumulating views needs dL_drgb_view (dL/dsh is rebuilt by ogs_sh_gradient_from_views)");
+	if ((x.stat_grad_norm != nullptr) != (x.stat_visible != nullptr) || (x.stat_grad_norm != nullptr) != (x.stat_max_radius != nullptr))
+		return fail(OGS_ERR_INVALID_ARG, "give all three statistics arrays or none");
 	if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
 		return fail(OGS_ERR_INVALID_ARG, "exactly one of (scales, rotations) / cov3D_precomp must be given");
 	GeomState g = GeomState::carve(geom_buffer, P);
@@ -492,15 +580,96 @@ OGS_API int ogs_lonlat_backward_finish(
 	a.P = P; a.D = D; a.M = shs ? M : 0; a.W = W; a.H = H; a.scale_modifier = scale_modifier;
 	a.means3D = means3D; a.shs = shs; a.scales = scales; a.rotations = rotations;
 	a.cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
-	a.viewmatrix = viewmatrix; a.campos = campos; a.radii = radii; a.clamped = g.clamped; a.grad_acc = g.grad_acc;
+	a.viewmatrix = viewmatrix; a.campos = campos; a.radii = radii; a.clamped = g.clamped;
+	a.grad_acc = x.grad_acc ? x.grad_acc : g.grad_acc;
 	a.g0 = g.g0; a.g1 = g.g1;
 	a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
 	a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = shs ? dL_dsh : nullptr;
 	a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
+	a.accumulate = x.accumulate; a.dL_drgb_view = shs ? x.dL_drgb_view : nullptr;
+	a.stat_grad_norm = x.stat_grad_norm; a.stat_visible = x.stat_visible; a.stat_max_radius = x.stat_max_radius;
 	prof_begin(OGS_PROF_PREPROCESS_BWD, st);
 	const int rc = launch_preprocess_bwd(a, st);
 	prof_end(OGS_PROF_PREPROCESS_BWD, st);
 	return rc;
+}
+
+OGS_API int ogs_lonlat_backward_finish(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* campos, const int* radii, char* geom_buffer,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream)
+{
+	if (P > 0 && (!dL_dmean2D || !dL_dcolor || !dL_dcov3D)) return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	return backward_finish_impl(P, D, M, W, H, means3D, shs, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
+	                            campos, radii, geom_buffer, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D,
+	                            dL_dcov3D, dL_dsh, dL_dscale, dL_drot, FinishExtras{}, (cudaStream_t)stream);
+}
+
+// ..._finish from caller-owned accumulators (see ogs_lonlat_backward_render_into)
+OGS_API int ogs_lonlat_backward_finish_from(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* campos, const int* radii, char* geom_buffer,
+	const float* grad_acc,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream)
+{
+	if (P > 0 && (!dL_dmean2D || !dL_dcolor || !dL_dcov3D || !grad_acc)) return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	FinishExtras x;
+	x.grad_acc = grad_acc;
+	return backward_finish_impl(P, D, M, W, H, means3D, shs, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
+	                            campos, radii, geom_buffer, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D,
+	                            dL_dcov3D, dL_dsh, dL_dscale, dL_drot, x, (cudaStream_t)stream);
+}
+
+// One view of a multi-view / data-parallel training step: render backward, then the per-Gaussian
+// backward ADDS (accumulate != 0) or writes (== 0, the step's first view) the four geometry gradients and the view's
+// densification statistics into the step's bucket and leaves the view's clamp-masked dL/dRGB factor [P,3] instead of a
+// 192-byte dL/dsh row; ogs_sh_gradient_from_views rebuilds dL/dsh once per step from all views' factors.
+OGS_API int ogs_lonlat_backward_view(
+	int P, int D, int M, int64_t num_rendered, int W, int H, const float* background,
+	const float* means3D, const float* shs, const float* scales, float scale_modifier, const float* rotations,
+	const float* viewmatrix, const float* campos, const int* radii,
+	char* geom_buffer, char* binning_buffer, char* img_buffer, const float* dL_dpix,
+	int accumulate, float* dL_dmean3D, float* dL_dopacity, float* dL_dscale, float* dL_drot,
+	float* dL_drgb_view, float* stat_grad_norm, float* stat_visible, float* stat_max_radius,
+	float* dL_dmean2D, void* stream)
+{
+	if (P > 0 && (!shs || !dL_drgb_view || !scales || !rotations))
+		return fail(OGS_ERR_INVALID_ARG, "the view backward needs shs, scales, rotations and dL_drgb_view");
+	if (int rc = ogs_lonlat_backward_render(P, num_rendered, W, H, background, geom_buffer, binning_buffer, img_buffer,
+	                                        dL_dpix, stream)) return rc;
+	FinishExtras x;
+	x.accumulate = accumulate ? 1 : 0; x.dL_drgb_view = dL_drgb_view;
+	x.stat_grad_norm = stat_grad_norm; x.stat_visible = stat_visible; x.stat_max_radius = stat_max_radius;
+	return backward_finish_impl(P, D, M, W, H, means3D, shs, scales, scale_modifier, rotations, nullptr, viewmatrix, campos,
+	                            radii, geom_buffer, dL_dmean2D, nullptr, dL_dopacity, nullptr, dL_dmean3D, nullptr, nullptr,
+	                            dL_dscale, dL_drot, x, (cudaStream_t)stream);
+}
+
+// dL/dsh [P,16,3] (or the split dL/dfeatures_dc + dL/dfeatures_rest) of a whole step from the views' dL/dRGB factors.
+// campos_views: device, n_views x 3; dL_drgb_views: HOST array of n_views device pointers (each [P,3]; may be peer memory).
+OGS_API int ogs_sh_gradient_from_views(
+	int P, int D, int M, int n_views, const float* means3D, const float* campos_views, const float* const* dL_drgb_views,
+	float* dL_dsh, float* dL_dfeatures_dc, float* dL_dfeatures_rest, void* stream)
+{
+	if (P < 0 || n_views < 1 || n_views > kMaxStepViews) return fail(OGS_ERR_INVALID_ARG, "1 <= n_views <= 16");
+	if (P == 0) return OGS_OK;
+	if (M != 16 || D < 0 || D > 3) return fail(OGS_ERR_INVALID_ARG, "ogs_sh_gradient_from_views needs M == 16, 0 <= D <= 3");
+	if (!means3D || !campos_views || !dL_drgb_views) return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	if ((dL_dsh != nullptr) == (dL_dfeatures_dc != nullptr || dL_dfeatures_rest != nullptr) || (!dL_dsh && (!dL_dfeatures_dc || !dL_dfeatures_rest)))
+		return fail(OGS_ERR_INVALID_ARG, "give dL_dsh or (dL_dfeatures_dc, dL_dfeatures_rest)");
+	if (dL_dsh && (reinterpret_cast<uintptr_t>(dL_dsh) & 15u)) return fail(OGS_ERR_INVALID_ARG, "dL_dsh must be 16-byte aligned");
+	ShFromViewsArgs a{};
+	a.P = P; a.D = D; a.M = M; a.n_views = n_views; a.means3D = means3D; a.campos = campos_views;
+	for (int v = 0; v < n_views; v++) {
+		if (!dL_drgb_views[v]) return fail(OGS_ERR_INVALID_ARG, "a view's dL_drgb pointer is NULL");
+		a.drgb[v] = dL_drgb_views[v];
+	}
+	a.dL_dsh = dL_dsh; a.dL_dfeatures_dc = dL_dfeatures_dc; a.dL_dfeatures_rest = dL_dfeatures_rest;
+	return launch_sh_gradient_from_views(a, (cudaStream_t)stream);
 }
 
 // Byte offset of the packed render-backward accumulators ([P,12] float, raw sums over pixels: u*dx, u*dy,
@@ -606,7 +775,7 @@ OGS_API int ogs_lonlat_forward_raw_stage1(
 	const float* viewmatrix, const float* campos,
 	int* radii, char* geom_buffer, char* img_buffer, int64_t* num_rendered_host, void* stream)
 {
-	if (P > 0 && (!features_dc || !features_rest)) return fail(OGS_ERR_INVALID_ARG, "features_dc / features_rest are NULL");
+	if (P > 0 && (!features_dc || (M > 1 && !features_rest))) return fail(OGS_ERR_INVALID_ARG, "features_dc / features_rest are NULL");
 	const int gy = H > 0 ? ceil_div(H, kTile) : 0;
 	return forward_stage1_impl(P, D, M, W, H, 0, gy, xyz, nullptr, nullptr, opacity_raw, scaling_raw, scale_modifier,
 	                           rotation_raw, nullptr, viewmatrix, campos, radii, geom_buffer, img_buffer,
@@ -626,10 +795,10 @@ OGS_API int ogs_lonlat_backward_raw(
 	if (int rc = ogs_lonlat_backward_render(P, num_rendered, W, H, background, geom_buffer, binning_buffer,
 	                                        img_buffer, dL_dpix, stream)) return rc;
 	if (P == 0) return OGS_OK;
-	if (!xyz || !features_dc || !features_rest || !scaling_raw || !rotation_raw || !viewmatrix || !campos || !radii ||
-	    !dL_dxyz || !dL_dfeatures_dc || !dL_dfeatures_rest || !dL_dopacity_raw || !dL_dscaling_raw || !dL_drotation_raw)
+	if (!xyz || !features_dc || (M > 1 && !features_rest) || !scaling_raw || !rotation_raw || !viewmatrix || !campos || !radii ||
+	    !dL_dxyz || !dL_dfeatures_dc || (M > 1 && !dL_dfeatures_rest) || !dL_dopacity_raw || !dL_dscaling_raw || !dL_drotation_raw)
 		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
-	if (M < 2 || (D + 1) * (D + 1) > M || D < 0 || D > 3) return fail(OGS_ERR_INVALID_ARG, "SH degree / coefficient count mismatch");
+	if (M < 1 || (D + 1) * (D + 1) > M || D < 0 || D > 3) return fail(OGS_ERR_INVALID_ARG, "SH degree / coefficient count mismatch");
 	GeomState g = GeomState::carve(geom_buffer, P);
 	PreprocessBwdArgs a{};
 	a.P = P; a.D = D; a.M = M; a.W = W; a.H = H; a.scale_modifier = scale_modifier;
@@ -706,6 +875,35 @@ OGS_API int ogs_multimem_allreduce_sum(float* multicast, int world, int rank, si
 	return launch_multimem_allreduce_sum(multicast, world, rank, count, (cudaStream_t)stream);
 }
 
+OGS_API int ogs_peer_allreduce(float* const* bufs, int world, int rank, size_t count_sum, size_t count_max, void* stream)
+{
+	if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(OGS_ERR_INVALID_ARG, "1 <= world <= 8, 0 <= rank < world");
+	if (!bufs || (count_sum & 3u) || (count_max & 3u)) return fail(OGS_ERR_INVALID_ARG, "counts must be multiples of 4 floats");
+	for (int r = 0; r < world; r++)
+		if (!bufs[r] || (reinterpret_cast<uintptr_t>(bufs[r]) & 15u)) return fail(OGS_ERR_INVALID_ARG, "peer buffers must be 16-byte aligned");
+	return launch_peer_allreduce(bufs, world, rank, count_sum, count_max, (cudaStream_t)stream);
+}
+
+OGS_API int ogs_multimem_allreduce(float* multicast, int world, int rank, size_t count_sum, size_t count_max, void* stream)
+{
+	if (world < 1 || rank < 0 || rank >= world) return fail(OGS_ERR_INVALID_ARG, "0 <= rank < world");
+	if (!multicast || (reinterpret_cast<uintptr_t>(multicast) & 15u) || (count_sum & 3u))
+		return fail(OGS_ERR_INVALID_ARG, "multicast pointer must be 16-byte aligned, count_sum a multiple of 4 floats");
+	return launch_multimem_allreduce(multicast, world, rank, count_sum, count_max, (cudaStream_t)stream);
+}
+
+OGS_API int ogs_band_rows_allgather(float* const* images, int world, int rank, const float* src, int W, int H,
+                                    int y0, int y1, void* stream)
+{
+	if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(OGS_ERR_INVALID_ARG, "1 <= world <= 8, 0 <= rank < world");
+	if (int rc = check_image(W, H)) return rc;
+	if (!images || !src || y0 < 0 || y1 > H || y1 < y0) return fail(OGS_ERR_INVALID_ARG, "bad band rows");
+	for (int r = 0; r < world; r++)
+		if (!images[r] || (reinterpret_cast<uintptr_t>(images[r]) & 15u)) return fail(OGS_ERR_INVALID_ARG, "images must be 16-byte aligned");
+	if (reinterpret_cast<uintptr_t>(src) & 15u) return fail(OGS_ERR_INVALID_ARG, "src must be 16-byte aligned");
+	return launch_band_rows_allgather(images, world, src, W, H, y0, y1, (cudaStream_t)stream);
+}
+
 OGS_API int ogs_view_stats(int P, const int* radii, const float* dL_dmean2D, float* grad_norm, float* visible,
                            float* radius, void* stream)
 {
@@ -769,46 +967,6 @@ OGS_API int ogs_export_binning(
 		if (point_list_keys)
 			if (int rc = launch_rebuild_keys(img, b, g, W, H, point_list_keys, st)) return rc;
 	}
-	return OGS_OK;
-}
-
-OGS_API int ogs_lonlat_train_view_host(
-	int P, int D, int M, int W, int H,
-	const float* background,
-	const float* means3D, const float* shs, const float* opacities,
-	const float* scales, float scale_modifier, const float* rotations,
-	const float* viewmatrix_host, const float* campos_host, const float* dL_dpix_host,
-	float* view_scratch, float* dL_dpix_dev,
-	int* radii, char* geom_buffer, char* binning_buffer, size_t binning_capacity, char* img_buffer,
-	float* out_color_dev, float* out_color_host,
-	float* dL_dmean2D, float* dL_dopacity, float* dL_dcolor,
-	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
-	int64_t* num_rendered_host, size_t* binning_needed, void* stream)
-{
-	cudaStream_t st = (cudaStream_t)stream;
-	if (!viewmatrix_host || !campos_host || !dL_dpix_host || !view_scratch || !dL_dpix_dev || !out_color_dev ||
-	    !out_color_host || !num_rendered_host)
-		return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
-	if (int rc = check_image(W, H)) return rc;
-	const size_t img_bytes = sizeof(float) * 3 * (size_t)W * H;
-	OGS_CUDA_TRY(cudaMemcpyAsync(view_scratch, viewmatrix_host, sizeof(float) * 16, cudaMemcpyHostToDevice, st));
-	OGS_CUDA_TRY(cudaMemcpyAsync(view_scratch + 16, campos_host, sizeof(float) * 3, cudaMemcpyHostToDevice, st));
-	OGS_CUDA_TRY(cudaMemcpyAsync(dL_dpix_dev, dL_dpix_host, img_bytes, cudaMemcpyHostToDevice, st));
-	if (int rc = ogs_lonlat_forward_stage1(P, D, M, W, H, means3D, shs, nullptr, opacities, scales, scale_modifier,
-	                                       rotations, nullptr, view_scratch, view_scratch + 16, radii, geom_buffer,
-	                                       img_buffer, num_rendered_host, stream)) return rc;
-	const size_t need = ogs_binning_bytes(*num_rendered_host, W, H);
-	if (binning_needed) *binning_needed = need;
-	if (need > binning_capacity) return fail(OGS_ERR_INVALID_ARG, "binning_buffer too small (see *binning_needed)");
-	if (int rc = ogs_lonlat_forward_stage2(P, W, H, *num_rendered_host, background, geom_buffer, binning_buffer,
-	                                       img_buffer, out_color_dev, stream)) return rc;
-	OGS_CUDA_TRY(cudaMemcpyAsync(out_color_host, out_color_dev, img_bytes, cudaMemcpyDeviceToHost, st));
-	if (int rc = ogs_lonlat_backward(P, D, M, *num_rendered_host, W, H, background, means3D, shs, nullptr, scales,
-	                                 scale_modifier, rotations, nullptr, view_scratch, view_scratch + 16, radii,
-	                                 geom_buffer, binning_buffer, img_buffer, dL_dpix_dev, dL_dmean2D, nullptr,
-	                                 dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot,
-	                                 stream)) return rc;
-	OGS_CUDA_TRY(cudaStreamSynchronize(st));
 	return OGS_OK;
 }
 

@@ -20,6 +20,9 @@ struct PreprocessFwdArgs {
 	int raw;
 	const float* features_dc;
 	const float* features_rest;
+	// defer_colors != 0: geometry only — colours and clamp masks are filled in later by launch_sh_colors (the data-parallel
+	// trainer overlaps the exchange of the SH gradients with this kernel, the depth order and the tile sort)
+	int defer_colors;
 	// perspective camera (pinhole != 0): full projection matrix, focal lengths in pixels, tan(fov/2)
 	int pinhole, render_depth;
 	const float* projmatrix;
@@ -75,8 +78,33 @@ struct PreprocessBwdArgs {
 	float* dL_dsh;
 	float* dL_dscale;
 	float* dL_drot;
+	// multi-view / data-parallel mode: accumulate != 0 ADDS this view to dL_dmean3D / dL_dopacity /
+	// dL_dscale / dL_drot and to the statistics; dL_drgb_view != NULL replaces the dL/dsh (dL/dfeatures) row by the
+	// view's clamp-masked dL/dRGB [P,3] (see launch_sh_gradient_from_views); stat_* (all three or none): the view's
+	// densification statistics (sum of |dL_dmean2D.xy|, visibility count, max radius as float)
+	int accumulate;
+	float* dL_drgb_view;
+	float* stat_grad_norm;
+	float* stat_visible;
+	float* stat_max_radius;
 };
+// dL/dsh [P,M,3] (or split dL/dfeatures_dc [P,1,3] + dL/dfeatures_rest [P,M-1,3]) = sum over views, in view order, of
+// b_k(direction from the view's camera centre) * dL/dRGB_view.  drgb[v] may point into a peer GPU's memory.
+constexpr int kMaxStepViews = 16;
+struct ShFromViewsArgs {
+	int P, D, M, n_views;
+	const float* means3D;
+	const float* campos;                 // n_views x 3 (device)
+	const float* drgb[kMaxStepViews];    // each [P,3]
+	float* dL_dsh;                       // [P,M,3] or NULL
+	float* dL_dfeatures_dc;              // split layout (raw-parameter trainer) when dL_dsh is NULL
+	float* dL_dfeatures_rest;
+};
+int launch_sh_gradient_from_views(const ShFromViewsArgs& a, cudaStream_t st);
 int launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t st);
+// SH -> RGB + clamp mask of every Gaussian with radii > 0 into the packed records (forward.cu:688-692 with :30-83)
+int launch_sh_colors(int P, int D, int M, const float* means3D, const float* shs, const float* campos, const int* radii,
+                     float4* g1, float2* gb, uint8_t* clamped, cudaStream_t st);
 int launch_mark_all_visible(int P, uint8_t* present, cudaStream_t st);
 int launch_check_frustum(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
 int launch_depth_order(const GeomState& g, int P, cudaStream_t st);
@@ -122,8 +150,13 @@ int launch_view_stats(int P, const int* radii, const float* dL_dmean2D, float* g
                       cudaStream_t st);
 // ---- peer_collective.cu
 constexpr int kMaxPeers = 8;
+// the first count_sum floats are summed, the count_max floats behind them (non-negative: ordered like their bit patterns)
+// are max-reduced
 int launch_peer_allreduce_sum(float* const* bufs, int world, int rank, size_t count, cudaStream_t st);
 int launch_multimem_allreduce_sum(float* multicast, int world, int rank, size_t count, cudaStream_t st);
+int launch_peer_allreduce(float* const* bufs, int world, int rank, size_t count_sum, size_t count_max, cudaStream_t st);
+int launch_multimem_allreduce(float* multicast, int world, int rank, size_t count_sum, size_t count_max, cudaStream_t st);
+int launch_band_rows_allgather(float* const* images, int world, const float* src, int W, int H, int y0, int y1, cudaStream_t st);
 int launch_densify_stats(int P, const int* radii, const float* dL_dmean2D, float* max_radii2D,
                          float* xyz_gradient_accum, float* denom, cudaStream_t st);
 

@@ -65,7 +65,7 @@ struct GeomState {               // per-Gaussian, P-sized
 	uint32_t* emit_offset;       // P+1: exclusive prefix of tiles_touched in depth order
 	uint32_t* depth_hist;        // 4 x 256 digit counts for the depth sort
 	uint32_t* depth_status;      // decoupled look-back status words for the 4 depth passes
-	uint32_t* scan_status;       // look-back status for the emit-offset scan
+	unsigned long long* scan_status; // look-back status for the emit-offset scan (64-bit words: sums up to 2^31-1)
 	float* grad_acc;             // 12 per Gaussian: render-backward accumulators (zeroed by backward)
 	unsigned long long* scalars; // [0] = sum tiles_touched (num_rendered), [1..] tickets/counters
 	size_t scalars_bytes;

@@ -4,7 +4,7 @@
 // (depth key, pixel position, conic, radius, tile rect) is written with explicit round-to-nearest intrinsics in
 // the operation order of the reference's compiled preprocessCUDA (cuda_rasterizer/forward.cu:232-340, read off
 // its sm_100 SASS): sums of three products are fma(a2,b2, fma(a0,b0, mul(a1,b1))), `/` is an IEEE division,
-// 1/x an IEEE reciprocal.  The backward (backward.cu:156-292, :558-608) is tolerance-bound only.
+// 1/x an IEEE reciprocal.  The backward (backward.cu:156-292, :558-608) is tolerance-bound: gaussian_grad.cuh.
 #pragma once
 #include "lonlat_math.cuh"
 
@@ -23,7 +23,10 @@ OGS_D float4 proj_point_p(const float* M, float3 p)
 
 // The perspective Jacobian with the reference's frustum clamp (forward.cu:94-108 / backward.cu:179-196).
 // t is the camera-space mean; on return t.x, t.y hold the clamped values the Jacobian was evaluated at.
-OGS_D LonlatJac pinhole_jacobian_p(float3& t, float focal_x, float focal_y, float tan_fovx, float tan_fovy,
+struct PinholeJac {   // the four non-zero entries of d(pixel)/d(t)
+	float j00, j02, j11, j12;
+};
+OGS_D PinholeJac pinhole_jacobian_p(float3& t, float focal_x, float focal_y, float tan_fovx, float tan_fovy,
                                    float& x_grad_mul, float& y_grad_mul)
 {
 	const float limx = __fmul_rn(1.3f, tan_fovx);
@@ -35,10 +38,9 @@ OGS_D LonlatJac pinhole_jacobian_p(float3& t, float focal_x, float focal_y, floa
 	x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
 	y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
 	const float tzz = __fmul_rn(t.z, t.z);
-	LonlatJac J;
+	PinholeJac J;
 	J.j00 = __fdiv_rn(focal_x, t.z);
 	J.j02 = __fdiv_rn(-__fmul_rn(focal_x, t.x), tzz);
-	J.j10 = 0.0f;
 	J.j11 = __fdiv_rn(focal_y, t.z);
 	J.j12 = __fdiv_rn(-__fmul_rn(focal_y, t.y), tzz);
 	return J;
@@ -50,7 +52,7 @@ OGS_D float3 cov2d_pinhole_p(float3 t, const float* V, const float* c6, float fo
                              float tan_fovx, float tan_fovy)
 {
 	float gx, gy;
-	const LonlatJac J = pinhole_jacobian_p(t, focal_x, focal_y, tan_fovx, tan_fovy, gx, gy);
+	const PinholeJac J = pinhole_jacobian_p(t, focal_x, focal_y, tan_fovx, tan_fovy, gx, gy);
 	float T0[3], T1[3];
 #pragma unroll
 	for (int k = 0; k < 3; k++) {
@@ -69,42 +71,6 @@ OGS_D float3 cov2d_pinhole_p(float3 t, const float* V, const float* c6, float fo
 	cov.y = dot3p(p01, T0[0], p11, T0[1], p21, T0[2]);
 	cov.z = __fadd_rn(dot3p(p01, T1[0], p11, T1[1], p21, T1[2]), 0.3f);
 	return cov;
-}
-
-// computeCov2DCUDA (backward.cu:156-292): dL/dconic -> dL/dcov3D and the covariance branch of dL/dmean.
-OGS_D void cov2d_pinhole_backward(float3 mean, const float* cov6, const float* V, float focal_x, float focal_y,
-                                  float tan_fovx, float tan_fovy, float3 dL_dconic, float* dL_dcov6, float3& dL_dmean)
-{
-	float3 t = view_point(V, mean);
-	float x_grad_mul, y_grad_mul;
-	const LonlatJac Jv = pinhole_jacobian_p(t, focal_x, focal_y, tan_fovx, tan_fovy, x_grad_mul, y_grad_mul);
-	float dL_dJ00, dL_dJ02, dL_dJ10, dL_dJ11, dL_dJ12;
-	conic_to_cov3d_and_jacobian_backward(Jv, V, cov6, dL_dconic, dL_dcov6, dL_dJ00, dL_dJ02, dL_dJ10, dL_dJ11, dL_dJ12);
-	const float tz = 1.f / t.z;
-	const float tz2 = tz * tz;
-	const float tz3 = tz2 * tz;
-	// backward.cu:276-283
-	const float dL_dtx = x_grad_mul * -focal_x * tz2 * dL_dJ02;
-	const float dL_dty = y_grad_mul * -focal_y * tz2 * dL_dJ12;
-	const float dL_dtz = -focal_x * tz2 * dL_dJ00 - focal_y * tz2 * dL_dJ11 + (2 * focal_x * t.x) * tz3 * dL_dJ02 +
-	                     (2 * focal_y * t.y) * tz3 * dL_dJ12;
-	dL_dmean = view_vec_t(V, float3{ dL_dtx, dL_dty, dL_dtz });
-}
-
-// Screen-position branch of dL/dmean through the full projection (backward.cu:583-597).
-OGS_D float3 proj_point_backward(const float* proj, float3 m, float dL_dx, float dL_dy)
-{
-	const float4 m_hom = { proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12],
-	                       proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13], 0.f,
-	                       proj[3] * m.x + proj[7] * m.y + proj[11] * m.z + proj[15] };
-	const float m_w = 1.0f / (m_hom.w + kEps7);
-	const float mul1 = m_hom.x * m_w * m_w;
-	const float mul2 = m_hom.y * m_w * m_w;
-	float3 d;
-	d.x = (proj[0] * m_w - proj[3] * mul1) * dL_dx + (proj[1] * m_w - proj[3] * mul2) * dL_dy;
-	d.y = (proj[4] * m_w - proj[7] * mul1) * dL_dx + (proj[5] * m_w - proj[7] * mul2) * dL_dy;
-	d.z = (proj[8] * m_w - proj[11] * mul1) * dL_dx + (proj[9] * m_w - proj[11] * mul2) * dL_dy;
-	return d;
 }
 
 } // namespace ogs

@@ -20,7 +20,13 @@
 // (sigmoid / exp / normalize / cat, gaussian_model.cpp:54-77), i.e. the kernel returns what LibTorch's
 // autograd would deliver to the optimiser's six parameter tensors (xyz_, features_dc_, features_rest_,
 // opacity_, scaling_, rotation_), and the dL/dfeatures rows of the CTA leave as two bulk stores.
+// Data-parallel / multi-view mode (PreprocessBwdArgs::accumulate, dL_drgb_view, stat_*): the four
+// geometry gradients are ADDED to what the step's bucket already holds, the densification statistics of the view
+// (gaussian_mapper.cpp:427-434) are folded in by the same thread, and instead of the 192-byte dL/dsh row the kernel
+// leaves the view's clamp-masked dL/dRGB (12 bytes): dL/dsh = sum over views of b(dir_view) (x) dL/dRGB_view is rebuilt
+// once per step by sh_gradient_from_views_kernel below, bit-identical to the sum of the per-view rows in view order.
 #include "pinhole_math.cuh"
+#include "gaussian_grad.cuh"
 #include "launchers.cuh"
 #include "async_copy.cuh"
 
@@ -37,6 +43,7 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 	constexpr bool kRaw = (kMode >= 2);
 	__shared__ float sV[16];
 	__shared__ float sCam[3];
+	__shared__ float sP[kPinhole ? 16 : 1];
 	__shared__ __align__(16) float s_sh[kBulkSH ? kPreBwdThreads * kShPitchFloats : 4];
 	__shared__ __align__(8) uint64_t s_bar;
 	__shared__ __align__(8) uint64_t s_rows_done;   // raw mode: counts the CTA's gradient rows written to shared memory
@@ -44,6 +51,7 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 	const int idx = blockIdx.x * kPreBwdThreads + tid;
 	if (tid < 16) sV[tid] = a.viewmatrix[tid];
 	if (tid < 3) sCam[tid] = a.campos[tid];
+	if (kPinhole && tid < 16) sP[tid] = a.projmatrix[tid];
 	const int rows = min(kPreBwdThreads, a.P - (int)blockIdx.x * kPreBwdThreads);
 	const int rows4 = rows & ~3;   // raw mode: rows covered by the per-CTA bulk copies (sizes stay multiples of 16 B)
 	if (kBulkSH && tid == 0) {
@@ -76,7 +84,9 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 		return;
 	}
 
-	const bool visible = a.radii[idx] > 0;
+	const int radius = a.radii[idx];
+	const bool visible = radius > 0;
+	const bool write_sh = a.dL_drgb_view == nullptr;   // data-parallel mode leaves dL/dRGB instead of the dL/dsh row
 
 	float g[9];
 	if (visible) {
@@ -96,160 +106,166 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 		for (int k = 0; k < 9; k++) g[k] = 0.f;
 	}
 
-	// the render-backward outputs in the reference's layouts
-	if (!kRaw || a.dL_dmean2D) {
+	// the render-backward outputs in the reference's layouts (all optional)
+	if (a.dL_dmean2D) {
 		a.dL_dmean2D[3 * (size_t)idx + 0] = g[0];
 		a.dL_dmean2D[3 * (size_t)idx + 1] = g[1];
 		a.dL_dmean2D[3 * (size_t)idx + 2] = 0.f;
 	}
 	if (a.dL_dconic) reinterpret_cast<float4*>(a.dL_dconic)[idx] = make_float4(g[2], g[3], 0.f, g[4]);
+	float dopacity = g[5];
 	if constexpr (kRaw) {
 		// d sigmoid: the activated opacity is in the packed record (gaussian_model.cpp:74-77)
 		const float o = visible ? a.g1[idx].y : 0.f;
-		a.dL_dopacity[idx] = g[5] * o * (1.f - o);
-	} else {
-		a.dL_dopacity[idx] = g[5];
+		dopacity = g[5] * o * (1.f - o);
+	} else if (a.dL_dcolor) {
 		a.dL_dcolor[3 * (size_t)idx + 0] = g[6];
 		a.dL_dcolor[3 * (size_t)idx + 1] = g[7];
 		a.dL_dcolor[3 * (size_t)idx + 2] = g[8];
 	}
+	// densification statistics of this view (gaussian_mapper.cpp:427-434, gaussian_model.cpp:839-853)
+	if (a.stat_grad_norm) {
+		const float gn = visible ? sqrtf(g[0] * g[0] + g[1] * g[1]) : 0.f;
+		const float one = visible ? 1.f : 0.f, rad = (float)radius;
+		if (a.accumulate) {
+			a.stat_grad_norm[idx] += gn;
+			a.stat_visible[idx] += one;
+			a.stat_max_radius[idx] = fmaxf(a.stat_max_radius[idx], rad);
+		} else {
+			a.stat_grad_norm[idx] = gn;
+			a.stat_visible[idx] = one;
+			a.stat_max_radius[idx] = rad;
+		}
+	}
 
 	float dcov6[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
 	float3 dmean = { 0.f, 0.f, 0.f };
-	float3 dscale = { 0.f, 0.f, 0.f };
-	float4 drot = { 0.f, 0.f, 0.f, 0.f };
-	float* dsh_row = (!kRaw && a.dL_dsh) ? a.dL_dsh + (size_t)idx * a.M * 3 : nullptr;
+	float dscale[3] = { 0.f, 0.f, 0.f };
+	float drot[4] = { 0.f, 0.f, 0.f, 0.f };
+	float drgb[3] = { 0.f, 0.f, 0.f };
+	float* dsh_row = (!kRaw && a.dL_dsh && write_sh) ? a.dL_dsh + (size_t)idx * a.M * 3 : nullptr;
 	bool sh_waited = false, sh_row_ready = false;
 
 	if (visible) {
 		float V[16];
 #pragma unroll
 		for (int i = 0; i < 16; i++) V[i] = sV[i];
-		const float3 mean = { a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2] };
+		const grad::Vec3<float> mean = { a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2] };
 		float cov6[6];
 #pragma unroll
 		for (int i = 0; i < 6; i++) cov6[i] = a.cov3D[6 * (size_t)idx + i];
 
+		// covariance / conic branch and screen-position branch (backward.cu:297-485 + :642-660; pinhole :156-292 + :583-597)
+		// in our own chain-rule form: gaussian_grad.cuh
+		float Pm[16];
 		if constexpr (kPinhole) {
-			// covariance / conic branch (backward.cu:156-292), then the screen position through the full
-			// projection (backward.cu:583-597)
-			cov2d_pinhole_backward(mean, cov6, V, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy,
-			                       float3{ g[2], g[3], g[4] }, dcov6, dmean);
-			const float3 dm2 = proj_point_backward(a.projmatrix, mean, g[0], g[1]);
-			dmean.x += dm2.x; dmean.y += dm2.y; dmean.z += dm2.z;
-		} else {
-			// covariance / conic branch (backward.cu:297-485); assigns dL/dmean
-			float3 dpx_dt, dpy_dt;
-			cov2d_lonlat_backward(mean, cov6, V, a.W, a.H, float3{ g[2], g[3], g[4] }, dcov6, dmean, dpx_dt, dpy_dt);
-
-			// screen-position branch (backward.cu:642-660)
-			const float dsx_dpx = 2.0f / (float)a.W;
-			const float dsy_dpy = 2.0f / (float)a.H;
-			const float dL_dpx = g[0] * dsx_dpx;
-			const float dL_dpy = g[1] * dsy_dpy;
-			const float dL_dtx = dL_dpx * dpx_dt.x + dL_dpy * dpy_dt.x;
-			const float dL_dty = dL_dpx * dpx_dt.y + dL_dpy * dpy_dt.y;
-			const float dL_dtz = dL_dpx * dpx_dt.z + dL_dpy * dpy_dt.z;
-			const float3 dm2 = view_vec_t(V, float3{ dL_dtx, dL_dty, dL_dtz });
-			dmean.x += dm2.x; dmean.y += dm2.y; dmean.z += dm2.z;
+#pragma unroll
+			for (int i = 0; i < 16; i++) Pm[i] = sP[i];
 		}
+		const grad::Vec3<float> dmp = grad::projection_backward<float, kPinhole>(
+			mean, cov6, V, Pm, a.W, a.H, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, g[0], g[1], g[2], g[3], g[4], dcov6);
+		dmean = { dmp.x, dmp.y, dmp.z };
 
-		// SH backward (backward.cu:30-151)
+		// colour branch (backward.cu:30-151)
 		if (kRaw || a.shs != nullptr) {
 			const unsigned cm = a.clamped[idx];
-			V3 dRGB = { g[6], g[7], g[8] };
-			dRGB.x *= (cm & 1u) ? 0 : 1;
-			dRGB.y *= (cm & 2u) ? 0 : 1;
-			dRGB.z *= (cm & 4u) ? 0 : 1;
-			float3 dm3;
-			if constexpr (kMode == 2) {
+			drgb[0] = (cm & 1u) ? 0.f : g[6];
+			drgb[1] = (cm & 2u) ? 0.f : g[7];
+			drgb[2] = (cm & 4u) ? 0.f : g[8];
+			const grad::Vec3<float> cam = { sCam[0], sCam[1], sCam[2] };
+			grad::Vec3<float> dm3;
+			if constexpr (kBulkSH) {
 				mbar_wait(&s_bar, 0);
 				sh_waited = true;
 				float shr[kShRowFloats], dshr[kShRowFloats];
+				if constexpr (kMode == 2) {
 #pragma unroll
-				for (int k = 0; k < 3; k++) shr[k] = s_sh[kRawDcOffset + tid * 3 + k];
+					for (int k = 0; k < 3; k++) shr[k] = s_sh[kRawDcOffset + tid * 3 + k];
 #pragma unroll
-				for (int k = 0; k < kRawRestFloats; k++) shr[3 + k] = s_sh[tid * kRawRestFloats + k];
+					for (int k = 0; k < kRawRestFloats; k++) shr[3 + k] = s_sh[tid * kRawRestFloats + k];
+				} else {
+					const float4* row = reinterpret_cast<const float4*>(&s_sh[tid * kShPitchFloats]);
 #pragma unroll
-				for (int k = 0; k < kShRowFloats; k++) dshr[k] = 0.f;
-				auto sh = [&shr](int k) { return V3{ shr[3 * k], shr[3 * k + 1], shr[3 * k + 2] }; };
-				auto dsh = [&dshr](int k, V3 v) { dshr[3 * k] = v.x; dshr[3 * k + 1] = v.y; dshr[3 * k + 2] = v.z; };
-				dm3 = sh_backward(a.D, mean, float3{ sCam[0], sCam[1], sCam[2] }, sh, dRGB, dsh);
+					for (int k = 0; k < kShRowFloats / 4; k++) {
+						const float4 q = row[k];
+						shr[4 * k] = q.x; shr[4 * k + 1] = q.y; shr[4 * k + 2] = q.z; shr[4 * k + 3] = q.w;
+					}
+				}
 #pragma unroll
-				for (int k = 0; k < 3; k++) s_sh[kRawDcOffset + tid * 3 + k] = dshr[k];
+				for (int k = 0; k < kShRowFloats; k++) dshr[k] = 0.f;   // rows beyond (D+1)^2 stay zero
+				auto sh = [&shr](int k, int c) { return shr[3 * k + c]; };
+				auto dsh = [&dshr](int k, int c, float v) { dshr[3 * k + c] = v; };
+				dm3 = grad::colour_backward<float>(a.D, mean, cam, sh, drgb, dsh);
+				if (write_sh) {
+					if constexpr (kMode == 2) {
 #pragma unroll
-				for (int k = 0; k < kRawRestFloats; k++) s_sh[tid * kRawRestFloats + k] = dshr[3 + k];
-				sh_row_ready = true;
+						for (int k = 0; k < 3; k++) s_sh[kRawDcOffset + tid * 3 + k] = dshr[k];
+#pragma unroll
+						for (int k = 0; k < kRawRestFloats; k++) s_sh[tid * kRawRestFloats + k] = dshr[3 + k];
+					} else {
+						float4* row = reinterpret_cast<float4*>(&s_sh[tid * kShPitchFloats]);
+#pragma unroll
+						for (int k = 0; k < kShRowFloats / 4; k++)
+							row[k] = make_float4(dshr[4 * k], dshr[4 * k + 1], dshr[4 * k + 2], dshr[4 * k + 3]);
+					}
+					sh_row_ready = true;
+				}
 			} else if constexpr (kMode == 3) {
 				const float* dc = a.features_dc + (size_t)idx * 3;
 				const float* rest = a.features_rest + (size_t)idx * (a.M - 1) * 3;
 				float* ddc = a.dL_dfeatures_dc + (size_t)idx * 3;
 				float* drest = a.dL_dfeatures_rest + (size_t)idx * (a.M - 1) * 3;
-				auto sh = [dc, rest](int k) {
-					const float* p = k == 0 ? dc : rest + 3 * (k - 1);
-					return V3{ p[0], p[1], p[2] };
+				auto sh = [dc, rest](int k, int c) { return k == 0 ? dc[c] : rest[3 * (k - 1) + c]; };
+				auto dsh = [ddc, drest, write_sh](int k, int c, float v) {
+					if (write_sh) { if (k == 0) ddc[c] = v; else drest[3 * (k - 1) + c] = v; }
 				};
-				auto dsh = [ddc, drest](int k, V3 v) {
-					float* p = k == 0 ? ddc : drest + 3 * (k - 1);
-					p[0] = v.x; p[1] = v.y; p[2] = v.z;
-				};
-				dm3 = sh_backward(a.D, mean, float3{ sCam[0], sCam[1], sCam[2] }, sh, dRGB, dsh);
-				for (int k = (a.D + 1) * (a.D + 1); k < a.M; k++) dsh(k, V3{ 0.f, 0.f, 0.f });
-				sh_row_ready = true;
-			} else if constexpr (kBulkSH) {
-				mbar_wait(&s_bar, 0);
-				sh_waited = true;
-				float shr[kShRowFloats], dshr[kShRowFloats];
-				float4* row = reinterpret_cast<float4*>(&s_sh[tid * kShPitchFloats]);
-#pragma unroll
-				for (int k = 0; k < kShRowFloats / 4; k++) {
-					const float4 q = row[k];
-					shr[4 * k] = q.x; shr[4 * k + 1] = q.y; shr[4 * k + 2] = q.z; shr[4 * k + 3] = q.w;
+				dm3 = grad::colour_backward<float>(a.D, mean, cam, sh, drgb, dsh);
+				if (write_sh) {
+					for (int k = (a.D + 1) * (a.D + 1); k < a.M; k++)
+						for (int c = 0; c < 3; c++) dsh(k, c, 0.f);
+					sh_row_ready = true;
 				}
-#pragma unroll
-				for (int k = 0; k < kShRowFloats; k++) dshr[k] = 0.f;   // rows beyond (D+1)^2 stay zero
-				auto sh = [&shr](int k) { return V3{ shr[3 * k], shr[3 * k + 1], shr[3 * k + 2] }; };
-				auto dsh = [&dshr](int k, V3 v) { dshr[3 * k] = v.x; dshr[3 * k + 1] = v.y; dshr[3 * k + 2] = v.z; };
-				dm3 = sh_backward(a.D, mean, float3{ sCam[0], sCam[1], sCam[2] }, sh, dRGB, dsh);
-#pragma unroll
-				for (int k = 0; k < kShRowFloats / 4; k++)
-					row[k] = make_float4(dshr[4 * k], dshr[4 * k + 1], dshr[4 * k + 2], dshr[4 * k + 3]);
-				sh_row_ready = true;
 			} else {
 				const float* shp = a.shs + (size_t)idx * a.M * 3;
-				auto sh = [shp](int k) { return V3{ shp[3 * k], shp[3 * k + 1], shp[3 * k + 2] }; };
-				auto dsh = [dsh_row](int k, V3 v) {
-					dsh_row[3 * k] = v.x; dsh_row[3 * k + 1] = v.y; dsh_row[3 * k + 2] = v.z;
-				};
-				dm3 = sh_backward(a.D, mean, float3{ sCam[0], sCam[1], sCam[2] }, sh, dRGB, dsh);
-				for (int k = (a.D + 1) * (a.D + 1) * 3; k < a.M * 3; k++) dsh_row[k] = 0.f;
+				auto sh = [shp](int k, int c) { return shp[3 * k + c]; };
+				auto dsh = [dsh_row](int k, int c, float v) { if (dsh_row) dsh_row[3 * k + c] = v; };
+				dm3 = grad::colour_backward<float>(a.D, mean, cam, sh, drgb, dsh);
+				if (dsh_row)
+					for (int k = (a.D + 1) * (a.D + 1) * 3; k < a.M * 3; k++) dsh_row[k] = 0.f;
 			}
 			dmean.x += dm3.x; dmean.y += dm3.y; dmean.z += dm3.z;
 		}
 
-		// scale / rotation backward (backward.cu:489-552)
+		// scale / rotation branch (backward.cu:489-552)
 		if (a.scales != nullptr) {
-			float3 sc = { a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2] };
-			float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
+			float sc[3] = { a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2] };
+			const float4 q4 = reinterpret_cast<const float4*>(a.rotations)[idx];
+			float q[4] = { q4.x, q4.y, q4.z, q4.w };
 			if constexpr (kRaw) {
 				// through exp (gaussian_model.cpp:54-57) and normalize (:59-62):
 				// dL/ds_raw = dL/ds * exp(s_raw);  dL/dq_raw = (dL/dqn - qn <qn, dL/dqn>) / ||q_raw||
-				sc = { expf(sc.x), expf(sc.y), expf(sc.z) };
-				const float n = quat_norm_clamped(q);
-				const float4 qn = make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
-				cov3d_backward(sc, a.scale_modifier, qn, dcov6, dscale, drot);
-				dscale = { dscale.x * sc.x, dscale.y * sc.y, dscale.z * sc.z };
-				const float d = qn.x * drot.x + qn.y * drot.y + qn.z * drot.z + qn.w * drot.w;
-				drot = make_float4((drot.x - qn.x * d) / n, (drot.y - qn.y * d) / n, (drot.z - qn.z * d) / n, (drot.w - qn.w * d) / n);
+				const float act[3] = { expf(sc[0]), expf(sc[1]), expf(sc[2]) };
+				const float n = quat_norm_clamped(q4);
+				const float qn[4] = { q[0] / n, q[1] / n, q[2] / n, q[3] / n };
+#pragma unroll
+				for (int k = 0; k < 3; k++) sc[k] = a.scale_modifier * act[k];
+				grad::scale_rotation_grad<float>(sc, qn, dcov6, dscale, drot);
+				const float d = qn[0] * drot[0] + qn[1] * drot[1] + qn[2] * drot[2] + qn[3] * drot[3];
+#pragma unroll
+				for (int k = 0; k < 3; k++) dscale[k] *= act[k];
+#pragma unroll
+				for (int k = 0; k < 4; k++) drot[k] = (drot[k] - qn[k] * d) / n;
 			} else {
-				cov3d_backward(sc, a.scale_modifier, q, dcov6, dscale, drot);
+#pragma unroll
+				for (int k = 0; k < 3; k++) sc[k] *= a.scale_modifier;
+				grad::scale_rotation_grad<float>(sc, q, dcov6, dscale, drot);
 			}
 		}
 	} else if (dsh_row && !kBulkSH) {
 		for (int k = 0; k < a.M * 3; k++) dsh_row[k] = 0.f;
 	}
 	if constexpr (kMode == 3) {
-		if (!sh_row_ready) {
+		if (write_sh && !sh_row_ready) {
 			for (int k = 0; k < 3; k++) a.dL_dfeatures_dc[(size_t)idx * 3 + k] = 0.f;
 			for (int k = 0; k < (a.M - 1) * 3; k++) a.dL_dfeatures_rest[(size_t)idx * (a.M - 1) * 3 + k] = 0.f;
 		}
@@ -257,51 +273,140 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 	if constexpr (kMode == 2) {
 		// gradient rows (zeros for culled Gaussians) leave as two bulk stores per CTA; <= 3 tail rows plainly
 		if (!sh_waited) mbar_wait(&s_bar, 0);
-		if (!sh_row_ready) {
-			for (int k = 0; k < 3; k++) s_sh[kRawDcOffset + tid * 3 + k] = 0.f;
-			for (int k = 0; k < kRawRestFloats; k++) s_sh[tid * kRawRestFloats + k] = 0.f;
-		}
-		if (tid >= rows4) {
-			for (int k = 0; k < kRawRestFloats; k++) a.dL_dfeatures_rest[(size_t)idx * kRawRestFloats + k] = s_sh[tid * kRawRestFloats + k];
-			for (int k = 0; k < 3; k++) a.dL_dfeatures_dc[(size_t)idx * 3 + k] = s_sh[kRawDcOffset + tid * 3 + k];
-		}
-		// no block-wide barrier here: threads beyond P have left, and a partly active warp must not meet
-		// bar.sync divergently.  Every active thread arrives on s_rows_done; thread 0 waits for all of them.
-		fence_async_smem();
-		mbar_arrive(&s_rows_done);
-		if (tid == 0 && rows4) {
-			mbar_wait(&s_rows_done, 0);
-			const size_t first = (size_t)blockIdx.x * kPreBwdThreads;
-			bulk_store(a.dL_dfeatures_rest + first * kRawRestFloats, &s_sh[0], (uint32_t)rows4 * kRawRestFloats * 4u);
-			bulk_store(a.dL_dfeatures_dc + first * 3, &s_sh[kRawDcOffset], (uint32_t)rows4 * 12u);
-			bulk_commit();
+		if (write_sh) {
+			if (!sh_row_ready) {
+				for (int k = 0; k < 3; k++) s_sh[kRawDcOffset + tid * 3 + k] = 0.f;
+				for (int k = 0; k < kRawRestFloats; k++) s_sh[tid * kRawRestFloats + k] = 0.f;
+			}
+			if (tid >= rows4) {
+				for (int k = 0; k < kRawRestFloats; k++) a.dL_dfeatures_rest[(size_t)idx * kRawRestFloats + k] = s_sh[tid * kRawRestFloats + k];
+				for (int k = 0; k < 3; k++) a.dL_dfeatures_dc[(size_t)idx * 3 + k] = s_sh[kRawDcOffset + tid * 3 + k];
+			}
+			// no block-wide barrier here: threads beyond P have left, and a partly active warp must not meet
+			// bar.sync divergently.  Every active thread arrives on s_rows_done; thread 0 waits for all of them.
+			fence_async_smem();
+			mbar_arrive(&s_rows_done);
+			if (tid == 0 && rows4) {
+				mbar_wait(&s_rows_done, 0);
+				const size_t first = (size_t)blockIdx.x * kPreBwdThreads;
+				bulk_store(a.dL_dfeatures_rest + first * kRawRestFloats, &s_sh[0], (uint32_t)rows4 * kRawRestFloats * 4u);
+				bulk_store(a.dL_dfeatures_dc + first * 3, &s_sh[kRawDcOffset], (uint32_t)rows4 * 12u);
+				bulk_commit();
+			}
 		}
 	}
 	if constexpr (kMode == 1) {
 		// hand the gradient row (zeros for culled Gaussians) to the copy engine
 		if (!sh_waited) mbar_wait(&s_bar, 0);
-		float4* row = reinterpret_cast<float4*>(&s_sh[tid * kShPitchFloats]);
-		if (!sh_row_ready) {
+		if (write_sh) {
+			float4* row = reinterpret_cast<float4*>(&s_sh[tid * kShPitchFloats]);
+			if (!sh_row_ready) {
 #pragma unroll
-			for (int k = 0; k < kShRowFloats / 4; k++) row[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+				for (int k = 0; k < kShRowFloats / 4; k++) row[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+			fence_async_smem();
+			bulk_store(dsh_row, row, kShRowFloats * 4u);
+			bulk_commit();
 		}
-		fence_async_smem();
-		bulk_store(dsh_row, row, kShRowFloats * 4u);
-		bulk_commit();
+	}
+	if (a.dL_drgb_view) {
+		a.dL_drgb_view[3 * (size_t)idx + 0] = drgb[0];
+		a.dL_drgb_view[3 * (size_t)idx + 1] = drgb[1];
+		a.dL_drgb_view[3 * (size_t)idx + 2] = drgb[2];
 	}
 
-	a.dL_dmean3D[3 * (size_t)idx + 0] = dmean.x;
-	a.dL_dmean3D[3 * (size_t)idx + 1] = dmean.y;
-	a.dL_dmean3D[3 * (size_t)idx + 2] = dmean.z;
-	if (!kRaw || a.dL_dcov3D) {
+	float* m3 = a.dL_dmean3D + 3 * (size_t)idx;
+	float* ds = a.dL_dscale + 3 * (size_t)idx;
+	float4* dr = reinterpret_cast<float4*>(a.dL_drot) + idx;
+	if (a.accumulate) {
+		m3[0] += dmean.x; m3[1] += dmean.y; m3[2] += dmean.z;
+		a.dL_dopacity[idx] += dopacity;
+		ds[0] += dscale[0]; ds[1] += dscale[1]; ds[2] += dscale[2];
+		const float4 o = *dr;
+		*dr = make_float4(o.x + drot[0], o.y + drot[1], o.z + drot[2], o.w + drot[3]);
+	} else {
+		m3[0] = dmean.x; m3[1] = dmean.y; m3[2] = dmean.z;
+		a.dL_dopacity[idx] = dopacity;
+		ds[0] = dscale[0]; ds[1] = dscale[1]; ds[2] = dscale[2];
+		*dr = make_float4(drot[0], drot[1], drot[2], drot[3]);
+	}
+	if (a.dL_dcov3D) {
 #pragma unroll
 		for (int i = 0; i < 6; i++) a.dL_dcov3D[6 * (size_t)idx + i] = dcov6[i];
 	}
-	a.dL_dscale[3 * (size_t)idx + 0] = dscale.x;
-	a.dL_dscale[3 * (size_t)idx + 1] = dscale.y;
-	a.dL_dscale[3 * (size_t)idx + 2] = dscale.z;
-	reinterpret_cast<float4*>(a.dL_drot)[idx] = drot;
 	if (kBulkSH) bulk_wait_read_all();   // shared memory must outlive the outgoing copy
+}
+
+// dL/dsh of a whole training step from the per-view dL/dRGB factors: row k of a Gaussian's gradient is rank one per view,
+// b_k(dir_view) * dL/dRGB_view, so ranks exchange 12 bytes per Gaussian and view instead of 192 and every rank rebuilds the
+// same sum here (views in a fixed order: all replicas get identical bits, equal to adding up the per-view dL/dsh tensors
+// in that order).  drgb[v] may be a peer GPU's buffer (NVLink loads: the transfer IS this kernel's input stream).
+// One warp per 32 Gaussians: the 48-float rows are staged in shared memory and leave as fully coalesced 128-bit stores.
+constexpr int kShViewsThreads = 128;
+__global__ void __launch_bounds__(kShViewsThreads) sh_gradient_from_views_kernel(const ShFromViewsArgs a)
+{
+	__shared__ float s_rows[kShViewsThreads / 32][kShRowFloats * 33];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int first = (blockIdx.x * (kShViewsThreads / 32) + warp) * 32;   // first Gaussian of this warp
+	if (first >= a.P) return;
+	const int idx = first + lane;
+	const int n = (a.D + 1) * (a.D + 1);
+	float acc[kShRowFloats];
+#pragma unroll
+	for (int k = 0; k < kShRowFloats; k++) acc[k] = 0.f;
+	if (idx < a.P) {
+		const float mx = a.means3D[3 * (size_t)idx], my = a.means3D[3 * (size_t)idx + 1], mz = a.means3D[3 * (size_t)idx + 2];
+		for (int v = 0; v < a.n_views; v++) {
+			const float* dv = a.drgb[v] + 3 * (size_t)idx;
+			const float d0 = dv[0], d1 = dv[1], d2 = dv[2];
+			if (d0 == 0.f && d1 == 0.f && d2 == 0.f) continue;   // not visible in this view (or fully clamped): adds exact zeros
+			const float vx = mx - a.campos[3 * v], vy = my - a.campos[3 * v + 1], vz = mz - a.campos[3 * v + 2];
+			const float len = sqrtf(vx * vx + vy * vy + vz * vz);
+			float b[16];
+			grad::sh_weights<float>(a.D, vx / len, vy / len, vz / len, b);
+#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				if (k < n) {
+					acc[3 * k + 0] = __fadd_rn(acc[3 * k + 0], grad::mul1(b[k], d0));
+					acc[3 * k + 1] = __fadd_rn(acc[3 * k + 1], grad::mul1(b[k], d1));
+					acc[3 * k + 2] = __fadd_rn(acc[3 * k + 2], grad::mul1(b[k], d2));
+				}
+			}
+		}
+	}
+	// transposed staging at a 33-word pitch: element (row r, float k) at s[k * 33 + r] — lane-per-row writes and
+	// lane-per-output-float reads are both conflict-free
+	const int rows = min(32, a.P - first);
+	float* s = s_rows[warp];
+#pragma unroll
+	for (int k = 0; k < kShRowFloats; k++) s[k * 33 + lane] = acc[k];
+	__syncwarp();
+	if (a.dL_dsh) {
+		// [P,16,3]: the warp's rows are rows * 48 contiguous floats, stored as 128-bit words
+		float4* out = reinterpret_cast<float4*>(a.dL_dsh + (size_t)first * kShRowFloats);
+		for (int i = lane; i < rows * (kShRowFloats / 4); i += 32) {
+			const int f = 4 * i, r = f / kShRowFloats, k = f - r * kShRowFloats;   // 48 is a multiple of 4: one row per word
+			out[i] = make_float4(s[k * 33 + r], s[(k + 1) * 33 + r], s[(k + 2) * 33 + r], s[(k + 3) * 33 + r]);
+		}
+	} else {
+		// split layout (raw-parameter trainer): dL/dfeatures_rest rows of 45 floats, dL/dfeatures_dc rows of 3
+		float* rest = a.dL_dfeatures_rest + (size_t)first * kRawRestFloats;
+		float* dc = a.dL_dfeatures_dc + (size_t)first * 3;
+		for (int i = lane; i < rows * kRawRestFloats; i += 32) {
+			const int r = i / kRawRestFloats, k = i - r * kRawRestFloats;
+			rest[i] = s[(3 + k) * 33 + r];
+		}
+		for (int i = lane; i < rows * 3; i += 32) dc[i] = s[(i % 3) * 33 + i / 3];
+	}
+}
+
+int launch_sh_gradient_from_views(const ShFromViewsArgs& a, cudaStream_t st)
+{
+	if (a.P <= 0) return OGS_OK;
+	const int per_block = kShViewsThreads;   // Gaussians per block
+	sh_gradient_from_views_kernel<<<ceil_div(a.P, per_block), kShViewsThreads, 0, st>>>(a);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
 }
 
 int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st)

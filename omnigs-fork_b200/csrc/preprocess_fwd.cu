@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 	if (visible) {
 		float3 rgb;
 		unsigned cmask = 0;
-		if (a.colors_precomp == nullptr) {
+		if (a.defer_colors) {
+			rgb = { 0.f, 0.f, 0.f };   // launch_sh_colors fills colour and clamp mask before the blend
+		} else if (a.colors_precomp == nullptr) {
 			V3 c;
 			if constexpr (kMode == 2) {
 				float shr[kShRowFloats];
@@ -274,6 +276,72 @@ __global__ void mark_all_visible_kernel(int P, uint8_t* present)
 	if (i < P) present[i] = 1;
 }
 
+// Deferred colour evaluation (data-parallel trainer): SH -> RGB and the clamp mask of every Gaussian that is visible in
+// the full frame, written into the packed records the blend kernels gather (computeColorFromSH at its call site,
+// forward.cu:688-692, pinned like the fused path: sh_to_rgb_p).  SH rows by per-row bulk copies when M == 16.
+template <bool kBulk>
+__global__ void __launch_bounds__(kPreThreads) sh_colors_kernel(
+	int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ shs, const float* __restrict__ campos,
+	const int* __restrict__ radii, float4* __restrict__ g1, float2* __restrict__ gb, uint8_t* __restrict__ clamped)
+{
+	__shared__ __align__(16) float s_sh[kBulk ? kPreThreads * kShPitchFloats : 4];
+	__shared__ __align__(8) uint64_t s_bar;
+	__shared__ int s_rows;
+	const int tid = threadIdx.x;
+	const int idx = blockIdx.x * kPreThreads + tid;
+	const bool visible = idx < P && radii[idx] > 0;
+	if (kBulk) {
+		if (tid == 0) { s_rows = 0; mbar_init(&s_bar, 1); }
+		__syncthreads();
+		if (visible) atomicAdd(&s_rows, 1);
+		__syncthreads();
+		if (tid == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)s_rows * kShRowFloats * 4u);
+		__syncthreads();
+		if (visible) bulk_load(&s_sh[tid * kShPitchFloats], shs + (size_t)idx * kShRowFloats, kShRowFloats * 4u, &s_bar);
+		mbar_wait(&s_bar, 0);   // every thread: a CTA must not retire with copies in flight
+	}
+	if (!visible) return;
+	const float3 p = { means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2] };
+	const float3 cam = { campos[0], campos[1], campos[2] };
+	unsigned cmask = 0;
+	V3 c;
+	if constexpr (kBulk) {
+		float shr[kShRowFloats];
+		const float4* row = reinterpret_cast<const float4*>(&s_sh[tid * kShPitchFloats]);
+#pragma unroll
+		for (int k = 0; k < kShRowFloats / 4; k++) {
+			const float4 q = row[k];
+			shr[4 * k] = q.x; shr[4 * k + 1] = q.y; shr[4 * k + 2] = q.z; shr[4 * k + 3] = q.w;
+		}
+		auto sh = [&shr](int k) { return V3{ shr[3 * k], shr[3 * k + 1], shr[3 * k + 2] }; };
+		c = sh_to_rgb_p(D, p, cam, sh, cmask);
+	} else {
+		const float* shp = shs + (size_t)idx * M * 3;
+		auto sh = [shp](int k) { return V3{ shp[3 * k], shp[3 * k + 1], shp[3 * k + 2] }; };
+		c = sh_to_rgb_p(D, p, cam, sh, cmask);
+	}
+	clamped[idx] = (uint8_t)cmask;
+	float4 r1 = g1[idx];
+	r1.z = c.x; r1.w = c.y;
+	g1[idx] = r1;
+	float2 rb = gb[idx];
+	rb.x = c.z;
+	gb[idx] = rb;
+}
+
+int launch_sh_colors(int P, int D, int M, const float* means3D, const float* shs, const float* campos, const int* radii,
+                     float4* g1, float2* gb, uint8_t* clamped, cudaStream_t st)
+{
+	if (P <= 0) return OGS_OK;
+	const int blocks = ceil_div(P, kPreThreads);
+	if (sh_rows_bulk_capable(shs, M))
+		sh_colors_kernel<true><<<blocks, kPreThreads, 0, st>>>(P, D, M, means3D, shs, campos, radii, g1, gb, clamped);
+	else
+		sh_colors_kernel<false><<<blocks, kPreThreads, 0, st>>>(P, D, M, means3D, shs, campos, radii, g1, gb, clamped);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
 int launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t st)
 {
 	const int blocks = ceil_div(a.P, kPreThreads);
@@ -287,7 +355,7 @@ int launch_preprocess_fwd(const PreprocessFwdArgs& a, cudaStream_t st)
 			preprocess_lonlat_fwd_kernel<2><<<blocks, kPreThreads, 0, st>>>(a);
 		else
 			preprocess_lonlat_fwd_kernel<3><<<blocks, kPreThreads, 0, st>>>(a);
-	} else if (a.shs != nullptr && sh_rows_bulk_capable(a.shs, a.M))
+	} else if (!a.defer_colors && a.shs != nullptr && sh_rows_bulk_capable(a.shs, a.M))
 		preprocess_lonlat_fwd_kernel<1><<<blocks, kPreThreads, 0, st>>>(a);
 	else
 		preprocess_lonlat_fwd_kernel<0><<<blocks, kPreThreads, 0, st>>>(a);

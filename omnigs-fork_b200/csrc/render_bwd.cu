@@ -248,7 +248,11 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 						// power >= the Gaussian's cut-off (eb.y) IS the forward's alpha >= 1/255 decision, so the gradient
 						// arithmetic itself is free to use ex2.approx (2 instructions instead of expf's 9): gradients are
 						// tolerance-bound, not bit-compared
+#ifdef OGS_BWD_EXACT_MATH   // A/B build (tools/grad_noise.py): the reference's own expf / IEEE division
+						G = expf(power);
+#else
 						G = ex2_approx(power * 1.4426950408889634f);   // ex2.approx.ftz: no denormal rescaling (power >= cut-off > -6)
+#endif
 						alpha = fminf(0.99f, __fmul_rn(eb.z, G));
 					}
 					if (valid) {
@@ -257,7 +261,11 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 						// divisions by (1 - alpha)
 						const float4 pix = lds_f4(pix_addr + (uint32_t)(s * kBwdThreads * sizeof(float4)));
 						const float dL_dpixel[3] = { pix.x, pix.y, pix.z };
+#ifdef OGS_BWD_EXACT_MATH
+						const float inv = __fdiv_rn(1.f, 1.f - alpha);
+#else
 						const float inv = rcp_approx(1.f - alpha);
+#endif
 						T[s] = T[s] * inv;
 						const float dchannel_dcolor = alpha * T[s];
 						float dL_dalpha = 0.0f;

@@ -45,35 +45,63 @@ def allreduce_gradients(grads, radii=None, group=None):
     return grads, stats
 
 
-class GradientBucket:
-    """One flat float32 buffer holding, back to back, the five gradient tensors the optimiser consumes
-    (dL_dmeans3D [P,3], dL_dsh [P,M,3], dL_dopacity [P,1], dL_dscales [P,3], dL_drotations [P,4]) and the two
-    summed densification statistics ([P] each).  RasterizeGaussiansBackwardCUDA(..., out=bucket) lets the library
-    write the gradients straight into it, so the data-parallel exchange is ONE all-reduce(SUM) over
-    (59 + 2) floats per Gaussian (plus one small all-reduce(MAX) for the radii) instead of eight collectives:
-    collective launches are latency-bound, and one large message uses the NVLink/NVSwitch bandwidth better."""
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
 
-    def __init__(self, P, M, device, peer=None):
-        """peer: None = use NVLink peer memory when available (NCCL otherwise), False = always NCCL/gloo."""
+
+class GradientBucket:
+    """The per-step exchange buffer of data-parallel training: ONE flat float32 allocation (symmetric memory when the
+    ranks share NVLink, so that our own kernels can read and write every rank's copy) laid out as
+
+        [ summed section | max section | factor section ]
+
+    summed : the gradients the optimiser consumes and the two summed densification statistics ([P] each)
+    max    : max_radii2D [P] (radii are non-negative, so the same kernel max-reduces them on their bit patterns)
+    factors: (factored mode) this rank's views' clamp-masked dL/dRGB [views_per_rank, P, 3]
+
+    Dense mode (views_per_rank == 0): dL_dsh [P,M,3] sits in the summed section, 61 + 1 floats per Gaussian are exchanged.
+    Factored mode (views_per_rank >= 1): row k of dL/dsh is b_k(view direction) * dL/dRGB per view (reference
+    backward.cu:60-150), so ranks only publish the 3-float factor per view; every rank rebuilds the step's dL_dsh from ALL
+    views' factors, reading the peers' factors straight over NVLink inside the rebuild kernel
+    (ogs_sh_gradient_from_views).  13 + 1 floats per Gaussian are all-reduced and 12 bytes per Gaussian and remote view
+    are read, instead of 244 bytes; dL_dsh lives in a plain local tensor.  RasterizeGaussiansBackwardView writes a view
+    straight into the bucket (accumulating views after the first), statistics included."""
+
+    def __init__(self, P, M, device, peer=None, group=None, views_per_rank=0):
+        """peer: None = use NVLink peer memory when available (NCCL otherwise), False = always NCCL/gloo.
+        group: the process group the bucket is exchanged over (None = WORLD); the symmetric-memory rendezvous, the
+        barriers, the slices and the NCCL fallback all use it."""
         self.P, self.M = int(P), int(M)
+        self.group = group
+        self.views_per_rank = int(views_per_rank)
         self.peer = None
         self.peer_error = None
-        sizes = [("dL_dmeans3D", (P, 3)), ("dL_dsh", (P, M, 3)), ("dL_dopacity", (P, 1)), ("dL_dscales", (P, 3)),
-                 ("dL_drotations", (P, 4)), ("xyz_gradient_accum", (P,)), ("denom", (P,))]
-        # every section starts 16-byte aligned (the SH rows go through 16-byte bulk copies)
-        offs, total = [], 0
-        for _, shape in sizes:
-            offs.append(total)
-            n = 1
-            for d in shape:
-                n *= int(d)
-            total += -(-n // 4) * 4
+        summed = [("dL_dmeans3D", (P, 3))]
+        if self.views_per_rank == 0:
+            summed.append(("dL_dsh", (P, M, 3)))
+        summed += [("dL_dopacity", (P, 1)), ("dL_dscales", (P, 3)), ("dL_drotations", (P, 4)),
+                   ("xyz_gradient_accum", (P,)), ("denom", (P,))]
+        sizes = summed + [("max_radii2D", (P,))]
+        if self.views_per_rank:
+            sizes.append(("dL_drgb", (self.views_per_rank, P, 3)))
+        # every section starts 16-byte aligned (128-bit accesses, bulk copies of the SH rows)
+        offs, total = {}, 0
+        for name, shape in sizes:
+            offs[name] = total
+            total += -(-_numel(shape) // 4) * 4
+        self.count_sum = offs["max_radii2D"]
+        self.count_max = -(-int(P) // 4) * 4
+        self.offsets = offs
         self.flat = None
-        if peer is not False and is_distributed() and torch.device(device).type == "cuda":
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if peer is not False and distributed and torch.device(device).type == "cuda":
             flat = self._symmetric(total, device)
             # every rank must take the same path (the peer kernel is bracketed by cross-rank barriers)
             ok = torch.tensor([1 if flat is not None else 0], dtype=torch.int32, device=device)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
             if int(ok.item()) == 1:
                 self.flat = flat
             else:
@@ -81,26 +109,38 @@ class GradientBucket:
         if self.flat is None:
             self.flat = torch.empty((total,), dtype=torch.float32, device=device)
         self.tensors = {}
-        for (name, shape), o in zip(sizes, offs):
-            n = 1
-            for d in shape:
-                n *= int(d)
-            self.tensors[name] = self.flat[o:o + n].view(shape)
-        self.max_radii2D = torch.empty((P,), dtype=torch.float32, device=device)
+        for name, shape in sizes:
+            self.tensors[name] = self.flat[offs[name]:offs[name] + _numel(shape)].view(shape)
+        self.max_radii2D = self.tensors["max_radii2D"]
+        if self.views_per_rank:
+            self.tensors["dL_drgb"].zero_()                      # unused view slots contribute exact zeros
+            self.tensors["dL_dsh"] = torch.empty((P, M, 3), dtype=torch.float32, device=device)
 
     def __getitem__(self, name):
         return self.tensors[name]
+
+    @property
+    def factored(self):
+        return self.views_per_rank > 0
+
+    def world(self):
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def zero_step(self):
+        """A rank that renders no view in a step contributes zeros (its bucket must not hold a previous step)."""
+        self.flat.zero_()
 
     def _symmetric(self, total, device):
         """Allocate the bucket in torch.distributed symmetric memory and map every peer's copy into this process.
         Returns None (-> NCCL path) when that is not possible on this system."""
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            world = dist.get_world_size()
+            grp = self.group if self.group is not None else dist.group.WORLD
+            world = dist.get_world_size(grp)
             if world > 8:
                 return None
             flat = symm_mem.empty(total, dtype=torch.float32, device=device)
-            hdl = symm_mem.rendezvous(flat, dist.group.WORLD)
+            hdl = symm_mem.rendezvous(flat, grp)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
             if len(ptrs) != world or any(p == 0 or p % 16 for p in ptrs):
                 return None
@@ -112,7 +152,7 @@ class GradientBucket:
                     mc = int(hdl.multicast_ptr)
                 except Exception:
                     mc = 0
-            self.peer = dict(handle=hdl, ptrs=ptrs, rank=dist.get_rank(), world=world, multicast=mc)
+            self.peer = dict(handle=hdl, ptrs=ptrs, rank=dist.get_rank(grp), world=world, multicast=mc)
             return flat
         except Exception as e:   # no symmetric memory on this build / topology: remember why, use NCCL
             self.peer = None
@@ -122,7 +162,8 @@ class GradientBucket:
 
 def fill_view_stats(bucket, dL_dmeans2D, radii):
     """Write one view's densification-statistics increments into the bucket's slots (one kernel on the GPU):
-    ||dL_dmeans2D.xy|| and 1 where radii > 0, and the radius as float."""
+    ||dL_dmeans2D.xy|| and 1 where radii > 0, and the radius as float.  (RasterizeGaussiansBackwardView does this inside
+    the per-Gaussian backward; this is for the dense bucket fed by RasterizeGaussiansBackwardCUDA.)"""
     if bucket.flat.is_cuda:
         import ctypes
         from ._lib import load_library, check
@@ -138,42 +179,128 @@ def fill_view_stats(bucket, dL_dmeans2D, radii):
         bucket.max_radii2D.copy_(radii)
 
 
-def exchange_bucket(bucket, group=None):
-    """Sum the bucket (gradients + summed statistics) and take the maximum of the radii over ranks, in place.
-    One kernel over NVLink peer memory / the multicast address when the bucket lives in symmetric memory
-    (csrc/peer_collective.cu), NCCL / gloo all-reduce otherwise.  A no-op on a single rank."""
-    if is_distributed() and bucket.peer is not None:
-        # reduce-scatter + all-gather in one kernel, bracketed by the symmetric-memory barrier on this stream:
-        # all buckets written before, all slices stored after
+SH_C0 = 0.28209479177387814
+SH_C1 = 0.4886025119029199
+SH_C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+SH_C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+         1.445305721320277, -0.5900435899266435)
+
+
+def sh_weights(dirs, degree):
+    """The 16 real SH weights b_k(dir) of the reference's colour evaluation (forward.cu:30-83) for unit vectors
+    dirs [...,3] -> [...,16] (zeros beyond (degree+1)^2).  Torch restatement used where no CUDA kernel can run (gloo
+    tests on CPU tensors) and as the checker of ogs_sh_gradient_from_views."""
+    x, y, z = dirs[..., 0], dirs[..., 1], dirs[..., 2]
+    b = [torch.full_like(x, SH_C0)]
+    if degree > 0:
+        b += [-SH_C1 * y, SH_C1 * z, -SH_C1 * x]
+    if degree > 1:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        b += [SH_C2[0] * xy, SH_C2[1] * yz, SH_C2[2] * (2 * zz - xx - yy), SH_C2[3] * xz, SH_C2[4] * (xx - yy)]
+    if degree > 2:
+        b += [SH_C3[0] * y * (3 * xx - yy), SH_C3[1] * xy * z, SH_C3[2] * y * (4 * zz - xx - yy),
+              SH_C3[3] * z * (2 * zz - 3 * xx - 3 * yy), SH_C3[4] * x * (4 * zz - xx - yy), SH_C3[5] * z * (xx - yy),
+              SH_C3[6] * x * (xx - 3 * yy)]
+    b += [torch.zeros_like(x)] * (16 - len(b))
+    return torch.stack(b, dim=-1)
+
+
+def sh_gradient_from_views(means3D, campos_views, factors, degree, out):
+    """out[P,16,3] = sum over views v (in order) of b(dir_v) (x) factors[v]; factors: list of [P,3] tensors (CUDA tensors
+    may live on peer GPUs: pass raw pointers with `factor_ptrs` through rebuild_sh_gradient instead)."""
+    if out.is_cuda:
         import ctypes
         from ._lib import load_library, check
-        pr = bucket.peer
-        w2 = dist.all_reduce(bucket.max_radii2D, op=dist.ReduceOp.MAX, group=group, async_op=True)
-        arr = (ctypes.c_void_p * pr["world"])(*pr["ptrs"])
-        stream = ctypes.c_void_p(torch.cuda.current_stream(bucket.flat.device).cuda_stream)
-        pr["handle"].barrier(channel=0)
+        P, M = int(out.size(0)), int(out.size(1))
+        ptrs = (ctypes.c_void_p * len(factors))(*[int(f) if isinstance(f, int) else f.data_ptr() for f in factors])
+        campos_views = campos_views.contiguous()
+        check(load_library().ogs_sh_gradient_from_views(
+            P, int(degree), M, len(factors), ctypes.c_void_p(means3D.data_ptr()), ctypes.c_void_p(campos_views.data_ptr()),
+            ptrs, ctypes.c_void_p(out.data_ptr()), None, None,
+            ctypes.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)))
+        return out
+    out.zero_()
+    for v, f in enumerate(factors):
+        d = means3D - campos_views[v][None, :]
+        b = sh_weights(d / d.norm(dim=-1, keepdim=True), degree)          # [P,16]
+        out += b[:, :out.size(1), None] * f[:, None, :]
+    return out
+
+
+def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=3, sh_stream=None):
+    """Sum the bucket's summed section and max-reduce its radii over ranks, in place: one kernel over NVLink peer
+    memory / the multicast address when the bucket lives in symmetric memory (csrc/peer_collective.cu), NCCL / gloo
+    all-reduce otherwise.  Factored buckets then rebuild bucket["dL_dsh"] from every rank's view factors (means3D and
+    campos_views [views_per_rank * world, 3], view v = slot * world + rank, are needed for the directions).  With
+    `sh_stream` the rebuild runs on that stream underneath whatever the caller queues next on the current one; the
+    returned event marks dL_dsh ready AND every rank done reading this rank's factors — wait for it before reading
+    dL_dsh and before the next step's backward.  A no-op on a single rank (apart from the rebuild)."""
+    group = group if group is not None else bucket.group
+    if group is not bucket.group:
+        raise RuntimeError("exchange_bucket: the bucket was built for another process group")
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    cs, cm = bucket.count_sum, bucket.count_max
+    factor_srcs = None
+    pr = bucket.peer if distributed else None
+    cur = torch.cuda.current_stream(bucket.flat.device) if bucket.flat.is_cuda else None
+    if pr is not None:
+        import ctypes
+        from ._lib import load_library, check
+        stream = ctypes.c_void_p(cur.cuda_stream)
+        pr["handle"].barrier(channel=0)      # every rank's bucket (and factors) of this step are written
+        fork = None
+        if bucket.factored and sh_stream is not None:
+            fork = torch.cuda.Event()
+            fork.record(cur)
         if pr.get("multicast") and pr.get("use_multimem", pr["world"] > 4):
-            # NVSwitch in-switch reduction: one inbound copy per element instead of world - 1.  Measured on the 244 MB
-            # bucket: peer loads/stores win up to four ranks (2: 0.36 ms; 4: 0.575 against 0.598), the multicast path
-            # beyond (8: 0.63 against 0.74)
-            check(load_library().ogs_multimem_allreduce_sum(ctypes.c_void_p(pr["multicast"]), pr["world"], pr["rank"],
-                                                            bucket.flat.numel(), stream))
+            # NVSwitch in-switch reduction: one inbound copy per element instead of world - 1.  Measured on a 244 MB
+            # bucket: peer loads/stores win up to four ranks, the multicast path beyond (profiles/r01_peer_allreduce_*.log)
+            check(load_library().ogs_multimem_allreduce(ctypes.c_void_p(pr["multicast"]), pr["world"], pr["rank"], cs, cm, stream))
         else:
-            check(load_library().ogs_peer_allreduce_sum(arr, pr["world"], pr["rank"], bucket.flat.numel(), stream))
+            arr = (ctypes.c_void_p * pr["world"])(*pr["ptrs"])
+            check(load_library().ogs_peer_allreduce(arr, pr["world"], pr["rank"], cs, cm, stream))
+        if bucket.factored:
+            off = bucket.offsets["dL_drgb"] * 4
+            step = bucket.P * 3 * 4
+            factor_srcs = [pr["ptrs"][r] + off + s * step for s in range(bucket.views_per_rank) for r in range(world)]
+            if sh_stream is None:
+                sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
+                pr["handle"].barrier(channel=1)   # all sums stored, all factors read
+                return None
+            sh_stream.wait_event(fork)
+            with torch.cuda.stream(sh_stream):
+                sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
+                pr["handle"].barrier(channel=2)   # every rank has read this rank's factors
+                done = torch.cuda.Event()
+                done.record(sh_stream)
+            pr["handle"].barrier(channel=1)       # all sums stored
+            return done
         pr["handle"].barrier(channel=1)
-        w2.wait()
-    elif is_distributed():
-        w1 = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
-        w2 = dist.all_reduce(bucket.max_radii2D, op=dist.ReduceOp.MAX, group=group, async_op=True)
+        return None
+    if distributed:
+        w1 = dist.all_reduce(bucket.flat[:cs], op=dist.ReduceOp.SUM, group=group, async_op=True)
+        w2 = dist.all_reduce(bucket.flat[cs:cs + cm], op=dist.ReduceOp.MAX, group=group, async_op=True)
+        gathered = None
+        if bucket.factored:
+            gathered = [torch.empty_like(bucket["dL_drgb"]) for _ in range(world)]
+            dist.all_gather(gathered, bucket["dL_drgb"].contiguous(), group=group)
         w1.wait()
         w2.wait()
+        if bucket.factored:
+            factor_srcs = [gathered[r][s] for s in range(bucket.views_per_rank) for r in range(world)]
+    elif bucket.factored:
+        factor_srcs = [bucket["dL_drgb"][s] for s in range(bucket.views_per_rank)]
+    if bucket.factored:
+        sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
+    return None
 
 
 def allreduce_bucket(bucket, dL_dmeans2D, radii, group=None):
-    """One view per rank and step: fill the statistics slots of `bucket` from this rank's view and sum the whole
-    bucket over ranks in one collective.  Returns (dict of the five summed gradients, stats dict) like
-    allreduce_gradients.  (Several views per rank: fill_view_stats + local accumulation + exchange_bucket,
-    see tools/bench_dp_views.py.)"""
+    """One view per rank and step with a DENSE bucket: fill the statistics slots of `bucket` from this rank's view and
+    sum the whole bucket over ranks in one collective.  Returns (dict of the five summed gradients, stats dict) like
+    allreduce_gradients."""
     fill_view_stats(bucket, dL_dmeans2D, radii)
     exchange_bucket(bucket, group)
     grads = {n: bucket[n] for n in OPTIMISED}
@@ -188,13 +315,97 @@ def tile_row_counts(ranges, W, H):
     return lens.sum(dim=1).tolist()
 
 
-def render_band_forward(rasterize, band, H, group=None):
+class BandExchange:
+    """Buffers and exchanges of latitude-band rendering: every rank bins / sorts / blends only its
+    tile rows of one large panorama and holds all Gaussians.  Per frame the ranks exchange
+      forward : their pixel rows — an all-gather of band rows into every rank's image (the trainer's loss wants the
+                frame whole); peer stores over NVLink (ogs_band_rows_allgather), NCCL/gloo all_gather otherwise;
+      backward: the packed [P,12] render-backward accumulators (48 B/Gaussian, summed) between the two backward kernels,
+                through the same NVLink all-reduce kernel as the data-parallel bucket (peer loads/stores up to four
+                ranks, multimem beyond), NCCL/gloo otherwise.
+    `image` and `acc` live in one symmetric allocation."""
+
+    def __init__(self, P, W, H, device, group=None, peer=None):
+        self.P, self.W, self.H, self.group = int(P), int(W), int(H), group
+        self.peer = None
+        n_acc = -(-12 * self.P // 4) * 4
+        total = n_acc + 3 * self.W * self.H
+        self.flat = None
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if peer is not False and self.distributed and torch.device(device).type == "cuda":
+            helper = GradientBucket.__new__(GradientBucket)      # reuse the rendezvous
+            helper.group, helper.peer, helper.peer_error = group, None, None
+            flat = helper._symmetric(total, device)
+            ok = torch.tensor([1 if flat is not None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 1:
+                self.flat, self.peer = flat, helper.peer
+        if self.flat is None:
+            self.flat = torch.empty((total,), dtype=torch.float32, device=device)
+        self.acc = self.flat[:12 * self.P].view(self.P, 12)
+        self.image = self.flat[n_acc:].view(3, self.H, self.W)
+        self._img_off = n_acc * 4
+
+    def gather_image(self, band_image, band):
+        """band_image: this rank's render [3,H,W] (valid in its rows); band = (ty0, ty1) tile rows.  Returns the full
+        frame (every rank's rows in place)."""
+        y0, y1 = min(self.H, band[0] * 16), min(self.H, band[1] * 16)
+        if not self.distributed:
+            return band_image
+        if self.peer is not None:
+            import ctypes
+            from ._lib import load_library, check
+            pr = self.peer
+            imgs = (ctypes.c_void_p * pr["world"])(*[p + self._img_off for p in pr["ptrs"]])
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+            check(load_library().ogs_band_rows_allgather(imgs, pr["world"], pr["rank"], ctypes.c_void_p(band_image.data_ptr()),
+                                                         self.W, self.H, y0, y1, stream))
+            pr["handle"].barrier(channel=3)      # every band has landed in every image
+            return self.image
+        world = dist.get_world_size(self.group)
+        bands = [None] * world
+        dist.all_gather_object(bands, (y0, y1), group=self.group)
+        rows = max(b - a for a, b in bands)
+        mine = band_image.new_zeros((3, rows, self.W))
+        mine[:, :y1 - y0] = band_image[:, y0:y1]
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=self.group)
+        for (a, b), part in zip(bands, parts):
+            self.image[:, a:b] = part[:, :b - a]
+        return self.image
+
+    def reduce_accumulators(self, acc=None):
+        """Sum self.acc over the ranks, in place (call between the two backward kernels:
+        RasterizeGaussiansBackwardCUDA(..., accumulators=ex.acc, reduce_accumulators=ex.reduce_accumulators))."""
+        if not self.distributed:
+            return
+        if self.peer is not None:
+            import ctypes
+            from ._lib import load_library, check
+            pr = self.peer
+            n = -(-12 * self.P // 4) * 4
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+            pr["handle"].barrier(channel=0)
+            if pr.get("multicast") and pr.get("use_multimem", pr["world"] > 4):
+                check(load_library().ogs_multimem_allreduce(ctypes.c_void_p(pr["multicast"]), pr["world"], pr["rank"], n, 0, stream))
+            else:
+                arr = (ctypes.c_void_p * pr["world"])(*pr["ptrs"])
+                check(load_library().ogs_peer_allreduce(arr, pr["world"], pr["rank"], n, 0, stream))
+            pr["handle"].barrier(channel=1)
+        else:
+            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM, group=self.group)
+
+
+def render_band_forward(rasterize, band, H, group=None, exchange=None):
     """Latitude-band forward for this rank.  `rasterize(band)` must call RasterizeGaussiansCUDA(...,
-    band=band) and return its 6-tuple.  Pixel rows outside the band are zeroed and the per-rank images
-    are summed, so every rank ends with the full frame (the loss of the trainer needs it whole; a band-
-    wise loss would only need an 11x11-SSIM halo of 5 rows).  Returns (image, forward_tuple)."""
+    band=band) and return its 6-tuple.  With a BandExchange the ranks all-gather their pixel rows (each pixel crosses
+    NVLink once per peer); without one, rows outside the band are zeroed and the per-rank images are summed
+    (all-reduce of full frames: twice the bytes, kept for callers without symmetric memory).  Every rank ends with
+    the full frame.  Returns (image, forward_tuple)."""
     fwd = rasterize(band)
     img = fwd[1]
+    if exchange is not None:
+        return exchange.gather_image(img, band), fwd
     y0, y1 = min(H, band[0] * 16), min(H, band[1] * 16)
     full = torch.zeros_like(img)
     full[:, y0:y1] = img[:, y0:y1]

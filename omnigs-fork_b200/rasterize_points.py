@@ -130,7 +130,8 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
 def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                    cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                    dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                   imageBuffer, camera_type=PINHOLE, reduce_accumulators=None, out=None):
+                                   imageBuffer, camera_type=PINHOLE, reduce_accumulators=None, out=None,
+                                   accumulators=None, conic_out=None):
     """reference src/rasterize_points.cu:166-285.
 
     Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
@@ -141,7 +142,13 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
     backward kernels, e.g. ``lambda t: dist.all_reduce(t)``; the per-Gaussian backward then runs on the
     sums, so every rank ends with the full-frame gradients after exchanging 48 B/Gaussian.
 
-    ``out`` (extension for data-parallel training): a ``parallel.GradientBucket``; the five optimiser-facing
+    ``accumulators`` (with ``reduce_accumulators``): a caller-owned [P,12] float32 tensor to use instead of the
+    geometry buffer's (e.g. ``parallel.BandExchange`` keeps it in symmetric memory and sums it with the library's own
+    NVLink kernel).
+
+    ``conic_out`` (tests): a [P,4] float32 tensor that receives the reference's intermediate dL_dconic (.x, .y, .w used).
+
+    ``out`` (extension for data-parallel training): a dense ``parallel.GradientBucket``; the five optimiser-facing
     gradients are then written into its flat buffer (and returned as views of it) instead of fresh tensors.
     """
     _require_cuda(means3D, "means3D")
@@ -172,7 +179,7 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                 _f32c(t) for t in (background, means3D, colors, scales, rotations, cov3D_precomp, viewmatrix,
                                    sh, campos, dL_dout_color))
             radii_c = radii.contiguous()
-            outs = (_ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors),
+            outs = (_ptr(dL_dmeans2D), _ptr(conic_out), _ptr(dL_dopacity), _ptr(dL_dcolors),
                     _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
             if camera_type == PINHOLE:
                 projmatrix = _f32c(projmatrix)
@@ -189,6 +196,17 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                     _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
                     _ptr(viewmatrix), _ptr(campos), _ptr(radii_c),
                     _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer), _ptr(dL), *outs, _stream(device)))
+            elif accumulators is not None:
+                if accumulators.dtype != torch.float32 or accumulators.numel() != 12 * P or not accumulators.is_contiguous():
+                    raise RuntimeError("accumulators must be a contiguous float32 [P,12] tensor")
+                check(lib.ogs_lonlat_backward_render_into(
+                    P, int(R), W, H, _ptr(background), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                    _ptr(dL), _ptr(accumulators), _stream(device)))
+                reduce_accumulators(accumulators)
+                check(lib.ogs_lonlat_backward_finish_from(
+                    P, int(degree), M, W, H, _ptr(means3D_c), _ptr(sh), _ptr(scales), float(scale_modifier),
+                    _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(campos), _ptr(radii_c),
+                    _ptr(geomBuffer), _ptr(accumulators), *outs, _stream(device)))
             else:
                 check(lib.ogs_lonlat_backward_render(
                     P, int(R), W, H, _ptr(background), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
@@ -202,6 +220,87 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
             if M == 0:
                 dL_dsh = torch.zeros((P, 0, 3), **opts)
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def RasterizeGaussiansBackwardView(background, means3D, radii, scales, rotations, scale_modifier, viewmatrix,
+                                   dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer,
+                                   bucket, view_slot, want_means2D=False):
+    """One view of a multi-view / data-parallel step into a FACTORED ``parallel.GradientBucket`` (extension,
+    SURVEY.md §8(e-a); C ABI ogs_lonlat_backward_view).  ``view_slot`` 0 starts the step (the bucket's geometry
+    gradients and statistics are written), later slots are added inside the per-Gaussian backward; the view's
+    clamp-masked dL/dRGB goes to ``bucket["dL_drgb"][view_slot]`` — dL_dsh of the step is rebuilt from all views'
+    factors by ``parallel.exchange_bucket``.  lonlat camera, SH colours, scales + rotations (the live combination).
+    Returns dL_dmeans2D [P,3] when asked for (else None)."""
+    _require_cuda(means3D, "means3D")
+    lib = load_library()
+    device = means3D.device
+    P = int(means3D.size(0))
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    M = int(sh.size(1)) if sh.size(0) != 0 else 0
+    if not bucket.factored or bucket.P != P or bucket.M != M or not (0 <= view_slot < bucket.views_per_rank):
+        raise RuntimeError("bucket does not fit this call (factored, same P / M, view_slot < views_per_rank)")
+    m2d = torch.empty((P, 3), dtype=torch.float32, device=device) if want_means2D else None
+    if P == 0:
+        return m2d
+    with torch.cuda.device(device):
+        background, means3D_c, scales, rotations, viewmatrix, sh, campos, dL = (
+            _f32c(t) for t in (background, means3D, scales, rotations, viewmatrix, sh, campos, dL_dout_color))
+        check(lib.ogs_lonlat_backward_view(
+            P, int(degree), M, int(R), W, H, _ptr(background), _ptr(means3D_c), _ptr(sh), _ptr(scales),
+            float(scale_modifier), _ptr(rotations), _ptr(viewmatrix), _ptr(campos), _ptr(radii.contiguous()),
+            _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer), _ptr(dL),
+            0 if view_slot == 0 else 1, _ptr(bucket["dL_dmeans3D"]), _ptr(bucket["dL_dopacity"]), _ptr(bucket["dL_dscales"]),
+            _ptr(bucket["dL_drotations"]), _ptr(bucket["dL_drgb"][view_slot]), _ptr(bucket["xyz_gradient_accum"]),
+            _ptr(bucket["denom"]), _ptr(bucket.max_radii2D), _ptr(m2d), _stream(device)))
+    return m2d
+
+
+def RasterizeGaussiansGeometry(means3D, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, campos,
+                               image_height, image_width):
+    """First half of a pipelined lonlat forward (extension for data-parallel training): everything that does not read
+    the SH coefficients — per-Gaussian geometry, depth order, emission and tile sort (ogs_lonlat_forward_stage1_geometry
+    + ogs_lonlat_forward_bin).  Returns the state RasterizeGaussiansBlend completes."""
+    _require_cuda(means3D, "means3D")
+    lib = load_library()
+    device = means3D.device
+    P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+    byte_opts = dict(dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        radii = torch.empty((P,), dtype=torch.int32, device=device)
+        means3D_c, opacity, scales, rotations, cov3D_precomp, viewmatrix, campos = (
+            _f32c(t) for t in (means3D, opacity, scales, rotations, cov3D_precomp, viewmatrix, campos))
+        geomBuffer = torch.empty((lib.ogs_geom_bytes(P),), **byte_opts)
+        imgBuffer = torch.empty((lib.ogs_img_bytes(W, H),), **byte_opts)
+        n = ctypes.c_int64(0)
+        st = _stream(device)
+        check(lib.ogs_lonlat_forward_stage1_geometry(
+            P, W, H, _ptr(means3D_c), _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations),
+            _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(campos), _ptr(radii), _ptr(geomBuffer), _ptr(imgBuffer),
+            ctypes.byref(n), st))
+        rendered = int(n.value)
+        need = lib.ogs_binning_bytes(rendered, W, H)
+        binningBuffer = torch.empty((-(-need // _BINNING_GRANULE) * _BINNING_GRANULE,), **byte_opts)
+        check(lib.ogs_lonlat_forward_bin(P, W, H, rendered, _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), st))
+    return dict(R=rendered, radii=radii, geom=geomBuffer, binning=binningBuffer, img=imgBuffer, P=P, H=H, W=W,
+                means3D=means3D_c, campos=campos)
+
+
+def RasterizeGaussiansBlend(state, background, sh, degree):
+    """Second half: colours from the SH coefficients (ogs_lonlat_forward_colors) and the blend (ogs_lonlat_forward_blend).
+    Returns RasterizeGaussiansCUDA's 6-tuple; results are bit-identical to the one-call forward."""
+    lib = load_library()
+    device = state["geom"].device
+    P, H, W, R = state["P"], state["H"], state["W"], state["R"]
+    with torch.cuda.device(device):
+        out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=device)
+        background, sh = _f32c(background), _f32c(sh)
+        st = _stream(device)
+        M = int(sh.size(1)) if sh.size(0) != 0 else 0
+        check(lib.ogs_lonlat_forward_colors(P, int(degree), M, _ptr(state["means3D"]), _ptr(sh), _ptr(state["campos"]),
+                                            _ptr(state["radii"]), _ptr(state["geom"]), st))
+        check(lib.ogs_lonlat_forward_blend(P, W, H, R, _ptr(background), _ptr(state["geom"]), _ptr(state["binning"]),
+                                           _ptr(state["img"]), _ptr(out_color), st))
+    return R, out_color, state["radii"], state["geom"], state["binning"], state["img"]
 
 
 def markVisible(means3D, viewmatrix, projmatrix, camera_type=PINHOLE):

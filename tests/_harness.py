@@ -164,3 +164,95 @@ def reference_training_iteration(rasterize, ref, leaves, adam, stats, viewmatrix
         ref.densify_stats(stats[0], stats[1], stats[2], radii, means2D.grad)
         adam.step()
     return value
+
+
+# ------------------------------------------------------------------ gradient parity with a double-precision arbiter
+ILL_CONDITIONED = ("dL_dcov3D", "dL_dscales", "dL_drotations")
+CHAIN_OUTPUTS = ("dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations")
+
+
+def grad_stats(a, b):
+    """max-norm relative error, the SURVEY 8(c) per-element excess (max of |a-b| - (1e-4|b| + 1e-6 max|b|), relative to
+    max|b|; <= 0 passes) and the fraction of elements over that bound."""
+    import torch
+    a = torch.as_tensor(a).double().flatten().cpu()
+    b = torch.as_tensor(b).double().flatten().cpu()
+    if b.numel() == 0:
+        return dict(rel=0.0, excess=0.0, frac_over=0.0, scale=0.0)
+    scale = float(b.abs().max()) + 1e-300
+    diff = (a - b).abs()
+    bound = 1e-4 * b.abs() + 1e-6 * scale
+    return dict(rel=float(diff.max()) / scale, excess=float((diff - bound).max()) / scale,
+                frac_over=float((diff > bound).double().mean()), scale=scale)
+
+
+def chain_truth(scene, view, radii, clamped, cov3D, dL_dmeans2D, dL_dconic, dL_dcolors, degree=3):
+    """The per-Gaussian backward chain evaluated in DOUBLE on the host (the product's own gaussian_grad.cuh, double
+    instantiation: tests/native/grad_math_host.cu) from a given implementation's render-backward outputs.  Returns a
+    dict of float64 numpy arrays for CHAIN_OUTPUTS."""
+    import test_grad_math_cpu as T
+    fwd = dict(radii=radii, clamped=clamped, cov3D=cov3D)
+    g = dict(dL_dmeans2D=dL_dmeans2D, dL_dconic=dL_dconic, dL_dcolors=dL_dcolors)
+    return T.run_host(T.load_host_lib(), "ogs_grad_host_f64", np.float64, scene, fwd, view, g, degree)
+
+
+def config_parity_report(name, verbose=False):
+    """Gradient parity of one BASELINE config against the live reference (oracle/_ref), with two yardsticks beside the raw
+    difference: the reference's own run-to-run noise (second backward on the same forward state: unordered float
+    atomics) and, for the per-Gaussian chain, the distance of EACH implementation from a double evaluation of the chain
+    on its own render-backward outputs.  Returns {tensor: {...}} plus integer-parity flags."""
+    import torch
+    ref = load_reference()
+    assert ref is not None, "oracle/_ref/omnigs_ref.so missing"
+    sm = scene_mod
+    scene = sm.make_config_scene(name)
+    view = sm.random_view(300 + sm.CONFIG_INDEX[name])
+    d = torch_inputs(scene, view)
+    P = scene.P
+    dL = torch.from_numpy(sm.make_grad_image(scene.W, scene.H, 99)).cuda()
+    cpu = lambda t: t.detach().cpu().numpy()
+
+    fo = run_forward(pkg, d)
+    conic = torch.empty((P, 4), device="cuda")
+    go = [g.clone() for g in run_backward(pkg, d, fo, dL, conic_out=conic)]
+    go2 = run_backward(pkg, d, fo, dL)
+    so = pkg.export_forward_state(P, scene.W, scene.H, fo[0], fo[3], fo[4], fo[5], want_keys=False)
+    ours = dict(R=fo[0], radii=fo[2].clone(), image=fo[1].clone(), ranges=so["ranges"].clone(), n_contrib=so["n_contrib"].clone(),
+                point_list=so["point_list"].clone(), clamped=cpu(so["clamped"]), cov3D=cpu(so["cov3D"]), conic=cpu(conic))
+    own_noise = {n: grad_stats(a, b) for n, a, b in zip(GRAD_NAMES, go2, go)}
+    del fo, so, go2, conic
+    torch.cuda.empty_cache()
+
+    fr = run_forward(ref, d)
+    empty = d["colors"]
+    gr = ref.lonlat_backward_with_conic(d["background"], d["means3D"], fr[2], empty, d["scales"], d["rotations"], 1.0,
+                                        d["cov3D_precomp"], d["viewmatrix"], dL, d["sh"], 3, d["campos"], fr[3], fr[0], fr[4], fr[5])
+    gr2 = run_backward(ref, d, fr, dL)
+    torch.cuda.synchronize()
+    T = ((scene.W + 15) // 16) * ((scene.H + 15) // 16)
+    rgeom = ref.unpack_geom(fr[3], P)
+    rimg = ref.unpack_img(fr[5], scene.W * scene.H, T)
+    rbin_pl = ref.unpack_binning(fr[4], fr[0])["point_list"] if fr[0] == ours["R"] else None
+    report = {"P": P, "image": [scene.W, scene.H], "num_rendered": int(fr[0]), "integers": {
+        "num_rendered": bool(fr[0] == ours["R"]), "radii": bool(torch.equal(fr[2], ours["radii"])),
+        "ranges": bool(torch.equal(rimg["ranges"], ours["ranges"])),
+        "point_list": bool(rbin_pl is not None and torch.equal(rbin_pl, ours["point_list"])),
+        "n_contrib": bool(torch.equal(rimg["n_contrib"], ours["n_contrib"])),
+        "image_bits": bool(torch.equal(fr[1].view(torch.int32), ours["image"].view(torch.int32)))}, "tensors": {}}
+    del rbin_pl
+    # double-precision arbiter of the per-Gaussian chain, fed with each side's OWN render-backward outputs
+    t_ref = chain_truth(scene, view, cpu(fr[2]), cpu(rgeom["clamped"]), cpu(rgeom["cov3D"]), cpu(gr[0]), cpu(gr[8]), cpu(gr[1]))
+    t_ours = chain_truth(scene, view, cpu(ours["radii"]), ours["clamped"], ours["cov3D"], cpu(go[0]), ours["conic"], cpu(go[1]))
+    for i, n in enumerate(GRAD_NAMES):
+        row = {"ours_vs_ref": grad_stats(go[i], gr[i]), "ref_vs_ref": grad_stats(gr2[i], gr[i]), "ours_vs_ours": own_noise[n]}
+        if n in CHAIN_OUTPUTS:
+            row["ref_vs_double"] = grad_stats(gr[i], torch.from_numpy(t_ref[n].reshape(tuple(gr[i].shape))))
+            row["ours_vs_double"] = grad_stats(go[i], torch.from_numpy(t_ours[n].reshape(tuple(go[i].shape))))
+        report["tensors"][n] = row
+        if verbose:
+            extra = (f"  ref-double {row['ref_vs_double']['rel']:.2e}  ours-double {row['ours_vs_double']['rel']:.2e}"
+                     if n in CHAIN_OUTPUTS else "")
+            print(f"  {n:14s} ours-ref {row['ours_vs_ref']['rel']:.2e} (excess {row['ours_vs_ref']['excess']:+.1e}, over "
+                  f"{row['ours_vs_ref']['frac_over']:.1e})  ref-ref {row['ref_vs_ref']['rel']:.2e} (excess "
+                  f"{row['ref_vs_ref']['excess']:+.1e})  ours-ours {row['ours_vs_ours']['rel']:.2e}{extra}", flush=True)
+    return report

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_workspace_queries():
     lib = h.pkg.load_library()
-    assert lib.ogs_abi_version() == 1
+    assert lib.ogs_abi_version() == 2
     assert lib.ogs_geom_bytes(0) > 0
     g1, g2 = lib.ogs_geom_bytes(1000), lib.ogs_geom_bytes(2000)
     assert g2 > g1 > 1000 * 100

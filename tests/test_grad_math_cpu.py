@@ -1,0 +1,111 @@
+"""CPU check of the product's per-Gaussian backward math (omnigs-fork_b200/csrc/gaussian_grad.cuh, the code the CUDA
+kernel instantiates in float) against the oracle's restatement of the reference (oracle/lonlat_oracle.c,
+backward.cu:30-151, 156-292, 297-552).
+
+gaussian_grad.cuh is written from the chain rule in matrix form, so the two are different programs for the same
+function.  The header is templated on the scalar type: the double instantiation is the ground truth, and the test
+asserts (1) formula equality: the oracle's float result agrees with the double one to float accuracy on every output,
+(2) numerical quality: the product's float evaluation is no further from the double truth than the reference
+restatement's float evaluation (this is what bounds the ill-conditioned tensors dL_dcov3D / dL_dscales / dL_drotations,
+whose error is amplified by 1 / det(cov2D)^2 in both programs)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import _harness as h
+from oracle import oracle
+
+sm = h.scene_mod
+HERE = os.path.dirname(os.path.abspath(__file__))
+ILL = ("dL_dcov3D", "dL_dscales", "dL_drotations")
+
+
+def build_host_lib(out=None):
+    """Host-only build of gaussian_grad.cuh (float + double instantiations); __graft_entry__.build() calls this so the
+    GPU box finds tests/native/grad_math_host.so ready."""
+    out = out or os.path.join(HERE, "native", "grad_math_host.so")
+    src = os.path.join(HERE, "native", "grad_math_host.cu")
+    hdr = os.path.join(h.ROOT, "omnigs-fork_b200", "csrc", "gaussian_grad.cuh")
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return out
+    base = ["nvcc", "-x", "cu", "-O1", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-shared", "-o", out, src]
+    try:
+        subprocess.check_call(base + ["-Xcompiler", "-fPIC,-ffp-contract=off,-fopenmp", "-Xlinker", "-lgomp"], stderr=subprocess.DEVNULL)
+    except subprocess.CalledProcessError:
+        subprocess.check_call(base + ["-Xcompiler", "-fPIC,-ffp-contract=off"])
+    return out
+
+
+def load_host_lib():
+    return ctypes.CDLL(build_host_lib())
+
+
+@pytest.fixture(scope="module")
+def host_lib():
+    return load_host_lib()
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def run_host(lib, name, dtype, scene, fwd, view, g, degree, pin=None):
+    P, M = scene.P, scene.shs.shape[1]
+    out = dict(dL_dmeans3D=np.zeros((P, 3), dtype), dL_dcov3D=np.zeros((P, 6), dtype), dL_dsh=np.zeros((P, M, 3), dtype),
+               dL_dscales=np.zeros((P, 3), dtype), dL_drotations=np.zeros((P, 4), dtype))
+    f = np.float32
+    c = lambda a: np.ascontiguousarray(a, f)
+    proj = None if pin is None else c(pin["projmatrix"]).reshape(-1)
+    keep = [c(scene.means3D), np.ascontiguousarray(fwd["radii"], np.int32), c(scene.shs), np.ascontiguousarray(fwd["clamped"], np.uint8),
+            c(scene.scales), c(scene.rotations), c(fwd["cov3D"]), c(view[0]).reshape(-1), c(view[1]).reshape(-1),
+            c(g["dL_dmeans2D"]), c(g["dL_dconic"]), c(g["dL_dcolors"])]
+    getattr(lib, name)(
+        P, degree, M, _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]), _p(keep[4]), _p(keep[5]), ctypes.c_float(1.0),
+        _p(keep[6]), _p(keep[7]), _p(proj), scene.W, scene.H,
+        ctypes.c_float(0.0 if pin is None else pin["tan_fovx"]), ctypes.c_float(0.0 if pin is None else pin["tan_fovy"]),
+        _p(keep[8]), _p(keep[9]), _p(keep[10]), _p(keep[11]),
+        _p(out["dL_dmeans3D"]), _p(out["dL_dcov3D"]), _p(out["dL_dsh"]), _p(out["dL_dscales"]), _p(out["dL_drotations"]))
+    return out
+
+
+@pytest.mark.parametrize("camera,degree,seed", [("lonlat", 3, 1), ("lonlat", 1, 2), ("pinhole", 3, 3), ("pinhole", 2, 4)])
+def test_product_backward_math_against_reference_restatement(host_lib, camera, degree, seed):
+    W, H = 640, 320
+    scene = sm.make_scene(40000, W, H, 0.02, 500 + seed, pole_frac=0.1, seam_frac=0.03)
+    bg = np.zeros(3, np.float32)
+    if camera == "pinhole":
+        pv = sm.perspective_view(600 + seed, W, H, 80.0)
+        view, pin = (pv[0], pv[2]), dict(projmatrix=pv[1], tan_fovx=pv[3], tan_fovy=pv[4])
+    else:
+        view, pin = sm.random_view(600 + seed), None
+    kw = dict(shs=scene.shs, degree=degree, scales=scene.scales, rotations=scene.rotations, pinhole=pin)
+    fwd = oracle.forward(scene.means3D, scene.opacities, view[0], view[1], W, H, bg, **kw)
+    dL = sm.make_grad_image(W, H, 700 + seed)
+    og = oracle.backward(fwd, dL, scene.means3D, view[0], view[1], W, H, bg, **kw)   # the restatement, float
+    mine32 = run_host(host_lib, "ogs_grad_host_f32", np.float32, scene, fwd, view, og, degree, pin)
+    truth = run_host(host_lib, "ogs_grad_host_f64", np.float64, scene, fwd, view, og, degree, pin)
+    vis = fwd["radii"] > 0
+    assert vis.sum() > 1000
+    report = {}
+    for n in ("dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"):
+        t = truth[n].reshape(scene.P, -1)[vis]
+        a = mine32[n].reshape(scene.P, -1).astype(np.float64)[vis]
+        b = og[n].reshape(scene.P, -1).astype(np.float64)[vis]
+        scale = np.abs(t).max() + 1e-300
+        err_mine = np.abs(a - t).max() / scale
+        err_ref = np.abs(b - t).max() / scale
+        report[n] = (err_mine, err_ref)
+        # (1) same function: the reference restatement evaluated in float sits at float accuracy from our double evaluation
+        #     (ill-conditioned rows amplify float rounding, never beyond 2e-3 of the tensor's scale)
+        assert err_ref < (2e-3 if n in ILL else 2e-4), (n, err_ref)
+        # ... and element-wise for the bulk of the rows
+        rel = np.abs(b - t) / (np.abs(t) + 1e-6 * scale)
+        assert np.median(rel) < 1e-5, (n, float(np.median(rel)))
+        # (2) our float evaluation is at least as close to the truth as the reference's float evaluation (x2 slack + floor)
+        assert err_mine <= 2.0 * err_ref + 2e-6, (n, err_mine, err_ref)
+    print(camera, degree, {k: (f"{v[0]:.1e}", f"{v[1]:.1e}") for k, v in report.items()})
+    # rows of culled Gaussians are never touched
+    assert not mine32["dL_dmeans3D"][~vis].any()

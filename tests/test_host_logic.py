@@ -79,7 +79,7 @@ def test_bench_algorithmic_bytes_match_the_survey_yardstick():
 def test_emit_slot_float_division_is_exact_with_its_correction():
     """binning.cu emit_slot(): q = local / w is evaluated as trunc(float_rz(local) * rcp.approx(float(w))) followed by a
     two-sided correction.  Restated in float32 numpy with the reciprocal off by -1 / 0 / +1 ulp (rcp.approx's error
-    bound) on adversarial slots (remainders next to 0 and w - 1, local up to 2^30, q up to 2^16): always exact."""
+    bound) on adversarial slots (remainders next to 0 and w - 1, local up to 2^31, q up to 2^16): always exact."""
     rng = np.random.default_rng(1)
     n = 1_500_000
     w = rng.integers(1, 65536, n).astype(np.int64)
@@ -87,7 +87,7 @@ def test_emit_slot_float_division_is_exact_with_its_correction():
     r = np.where(rng.random(n) < 0.5, rng.integers(0, 3, n), w - 1 - rng.integers(0, 3, n)).astype(np.int64)
     r = np.clip(r, 0, w - 1)
     local = q * w + r
-    keep = local < (1 << 30)
+    keep = local < (1 << 31)
     w, q, local = w[keep], q[keep], local[keep]
 
     def f32_rz(x):   # __uint2float_rz

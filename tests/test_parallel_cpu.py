@@ -124,41 +124,161 @@ def test_band_rows_balances_instances_and_covers_all_rows():
     assert par.band_rows([5, 5], 4)[-1][1] == 2   # more ranks than rows: trailing bands may be empty
 
 
+def _view_data(v, P=257):
+    """Fake per-view backward outputs: geometry gradients, radii, the clamp-masked dL/dRGB factor and a camera centre."""
+    grads, radii = _make(v, P)
+    g = torch.Generator().manual_seed(900 + v)
+    drgb = torch.randn((P, 3), generator=g) * (radii > 0)[:, None]
+    campos = torch.randn(3, generator=g) * 0.3
+    return grads, radii, drgb, campos
+
+
+def _means(P=257):
+    return torch.randn((P, 3), generator=torch.Generator().manual_seed(7)) * 5
+
+
+def _write_view(bucket, slot, grads, radii, drgb):
+    """What RasterizeGaussiansBackwardView does on the GPU (ogs_lonlat_backward_view): the step's first view writes the
+    geometry gradients and statistics, later views are added; the view's dL/dRGB factor goes to its slot."""
+    vis = radii > 0
+    gn = torch.where(vis, grads["dL_dmeans2D"][:, :2].norm(dim=-1), torch.zeros(radii.shape))
+    if slot == 0:
+        for n in ("dL_dmeans3D", "dL_dopacity", "dL_dscales", "dL_drotations"):
+            bucket[n].copy_(grads[n])
+        bucket["xyz_gradient_accum"].copy_(gn)
+        bucket["denom"].copy_(vis)
+        bucket.max_radii2D.copy_(radii)
+    else:
+        for n in ("dL_dmeans3D", "dL_dopacity", "dL_dscales", "dL_drotations"):
+            bucket[n].add_(grads[n])
+        bucket["xyz_gradient_accum"].add_(gn)
+        bucket["denom"].add_(vis)
+        torch.maximum(bucket.max_radii2D, radii.float(), out=bucket.max_radii2D)
+    bucket["dL_drgb"][slot].copy_(drgb)
+
+
 def _multiview_worker(rank, world, port, out, views):
-    """One step = `views` views: every rank accumulates its own views into the step's bucket and ONE exchange sums the
-    ranks (the flow of tools/bench_dp_views.py / BASELINE configs[2])."""
+    """One step = `views` views (BASELINE configs[2]): every rank accumulates its own views into the step's factored
+    bucket inside the backward, ONE exchange sums the ranks and rebuilds dL_dsh from all views' dL/dRGB factors."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    bucket = par.GradientBucket(257, 16, "cpu")
-    work = par.GradientBucket(257, 16, "cpu", peer=False)
-    for k, v in enumerate(par.views_for_rank(views, rank, world)):
-        grads, radii = _make(v)
-        tgt = bucket if k == 0 else work
-        for n in par.OPTIMISED:
-            tgt[n].copy_(grads[n])
-        par.fill_view_stats(tgt, grads["dL_dmeans2D"], radii)
-        if k > 0:
-            bucket.flat += work.flat
-            torch.maximum(bucket.max_radii2D, work.max_radii2D, out=bucket.max_radii2D)
-    par.exchange_bucket(bucket)
-    if rank == 0:
-        torch.save({"flat": bucket.flat.clone(), "max_radii2D": bucket.max_radii2D.clone(),
-                    "sh": bucket["dL_dsh"].clone(), "acc": bucket["xyz_gradient_accum"].clone(), "denom": bucket["denom"].clone()}, out)
+    mine = par.views_for_rank(views, rank, world)
+    vpr = -(-views // world)
+    bucket = par.GradientBucket(257, 16, "cpu", views_per_rank=vpr)
+    if not mine:
+        bucket.zero_step()
+    for k, v in enumerate(mine):
+        grads, radii, drgb, _ = _view_data(v)
+        _write_view(bucket, k, grads, radii, drgb)
+    campos = torch.stack([_view_data(v)[3] if v < views else torch.zeros(3) for v in range(vpr * world)])
+    par.exchange_bucket(bucket, means3D=_means(), campos_views=campos, degree=3)
+    torch.save({n: bucket[n].clone() for n in ("dL_dmeans3D", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dsh",
+                                               "xyz_gradient_accum", "denom", "max_radii2D")}, out + f".{rank}")
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _check_multiview(out, world, views):
+    per_view = [_view_data(v) for v in range(views)]
+    means = _means()
+    got = [torch.load(out + f".{r}") for r in range(world)]
+    for r in range(1, world):                       # replicas end bit-identical
+        for n, t in got[0].items():
+            assert torch.equal(t, got[r][n]), (n, r)
+    g = got[0]
+    for n in ("dL_dmeans3D", "dL_dopacity", "dL_dscales", "dL_drotations"):
+        assert torch.allclose(g[n], sum(pv[0][n] for pv in per_view), atol=1e-5), n
+    # dL_dsh = sum over views of b(direction) (x) dL/dRGB: the per-view rows the reference's backward writes
+    # (backward.cu:60-150: dL_dsh[k] = basis_k * dL_dRGB)
+    sh = torch.zeros(257, 16, 3)
+    for _, _, drgb, campos in per_view:
+        d = means - campos[None, :]
+        sh += par.sh_weights(d / d.norm(dim=-1, keepdim=True), 3)[:, :, None] * drgb[:, None, :]
+    assert torch.allclose(g["dL_dsh"], sh, atol=1e-5)
+    acc = sum(torch.where(r > 0, gr["dL_dmeans2D"][:, :2].norm(dim=-1), torch.zeros(r.shape)) for gr, r, _, _ in per_view)
+    assert torch.allclose(g["xyz_gradient_accum"], acc, atol=1e-5)
+    assert torch.equal(g["denom"], sum((r > 0).float() for _, r, _, _ in per_view))
+    assert torch.equal(g["max_radii2D"], torch.stack([r for _, r, _, _ in per_view]).max(dim=0).values.float())
 
 
 def test_multi_view_step_accumulates_locally_and_exchanges_once_world2_gloo(tmp_path):
     out, views = str(tmp_path / "mv.pt"), 4
     mp.spawn(_multiview_worker, args=(2, _free_port(), out, views), nprocs=2, join=True)
-    got = torch.load(out)
-    per_view = [_make(v) for v in range(views)]
-    assert torch.allclose(got["sh"], sum(g["dL_dsh"] for g, _ in per_view), atol=1e-5)
-    acc = sum(torch.where(r > 0, g["dL_dmeans2D"][:, :2].norm(dim=-1), torch.zeros(r.shape)) for g, r in per_view)
-    assert torch.allclose(got["acc"], acc, atol=1e-5)
-    assert torch.equal(got["denom"], sum((r > 0).float() for _, r in per_view))
-    assert torch.equal(got["max_radii2D"], torch.stack([r for _, r in per_view]).max(dim=0).values.float())
+    _check_multiview(out, 2, views)
+
+
+def test_multi_view_step_with_fewer_views_than_ranks_world2_gloo(tmp_path):
+    """A rank without a view in the step contributes zeros (it used to exchange an uninitialised bucket)."""
+    out = str(tmp_path / "mv1.pt")
+    mp.spawn(_multiview_worker, args=(2, _free_port(), out, 1), nprocs=2, join=True)
+    _check_multiview(out, 2, 1)
+
+
+def _subgroup_worker(rank, world, port, out):
+    """a bucket built for a sub-group must be exchanged over exactly that group."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    groups = [dist.new_group([0, 1]), dist.new_group([2, 3])]
+    grp = groups[rank // 2]
+    grads, radii = _make(rank)
+    bucket = par.GradientBucket(257, 16, "cpu", group=grp)
+    for n in par.OPTIMISED:
+        bucket[n].copy_(grads[n])
+    par.allreduce_bucket(bucket, grads["dL_dmeans2D"], radii)
+    try:
+        par.exchange_bucket(bucket, group=groups[1 - rank // 2])
+        wrong_group_refused = False
+    except RuntimeError:
+        wrong_group_refused = True
+    torch.save({"m3": bucket["dL_dmeans3D"].clone(), "radii": bucket.max_radii2D.clone(), "refused": wrong_group_refused}, out + f".{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucket_honours_its_process_group_world4_gloo(tmp_path):
+    out = str(tmp_path / "sg.pt")
+    mp.spawn(_subgroup_worker, args=(4, _free_port(), out), nprocs=4, join=True)
+    data = [_make(r) for r in range(4)]
+    for r in range(4):
+        got = torch.load(out + f".{r}")
+        a, b = (0, 1) if r < 2 else (2, 3)
+        assert torch.allclose(got["m3"], data[a][0]["dL_dmeans3D"] + data[b][0]["dL_dmeans3D"], atol=1e-6)
+        assert torch.equal(got["radii"], torch.maximum(data[a][1], data[b][1]).float())
+        assert got["refused"]
+
+
+def _band_worker(rank, world, port, out):
+    """SURVEY 8(e-b) on gloo: each rank owns a band of pixel rows of the frame and a partial [P,12] accumulator; the
+    band exchange all-gathers the rows and sums the accumulators."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P, W, H = 300, 70, 100
+    bands = [(0, 3), (3, 7)]                      # tile rows; the last band ends beyond H (7 * 16 = 112 > 100)
+    frame = torch.randn((3, H, W), generator=torch.Generator().manual_seed(5))
+    ex = par.BandExchange(P, W, H, "cpu")
+    y0, y1 = min(H, bands[rank][0] * 16), min(H, bands[rank][1] * 16)
+    mine = torch.full((3, H, W), float("nan"))    # rows outside the band are garbage as far as the exchange knows
+    mine[:, y0:y1] = frame[:, y0:y1]
+    full, _ = par.render_band_forward(lambda b: (0, mine, None, None, None, None), bands[rank], H, exchange=ex)
+    ex.acc.copy_(torch.randn((P, 12), generator=torch.Generator().manual_seed(50 + rank)))
+    ex.reduce_accumulators()
+    torch.save({"image": full.clone(), "acc": ex.acc.clone()}, out + f".{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_band_exchange_world2_gloo(tmp_path):
+    out = str(tmp_path / "band.pt")
+    mp.spawn(_band_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    frame = torch.randn((3, 100, 70), generator=torch.Generator().manual_seed(5))
+    acc = sum(torch.randn((300, 12), generator=torch.Generator().manual_seed(50 + r)) for r in range(2))
+    for r in range(2):
+        got = torch.load(out + f".{r}")
+        assert torch.equal(got["image"], frame)
+        assert torch.allclose(got["acc"], acc, atol=1e-6)
 
 
 def test_band_rows_properties_hold_for_arbitrary_row_loads():

@@ -542,19 +542,59 @@ def test_caller_streams_and_side_stream_ordering():
         assert_grads_close(g, base_g)
 
 
-def test_more_than_2_30_tile_instances_are_rejected():
-    """Maximum size: the tile sort carries 30-bit counts in its status words, so a frame with num_rendered >= 2^30 is
-    refused in stage 1 (OGS_ERR_TOO_MANY) before any R-sized buffer is asked for — the reference overflows its int
-    num_rendered at 2^31 instead (rasterizer_impl.cu:627-632).  32768 + 8 Gaussians that each cover all 32768 tiles of a
-    4096x2048 frame."""
-    P = 32768 + 8
-    scene = sm.make_scene(P, 4096, 2048, 0.02, 11)
-    scene.means3D[:] = (0.01, -3.0, 0.02)
+def _fan_out_scene(P, seed):
+    """P Gaussians next to the pole, each large enough to cover all 32768 tiles of a 4096x2048 frame, at distinct depths."""
+    scene = sm.make_scene(P, 4096, 2048, 0.02, seed)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    scene.means3D[:] = np.array((0.01, -3.0, 0.02), np.float32)[None, :] * rng.uniform(0.9, 1.1, (P, 1)).astype(np.float32)
     scene.scales[:] = (4.0, 4.0, 4.0)
+    return scene
+
+
+def test_more_than_2_30_tile_instances_sort_like_the_reference():
+    """Maximum size: the reference accepts any int num_rendered (rasterizer_impl.cu:627-632); round 1
+    refused R >= 2^30.  32768 + 8 Gaussians x 32768 tiles = 2^30 + 262144 instances (17 GB of binning state here, 39 GB in
+    the reference): every tile's list must be the depth order of all Gaussians; bit-exact against the reference when it
+    is on the box."""
+    P, T = 32768 + 8, 32768
+    scene = _fan_out_scene(P, 11)
     d = h.torch_inputs(scene, sm.identity_view())
-    with pytest.raises(h.pkg.OgsError, match="2\\^30"):
+    fwd = h.run_forward(h.pkg, d)
+    R = fwd[0]
+    assert R == P * T and R >= (1 << 30)
+    st = h.pkg.export_forward_state(P, scene.W, scene.H, R, fwd[3], fwd[4], fwd[5], want_keys=False)
+    ranges = st["ranges"].long() & 0xFFFFFFFF
+    assert torch.equal(ranges[:, 0], torch.arange(T, device="cuda") * P) and torch.equal(ranges[:, 1] - ranges[:, 0], torch.full((T,), P, device="cuda"))
+    # depth order (ties by index) of all P Gaussians, repeated once per tile
+    depth_bits = bits(st["depths"]).long() & 0xFFFFFFFF
+    order = torch.argsort(depth_bits * (1 << 20) + torch.arange(P, device="cuda"))
+    pl = st["point_list"].view(T, P)
+    for t0 in range(0, T, 4096):
+        assert bool((pl[t0:t0 + 4096] == order.to(torch.int32)[None, :]).all())
+    assert bool(torch.isfinite(fwd[1]).all())
+    ref = h.load_reference()
+    if ref is not None:
+        img, n_contrib = fwd[1].clone(), st["n_contrib"].clone()
+        pl_first, pl_last = pl[:64].clone(), pl[-64:].clone()
+        del fwd, st, pl
+        torch.cuda.empty_cache()
+        fr = h.run_forward(ref, d)
+        assert fr[0] == R
+        sr = h.ref_state(ref, d, fr)
+        rp = sr["point_list"].view(T, P)
+        assert torch.equal(rp[:64], pl_first) and torch.equal(rp[-64:], pl_last)
+        for t0 in range(0, T, 4096):
+            assert bool((rp[t0:t0 + 4096] == order.to(torch.int32)[None, :]).all())
+        assert torch.equal(bits(fr[1]), bits(img)) and torch.equal(sr["n_contrib"], n_contrib)
+
+
+def test_more_than_2_31_tile_instances_are_rejected():
+    """2^31 and more overflows the reference's `int num_rendered`; here stage 1 refuses (OGS_ERR_TOO_MANY) before any
+    R-sized buffer is asked for, and the library stays usable."""
+    scene = _fan_out_scene(65536 + 8, 13)
+    d = h.torch_inputs(scene, sm.identity_view())
+    with pytest.raises(h.pkg.OgsError, match="2\\^31"):
         h.run_forward(h.pkg, d)
-    # the library stays usable afterwards
     small = sm.make_scene(2000, 160, 80, 0.03, 12)
     fwd = h.run_forward(h.pkg, h.torch_inputs(small, sm.identity_view()))
     assert fwd[0] > 0 and bool(torch.isfinite(fwd[1]).all())
