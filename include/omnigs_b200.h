@@ -247,6 +247,13 @@ OGS_API int ogs_export_binning(
 	uint32_t* point_list /*[R]*/, uint64_t* point_list_keys /*[R]*/, uint32_t* ranges /*[T,2]*/,
 	float* final_T /*[H*W]*/, uint32_t* n_contrib /*[H*W]*/, void* stream);
 
+/* Measurement: the blending work of a rendered frame, independent of kernel organisation — counts (DEVICE, 4 x uint64):
+ * [0] sum over pixels of n_contrib (list entries the reference's renderCUDA visits up to each pixel's last contributor,
+ * forward.cu:403-455), [1] (pixel, Gaussian) pairs that blend, [2] entries a tile-synchronous kernel walks (the tile's
+ * largest n_contrib, per pixel), [3] pixels.  bench.py turns them into the compute roofline of the blend kernels. */
+OGS_API int ogs_export_pair_counts(int P, int W, int H, int64_t num_rendered, const char* geom_buffer,
+                                   const char* binning_buffer, const char* img_buffer, uint64_t* counts, void* stream);
+
 /*
  * Perspective camera (camera_type = 1): CudaRasterizer::Rasterizer::forward / backward /
  * markVisible (cuda_rasterizer/rasterizer.h:39-92, rasterizer_impl.cu:170-183,250-530) with preprocessCUDA

@@ -67,6 +67,7 @@ SYMBOLS = {
     "ogs_lonlat_backward_view": (_c_int, [_c_int] * 3 + [_c_i64, _c_int, _c_int] + [_p] * 4 + [_c_f] + [_p] * 4 + [_p] * 4
                                  + [_c_int] + [_p] * 9 + [_p]),
     "ogs_sh_gradient_from_views": (_c_int, [_c_int] * 4 + [_p] * 6 + [_p]),
+    "ogs_export_pair_counts": (_c_int, [_c_int] * 3 + [_c_i64] + [_p] * 4 + [_p]),
     "ogs_band_rows_allgather": (_c_int, [_p, _c_int, _c_int, _p] + [_c_int] * 4 + [_p]),
     "ogs_peer_allreduce": (_c_int, [_p, _c_int, _c_int, _c_sz, _c_sz, _p]),
     "ogs_multimem_allreduce": (_c_int, [_p, _c_int, _c_int, _c_sz, _c_sz, _p]),

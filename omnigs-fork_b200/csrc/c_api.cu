@@ -970,4 +970,22 @@ OGS_API int ogs_export_binning(
 	return OGS_OK;
 }
 
+// Measurement: how much blending work a rendered frame holds (see pair_count_kernel).  counts: DEVICE array of 4 uint64.
+OGS_API int ogs_export_pair_counts(int P, int W, int H, int64_t num_rendered, const char* geom_buffer,
+                                   const char* binning_buffer, const char* img_buffer, uint64_t* counts, void* stream)
+{
+	if (int rc = check_image(W, H)) return rc;
+	if (!img_buffer || !counts) return fail(OGS_ERR_INVALID_ARG, "img_buffer / counts is NULL");
+	if (P <= 0 || num_rendered <= 0) {
+		OGS_CUDA_TRY(cudaMemsetAsync(counts, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
+		return OGS_OK;
+	}
+	if (!geom_buffer || !binning_buffer) return fail(OGS_ERR_INVALID_ARG, "buffers missing");
+	ImageState img = ImageState::carve(const_cast<char*>(img_buffer), W, H);
+	GeomState g = GeomState::carve(const_cast<char*>(geom_buffer), P);
+	BinningState b = BinningState::carve(const_cast<char*>(binning_buffer), num_rendered, W, H);
+	return launch_pair_count(img.ranges, b.point_list, W, H, g.g0, g.g1, img.n_contrib,
+	                         reinterpret_cast<unsigned long long*>(counts), (cudaStream_t)stream);
+}
+
 } // extern "C"

@@ -116,6 +116,8 @@ int launch_rebuild_keys(const ImageState& img, const BinningState& b, const Geom
 int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
                       const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars, const float* bg,
                       float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st);
+int launch_pair_count(const uint2* ranges, const uint32_t* point_list, int W, int H, const float4* g0, const float4* g1,
+                      const uint32_t* n_contrib, unsigned long long* counts, cudaStream_t st);
 int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, int H, const float* bg,
                       const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,

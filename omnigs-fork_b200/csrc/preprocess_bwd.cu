@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 			if constexpr (kBulkSH) {
 				mbar_wait(&s_bar, 0);
 				sh_waited = true;
-				float shr[kShRowFloats], dshr[kShRowFloats];
+				// one register row: colour_backward reads coefficient k before it writes gradient k, so dL/dsh overwrites the
+				// coefficients in place (48 registers less than separate rows)
+				float shr[kShRowFloats];
 				if constexpr (kMode == 2) {
 #pragma unroll
 					for (int k = 0; k < 3; k++) shr[k] = s_sh[kRawDcOffset + tid * 3 + k];
@@ -191,22 +193,24 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(c
 						shr[4 * k] = q.x; shr[4 * k + 1] = q.y; shr[4 * k + 2] = q.z; shr[4 * k + 3] = q.w;
 					}
 				}
-#pragma unroll
-				for (int k = 0; k < kShRowFloats; k++) dshr[k] = 0.f;   // rows beyond (D+1)^2 stay zero
 				auto sh = [&shr](int k, int c) { return shr[3 * k + c]; };
-				auto dsh = [&dshr](int k, int c, float v) { dshr[3 * k + c] = v; };
+				auto dsh = [&shr](int k, int c, float v) { shr[3 * k + c] = v; };
 				dm3 = grad::colour_backward<float>(a.D, mean, cam, sh, drgb, dsh);
 				if (write_sh) {
+					const int n3 = 3 * (a.D + 1) * (a.D + 1);
+#pragma unroll
+					for (int k = 0; k < kShRowFloats; k++)
+						if (k >= n3) shr[k] = 0.f;   // rows beyond (D+1)^2 get zero gradient
 					if constexpr (kMode == 2) {
 #pragma unroll
-						for (int k = 0; k < 3; k++) s_sh[kRawDcOffset + tid * 3 + k] = dshr[k];
+						for (int k = 0; k < 3; k++) s_sh[kRawDcOffset + tid * 3 + k] = shr[k];
 #pragma unroll
-						for (int k = 0; k < kRawRestFloats; k++) s_sh[tid * kRawRestFloats + k] = dshr[3 + k];
+						for (int k = 0; k < kRawRestFloats; k++) s_sh[tid * kRawRestFloats + k] = shr[3 + k];
 					} else {
 						float4* row = reinterpret_cast<float4*>(&s_sh[tid * kShPitchFloats]);
 #pragma unroll
 						for (int k = 0; k < kShRowFloats / 4; k++)
-							row[k] = make_float4(dshr[4 * k], dshr[4 * k + 1], dshr[4 * k + 2], dshr[4 * k + 3]);
+							row[k] = make_float4(shr[4 * k], shr[4 * k + 1], shr[4 * k + 2], shr[4 * k + 3]);
 					}
 					sh_row_ready = true;
 				}

@@ -139,6 +139,60 @@ __global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_
 	}
 }
 
+// Measurement only (ogs_export_pair_counts): the amount of blending WORK in a frame, independent of how a kernel organises
+// it.  One thread per pixel walks its tile's list the way the reference's renderCUDA does (forward.cu:403-455) up to the
+// pixel's last contributor and counts  [0] list entries visited (= sum of n_contrib),  [1] pairs that blend (power <= 0 and
+// alpha >= 1/255),  [2] list entries a tile-synchronous kernel walks (max n_contrib of the tile, per pixel),  [3] pixels.
+__global__ void __launch_bounds__(kRenderThreads) pair_count_kernel(
+	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
+	const float4* __restrict__ g0, const float4* __restrict__ g1, const uint32_t* __restrict__ n_contrib,
+	unsigned long long* __restrict__ counts)
+{
+	__shared__ unsigned long long s_cnt[4];
+	__shared__ int s_max;
+	const int tile = blockIdx.x;
+	const int px = (tile % gx) * kTile + (threadIdx.x % kTile), py = (tile / gx) * kTile + (threadIdx.x / kTile);
+	const bool inside = px < W && py < H;
+	if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
+	if (threadIdx.x == 0) s_max = 0;
+	__syncthreads();
+	const uint2 range = ranges[tile];
+	const int last = inside ? (int)n_contrib[(size_t)W * py + px] : 0;
+	atomicMax(&s_max, last);
+	const float2 pixf = { (float)px, (float)py };
+	unsigned long long blended = 0;
+	for (int i = 0; i < last; i++) {
+		const uint32_t id = point_list[range.x + i];
+		const float4 a = g0[id];
+		const float4 b = g1[id];
+		float dx, dy;
+		const float power = pair_power(a.x, a.y, a.z, a.w, b.x, pixf, dx, dy);
+		if (power > 0.0f) continue;
+		if (fminf(0.99f, __fmul_rn(b.y, expf(power))) < kAlphaMin) continue;
+		blended++;
+	}
+	atomicAdd(&s_cnt[0], (unsigned long long)last);
+	atomicAdd(&s_cnt[1], blended);
+	if (inside) atomicAdd(&s_cnt[3], 1ull);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		atomicAdd(&counts[0], s_cnt[0]);
+		atomicAdd(&counts[1], s_cnt[1]);
+		atomicAdd(&counts[2], (unsigned long long)s_max * s_cnt[3]);
+		atomicAdd(&counts[3], s_cnt[3]);
+	}
+}
+
+int launch_pair_count(const uint2* ranges, const uint32_t* point_list, int W, int H, const float4* g0, const float4* g1,
+                      const uint32_t* n_contrib, unsigned long long* counts, cudaStream_t st)
+{
+	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
+	OGS_CUDA_TRY(cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), st));
+	pair_count_kernel<<<gx * gy, kRenderThreads, 0, st>>>(ranges, point_list, W, H, gx, g0, g1, n_contrib, counts);
+	OGS_CUDA_TRY(cudaGetLastError());
+	return OGS_OK;
+}
+
 int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
                       const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars, const float* bg,
                       float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st)

@@ -75,8 +75,7 @@ def test_views_accumulate_in_the_backward_and_sh_is_rebuilt_from_factors(step):
         assert rel(bucket[n], want) < 2e-5, (n, rel(bucket[n], want))
     for n in ("dL_dscales", "dL_drotations"):          # ill-conditioned: same bound as assert_own_runs_close
         want = sum(g[name[n]] for g in dense)
-        err = (bucket[n] - want).abs() / float(want.abs().max())
-        assert float((err > 3e-4).double().mean()) <= 1e-4 and float(err.max()) <= 5e-3, n
+        assert rel(bucket[n], want) < 3e-4, (n, rel(bucket[n], want))
     want_sh = sum(g[name["dL_dsh"]] for g in dense)
     assert rel(bucket["dL_dsh"], want_sh) < 2e-5
     for v in range(len(views)):
@@ -145,11 +144,7 @@ def test_split_forward_is_bit_identical_and_stage2_repeatable(step):
     assert torch.equal(bits(a["rgb"]), bits(b["rgb"]))
     ga, gb = h.run_backward(h.pkg, d, one, dL[1]), h.run_backward(h.pkg, d, two, dL[1])
     for n, x, y in zip(h.GRAD_NAMES, ga, gb):
-        if n in ("dL_dcov3D", "dL_dscales", "dL_drotations"):
-            err = (x - y).abs() / (float(y.abs().max()) + 1e-30)
-            assert float((err > 3e-4).double().mean()) <= 1e-4 and float(err.max()) <= 5e-3, n
-        else:
-            assert rel(x, y) < 2e-5, n
+        assert rel(x, y) < (3e-4 if n in ("dL_dcov3D", "dL_dscales", "dL_drotations") else 2e-5), (n, rel(x, y))
     # stage 2 again on the same buffers (the scan's ticket / look-back words were only zeroed by stage 1)
     import ctypes
     lib = h.pkg.load_library()

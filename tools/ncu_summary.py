@@ -1,7 +1,7 @@
 """Turn ncu reports into the markdown tables of profiles/*_ncu_summary.md (run where ncu is installed; no GPU needed).
 
   python tools/ncu_summary.py launches gpurun_out/ev_launches.csv
-  python tools/ncu_summary.py full gpurun_out/ev_frame.ncu-rep [traffic.json to update]
+  python tools/ncu_summary.py full gpurun_out/ev_frame.ncu-rep [profiles/kernel_counters.json to write] [source stamp]
 """
 import csv, io, json, re, subprocess, sys
 from collections import OrderedDict
@@ -36,7 +36,7 @@ def launches(path):
         print(f"| `{k}` | {c} | {ns / c / 1e3:.1f} | {100 * ns / total:.1f} % |")
 
 
-def full(path, traffic_path=None):
+def full(path, traffic_path=None, stamp=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[0]
@@ -48,6 +48,7 @@ def full(path, traffic_path=None):
     print("| kernel | us | DRAM read MB | DRAM write MB | DRAM % of peak | warps active % | regs | issue active % | warp inst (M) | L1/shared % |")
     print("|---|---|---|---|---|---|---|---|---|---|")
     traffic = {}
+    counters = {}
     for r in rows[2:]:
         name = short(r[col["Kernel Name"]])
         def bytes_of(metric):
@@ -64,18 +65,39 @@ def full(path, traffic_path=None):
               f"{g(r, 'sm__inst_issued.avg.pct_of_peak_sustained_active'):.0f} | {g(r, 'inst_executed') / 1e6:.1f} | "
               f"{g(r, 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed'):.0f} |")
         traffic[name] = int(rd + wr)
+        red = g(r, "lts__t_sectors_srcunit_tex_op_red.sum") if "lts__t_sectors_srcunit_tex_op_red.sum" in col else float("nan")
+        redq = g(r, "lts__t_requests_srcunit_tex_op_red.sum") if "lts__t_requests_srcunit_tex_op_red.sum" in col else float("nan")
+        counters.setdefault(name, []).append({
+            "duration_us": dur_us, "dram_bytes": int(rd + wr), "warp_instructions": int(g(r, "inst_executed")),
+            "issue_active_pct": g(r, "sm__inst_issued.avg.pct_of_peak_sustained_active"),
+            "registers": int(g(r, "launch__registers_per_thread")),
+            "l2_red_sectors": None if red != red else int(red), "l2_red_requests": None if redq != redq else int(redq),
+            "l2_red_bytes": None if red != red else int(red) * 32})
     if traffic_path:
-        t = json.load(open(traffic_path))
-        for key, pat in (("render_bwd", "render_bwd_kernel"), ("render_fwd", "render_fwd_kernel"),
-                         ("preprocess_fwd", "preprocess_lonlat_fwd_kernel"), ("preprocess_bwd", "preprocess_lonlat_bwd_kernel")):
-            for n, b in traffic.items():
-                if n.startswith(pat):
-                    t[key] = b
-        json.dump(t, open(traffic_path, "w"), indent=1)
+        # profiles/kernel_counters.json: per stage group of bench.py, summed over the group's launches of ONE frame
+        groups = {"preprocess_fwd": ["preprocess_lonlat_fwd_kernel"], "render_fwd": ["render_fwd_kernel"],
+                  "render_bwd": ["render_bwd_kernel"], "preprocess_bwd": ["preprocess_lonlat_bwd_kernel"],
+                  "binning": ["depth_histogram_kernel", "onesweep_pass_kernel", "gather_scan_kernel", "tile_ranges_kernel"]}
+        out = {"source_stamp": stamp, "workload": "C2, one frame (tools/dbg_step.py)", "capture": path,
+               "how": "ncu --set full --clock-control none; dram_bytes = dram__bytes_read.sum + dram__bytes_write.sum, "
+                      "l2_red_sectors = lts__t_sectors_srcunit_tex_op_red.sum (32 B each), per launch, summed per group", "kernels": {}}
+        for key, pats in groups.items():
+            launches = [c for n, cs in counters.items() if any(n.startswith(p) for p in pats) for c in cs]
+            if not launches:
+                continue
+            agg = {"launches": len(launches)}
+            for f in ("duration_us", "dram_bytes", "warp_instructions", "l2_red_sectors", "l2_red_requests", "l2_red_bytes"):
+                vals = [c[f] for c in launches if c[f] is not None]
+                agg[f] = sum(vals) if vals else None
+            tot = sum(c["duration_us"] for c in launches)
+            agg["issue_active_pct"] = sum(c["issue_active_pct"] * c["duration_us"] for c in launches) / tot if tot else None
+            agg["registers"] = max(c["registers"] for c in launches)
+            out["kernels"][key] = agg
+        json.dump(out, open(traffic_path, "w"), indent=1)
 
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
     else:
-        full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
+        full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None, sys.argv[4] if len(sys.argv) > 4 else None)
