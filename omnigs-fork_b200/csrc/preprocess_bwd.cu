@@ -36,8 +36,11 @@ constexpr int kPreBwdThreads = 128;
 
 // kMode as in preprocess_fwd.cu: 0 plain SH rows, 1 bulk SH rows, 2 raw parameters (bulk), 3 raw parameters (plain)
 // kPinhole: the perspective camera's covariance and screen-position branches (backward.cu:156-292, :583-597).
+#ifndef OGS_PREBWD_MINBLOCKS
+#define OGS_PREBWD_MINBLOCKS 1
+#endif
 template <int kMode, bool kPinhole = false>
-__global__ void __launch_bounds__(kPreBwdThreads) preprocess_lonlat_bwd_kernel(const PreprocessBwdArgs a)
+__global__ void __launch_bounds__(kPreBwdThreads, OGS_PREBWD_MINBLOCKS) preprocess_lonlat_bwd_kernel(const PreprocessBwdArgs a)
 {
 	constexpr bool kBulkSH = (kMode == 1 || kMode == 2);
 	constexpr bool kRaw = (kMode >= 2);

@@ -63,16 +63,19 @@ py::dict unpack_img(torch::Tensor imgBuffer, int64_t N, int64_t T)
 	return d;
 }
 
-// The reference's LonlatRasterizer::backward (cuda_rasterizer/rasterizer.h:126-154) called with our own output tensors, so
+// The reference's {Lonlat,}Rasterizer::backward (cuda_rasterizer/rasterizer.h:66-92,126-154) called with our own output tensors, so
 // that its intermediate dL_dconic — which RasterizeGaussiansBackwardCUDA allocates and drops (src/rasterize_points.cu:203) —
 // can be inspected: the input of its per-Gaussian chain, needed to evaluate that chain in double (tests/test_parity_gpu.py).
 // Same argument preparation as src/rasterize_points.cu:246-276.  Returns the 8-tuple plus dL_dconic [P,4].
-std::vector<torch::Tensor> lonlat_backward_with_conic(
+// camera_type 3 -> LonlatRasterizer::backward, camera_type 1 -> Rasterizer::backward (rasterizer.h:66-92; projmatrix and
+// tan(fov/2) are used by that camera only).
+std::vector<torch::Tensor> backward_with_conic(
 	const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii, const torch::Tensor& colors,
 	const torch::Tensor& scales, const torch::Tensor& rotations, float scale_modifier, const torch::Tensor& cov3D_precomp,
-	const torch::Tensor& viewmatrix, const torch::Tensor& dL_dout_color, const torch::Tensor& sh, int degree,
+	const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, float tan_fovx, float tan_fovy,
+	const torch::Tensor& dL_dout_color, const torch::Tensor& sh, int degree,
 	const torch::Tensor& campos, const torch::Tensor& geomBuffer, int R, const torch::Tensor& binningBuffer,
-	const torch::Tensor& imageBuffer)
+	const torch::Tensor& imageBuffer, int camera_type)
 {
 	const int P = means3D.size(0), H = dL_dout_color.size(1), W = dL_dout_color.size(2);
 	const int M = sh.size(0) != 0 ? sh.size(1) : 0;
@@ -81,7 +84,7 @@ std::vector<torch::Tensor> lonlat_backward_with_conic(
 	torch::Tensor dL_dmeans3D = z({P, 3}), dL_dmeans2D = z({P, 3}), dL_dcolors = z({P, 3}), dL_dconic = z({P, 2, 2}),
 	              dL_dopacity = z({P, 1}), dL_dcov3D = z({P, 6}), dL_dsh = z({P, M, 3}), dL_dscales = z({P, 3}),
 	              dL_drotations = z({P, 4}), dpx_dt = z({P, 3}), dpy_dt = z({P, 3});
-	if (P != 0)
+	if (P != 0 && camera_type == 3)
 		CudaRasterizer::LonlatRasterizer::backward(P, degree, M, R, background.contiguous().data_ptr<float>(), W, H,
 			means3D.contiguous().data_ptr<float>(), sh.contiguous().data_ptr<float>(), colors.contiguous().data_ptr<float>(),
 			scales.data_ptr<float>(), scale_modifier, rotations.data_ptr<float>(), cov3D_precomp.contiguous().data_ptr<float>(),
@@ -91,6 +94,17 @@ std::vector<torch::Tensor> lonlat_backward_with_conic(
 			dL_dmeans2D.data_ptr<float>(), dL_dconic.data_ptr<float>(), dL_dopacity.data_ptr<float>(), dL_dcolors.data_ptr<float>(),
 			dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), dL_dsh.data_ptr<float>(), dL_dscales.data_ptr<float>(),
 			dL_drotations.data_ptr<float>(), dpx_dt.data_ptr<float>(), dpy_dt.data_ptr<float>());
+	else if (P != 0)
+		CudaRasterizer::Rasterizer::backward(P, degree, M, R, background.contiguous().data_ptr<float>(), W, H,
+			means3D.contiguous().data_ptr<float>(), sh.contiguous().data_ptr<float>(), colors.contiguous().data_ptr<float>(),
+			scales.data_ptr<float>(), scale_modifier, rotations.data_ptr<float>(), cov3D_precomp.contiguous().data_ptr<float>(),
+			viewmatrix.contiguous().data_ptr<float>(), projmatrix.contiguous().data_ptr<float>(), campos.contiguous().data_ptr<float>(),
+			tan_fovx, tan_fovy, radii.contiguous().data_ptr<int>(),
+			reinterpret_cast<char*>(geomBuffer.contiguous().data_ptr()), reinterpret_cast<char*>(binningBuffer.contiguous().data_ptr()),
+			reinterpret_cast<char*>(imageBuffer.contiguous().data_ptr()), dL_dout_color.contiguous().data_ptr<float>(),
+			dL_dmeans2D.data_ptr<float>(), dL_dconic.data_ptr<float>(), dL_dopacity.data_ptr<float>(), dL_dcolors.data_ptr<float>(),
+			dL_dmeans3D.data_ptr<float>(), dL_dcov3D.data_ptr<float>(), dL_dsh.data_ptr<float>(), dL_dscales.data_ptr<float>(),
+			dL_drotations.data_ptr<float>());
 	return { dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dconic.view({P, 4}) };
 }
 
@@ -103,7 +117,7 @@ PYBIND11_MODULE(omnigs_ref, m)
 	m.def("RasterizeGaussiansBackwardCUDA", &RasterizeGaussiansBackwardCUDA);
 	m.def("markVisible", &markVisible);
 	m.def("unpack_geom", &unpack_geom);
-	m.def("lonlat_backward_with_conic", &lonlat_backward_with_conic);
+	m.def("backward_with_conic", &backward_with_conic);
 	m.def("unpack_binning", &unpack_binning);
 	m.def("unpack_img", &unpack_img);
 }

@@ -52,15 +52,18 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_host(lib, name, dtype, scene, fwd, view, g, degree, pin=None):
+def run_host(lib, name, dtype, scene, fwd, view, g, degree, pin=None, use_sh=True, use_scales=True):
+    """use_sh=False: precomputed colours (no colour branch); use_scales=False: precomputed cov3D (no scale / rotation branch)."""
     P, M = scene.P, scene.shs.shape[1]
     out = dict(dL_dmeans3D=np.zeros((P, 3), dtype), dL_dcov3D=np.zeros((P, 6), dtype), dL_dsh=np.zeros((P, M, 3), dtype),
                dL_dscales=np.zeros((P, 3), dtype), dL_drotations=np.zeros((P, 4), dtype))
     f = np.float32
     c = lambda a: np.ascontiguousarray(a, f)
     proj = None if pin is None else c(pin["projmatrix"]).reshape(-1)
-    keep = [c(scene.means3D), np.ascontiguousarray(fwd["radii"], np.int32), c(scene.shs), np.ascontiguousarray(fwd["clamped"], np.uint8),
-            c(scene.scales), c(scene.rotations), c(fwd["cov3D"]), c(view[0]).reshape(-1), c(view[1]).reshape(-1),
+    keep = [c(scene.means3D), np.ascontiguousarray(fwd["radii"], np.int32), c(scene.shs) if use_sh else None,
+            np.ascontiguousarray(fwd["clamped"], np.uint8),
+            c(scene.scales) if use_scales else None, c(scene.rotations) if use_scales else None, c(fwd["cov3D"]),
+            c(view[0]).reshape(-1), c(view[1]).reshape(-1),
             c(g["dL_dmeans2D"]), c(g["dL_dconic"]), c(g["dL_dcolors"])]
     getattr(lib, name)(
         P, degree, M, _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]), _p(keep[4]), _p(keep[5]), ctypes.c_float(1.0),
