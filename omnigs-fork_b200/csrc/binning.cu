@@ -18,6 +18,14 @@
 //
 // HBM traffic at R instances: 8R (first pass, which emits its own input) + 12R (second pass) = 20R bytes, against
 // 12R + (8 + 24*6)R = 164R for the reference's data flow.
+//
+// Column-segment path (default whenever the tile grid is at most 512 x 512; "classic" above otherwise and with
+// OGS_SEGMENT_SORT=0).  A Gaussian's rect is w columns of h tiles.  Sorting by (y, x) = sorting stably by x, then by y, and
+// all h tiles of one column of one Gaussian share x — so the x pass runs over the S = sum(w) ~ R / 5 column SEGMENTS
+// (emitted on the fly from the depth order), and only the y pass touches all R instances (expanding every sorted segment
+// along y on the fly, slot = y0 + local: no division) and writes the final list: ONE R-sized pass that stores 4 bytes per
+// instance.  Extra work: a second emission-offset scan over the S sorted segments and the x digit starts (a difference
+// array filled by the first scan).  Same output bits: the order is the stable (y, x, depth, index) order either way.
 #include "ogs_common.cuh"
 #include "launchers.cuh"
 #include <cstdlib>
@@ -36,7 +44,8 @@ struct Status32 {
 	static OGS_D word inclusive(uint32_t v) { return 0x80000000u | v; }
 	static OGS_D bool empty(word w) { return w == 0u; }
 	static OGS_D bool is_inclusive(word w) { return (w & 0x80000000u) != 0u; }
-	static OGS_D uint32_t value(word w) { return (w & 0x80000000u) ? (w & 0x7FFFFFFFu) : w - 1u; }
+	static OGS_D uint32_t raw(word w) { return w; }
+	static constexpr uint32_t kPartialBias = 1u, kInclusiveBias = 0x80000000u;
 	static OGS_D word load(const word* p) { return ld_acquire(p); }
 	static OGS_D void store(word* p, word w) { st_release(p, w); }
 };
@@ -46,7 +55,8 @@ struct Status64 {
 	static OGS_D word inclusive(uint32_t v) { return (2ull << 62) | v; }
 	static OGS_D bool empty(word w) { return (w >> 62) == 0ull; }
 	static OGS_D bool is_inclusive(word w) { return (w >> 62) == 2ull; }
-	static OGS_D uint32_t value(word w) { return (uint32_t)w; }
+	static OGS_D uint32_t raw(word w) { return (uint32_t)w; }
+	static constexpr uint32_t kPartialBias = 0u, kInclusiveBias = 0u;
 	static OGS_D word load(const word* p)
 	{
 		word v;
@@ -125,7 +135,7 @@ struct OnesweepSmem {
 
 constexpr int kLookbackBatch = 8;
 
-// Load-balanced emission of tile instances (see emit_instances below): staging area for one block of
+// Load-balanced emission of tile instances (emit_prepare / emit_slot below): staging area for one block of
 // kEmitPerBlock consecutive output slots.  The fused first tile-sort pass overlays it on OnesweepSmem.
 constexpr int kEmitPerBlock = 2048;
 static_assert(kEmitPerBlock == kSortItemsPerBlock, "the fused emit + sort pass produces one sort tile per block");
@@ -146,7 +156,10 @@ constexpr size_t kOnesweepSmemBytes = sizeof(OnesweepSmem) > sizeof(EmitSmem) ? 
 template <typename S>
 OGS_D uint32_t lookback_sum(const typename S::word* __restrict__ status, int tile, size_t stride, size_t offset)
 {
-	uint32_t excl = 0;
+	// Sum of the published values back to the nearest inclusive word.  The words are added up RAW and the encoding's
+	// biases (Status32: +1 per partial word, bit 31 on the inclusive one) are taken off once at the end, which keeps the
+	// per-word work at one add + two tests.
+	uint32_t raw = 0, partials = 0;
 	int t = tile - 1;
 	while (true) {
 		typename S::word s[kLookbackBatch];
@@ -161,15 +174,16 @@ OGS_D uint32_t lookback_sum(const typename S::word* __restrict__ status, int til
 				if (S::empty(s[i])) {
 					consumed = i;            // not published yet: poll again from this tile
 				} else {
-					excl += S::value(s[i]);
+					raw += S::raw(s[i]);
 					if (S::is_inclusive(s[i])) done = true;
+					else partials++;
 				}
 			}
 		}
 		if (done) break;
 		t -= consumed;
 	}
-	return excl;
+	return raw - partials * S::kPartialBias - S::kInclusiveBias;
 }
 
 
@@ -244,6 +258,23 @@ OGS_D void emit_slot(const EmitSmem& em, uint32_t o, uint32_t o0, int gx, uint32
 	gid = em.gid[src];
 }
 
+// Column-segment path, x pass: slot -> (x, Gaussian id) of the local-th column of the owning Gaussian's rect.
+OGS_D void emit_slot_column(const EmitSmem& em, uint32_t o, uint32_t o0, int gx, uint32_t& key, uint32_t& gid)
+{
+	const uint32_t src = em.src[o - o0];
+	uint32_t x = (em.rect[src].x & 0xFFFFu) + (o - em.off[src]);
+	if (x >= (uint32_t)gx) x -= (uint32_t)gx;   // rects that wrap around the longitude seam (opt-in mode)
+	key = x;
+	gid = em.gid[src];
+}
+// Column-segment path, y pass: slot -> (y, Gaussian id) of the local-th tile of the owning column segment.
+OGS_D void emit_slot_row(const EmitSmem& em, uint32_t o, uint32_t o0, uint32_t& key, uint32_t& gid)
+{
+	const uint32_t src = em.src[o - o0];
+	key = (em.rect[src].y & 0xFFFFu) + (o - em.off[src]);
+	gid = em.gid[src];
+}
+
 // kEmit: the pass generates its (tile key, Gaussian id) pairs itself (emit_prepare / emit_slot) instead of loading
 // them: the first tile-sort pass then needs no materialised unsorted list (saves writing and re-reading 8 R bytes).
 struct EmitSource {
@@ -254,7 +285,10 @@ struct EmitSource {
 	int gx;
 };
 
-template <int BITS, bool kEmit = false>
+// kEmit: 0 = keys / values are loaded, 1 = rect emission (tile id keys), 2 = column segments (x keys), 3 = segments
+// expanded along y (y keys).  n_dev != NULL: the item count is a device value (number of column segments) and the grid an
+// upper bound; CTAs beyond it leave at once.
+template <int BITS, int kEmit = 0>
 #ifndef OGS_SORT_MINBLOCKS
 #define OGS_SORT_MINBLOCKS 5
 #endif
@@ -263,7 +297,7 @@ __global__ void __launch_bounds__(kSortThreads, OGS_SORT_MINBLOCKS) onesweep_pas
 	uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
 	uint32_t n, int shift,
 	const uint32_t* __restrict__ digit_counts, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket,
-	const EmitSource es, const bool counts_are_starts)
+	const EmitSource es, const bool counts_are_starts, const uint32_t* __restrict__ n_dev)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
@@ -273,9 +307,14 @@ __global__ void __launch_bounds__(kSortThreads, OGS_SORT_MINBLOCKS) onesweep_pas
 	constexpr uint32_t mask = (uint32_t)nbins - 1u;
 
 	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+	if (n_dev) {
+		n = *n_dev;
+		__syncthreads();
+		if ((uint64_t)s_tile * kSortItemsPerBlock >= n) return;   // uniform: the grid was sized for an upper bound of n
+	}
 	uint32_t key[kSortItems];
 	uint32_t val[kSortItems];
-	if constexpr (kEmit) {
+	if constexpr (kEmit != 0) {
 		// the emission staging area overlays the sort's shared memory; it is dead once the pairs are in registers
 		__syncthreads();
 		EmitSmem& em = *reinterpret_cast<EmitSmem*>(smem_raw);
@@ -286,7 +325,11 @@ __global__ void __launch_bounds__(kSortThreads, OGS_SORT_MINBLOCKS) onesweep_pas
 			const uint32_t idx = o0 + warp * (32 * kSortItems) + k * 32 + lane;
 			key[k] = 0xFFFFFFFFu;
 			val[k] = 0u;
-			if (idx < n) emit_slot(em, idx, o0, es.gx, key[k], val[k]);
+			if (idx < n) {
+				if constexpr (kEmit == 1) emit_slot(em, idx, o0, es.gx, key[k], val[k]);
+				else if constexpr (kEmit == 2) emit_slot_column(em, idx, o0, es.gx, key[k], val[k]);
+				else emit_slot_row(em, idx, o0, key[k], val[k]);
+			}
 		}
 		__syncthreads();
 	}
@@ -307,7 +350,7 @@ __global__ void __launch_bounds__(kSortThreads, OGS_SORT_MINBLOCKS) onesweep_pas
 	// ---- load (warp-striped); count digits and publish the tile's counts before the (slow) ranking ----
 	uint32_t rank[kSortItems];
 	const uint32_t warp_base = tile_base + warp * (32 * kSortItems);
-	if constexpr (!kEmit) {
+	if constexpr (kEmit == 0) {
 #pragma unroll
 		for (int k = 0; k < kSortItems; k++) {
 			uint32_t idx = warp_base + k * 32 + lane;
@@ -323,7 +366,7 @@ __global__ void __launch_bounds__(kSortThreads, OGS_SORT_MINBLOCKS) onesweep_pas
 	for (int b = tid; b < nbins; b += kSortThreads)
 		Status32::store(&status[(size_t)tile * nbins + b], tile == 0 ? Status32::inclusive(sm.tile_hist[b]) : Status32::partial(sm.tile_hist[b]));
 	// values travel with the keys: issue their loads now, they are consumed after the look-back
-	if constexpr (!kEmit) {
+	if constexpr (kEmit == 0) {
 #pragma unroll
 		for (int k = 0; k < kSortItems; k++) {
 			uint32_t idx = warp_base + k * 32 + lane;
@@ -424,16 +467,26 @@ struct ScanSmem {
 	uint32_t tile;
 	uint32_t tile_excl;
 };
+// kCount: what a source contributes — 0: counts[order[i]] (tiles of a Gaussian's rect), 1: the rect's width (column segments
+// of a Gaussian; also fills the difference array of the segments' x coverage), 2: the rect's height (tiles of one column
+// segment; `order` = Gaussian id of the sorted segments, n = *n_dev of them, the grid is an upper bound).
+template <int kCount>
 __global__ void __launch_bounds__(kSortThreads) gather_scan_kernel(
-	const uint32_t* __restrict__ counts, const uint32_t* __restrict__ order, uint32_t n,
+	const uint32_t* __restrict__ counts, const uint32_t* __restrict__ order, uint32_t n, const uint32_t* __restrict__ n_dev,
+	const uint2* __restrict__ rect, int gx, int* __restrict__ col_diff,
 	uint32_t* __restrict__ out, unsigned long long* __restrict__ status, unsigned int* __restrict__ ticket,
 	uint32_t* __restrict__ first_src, const unsigned long long* __restrict__ total)
 {
 	__shared__ ScanSmem sm;
+	__shared__ int s_col[kCount == 1 ? kMaxBins + 1 : 1];
 	const int tid = threadIdx.x;
 	if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+	if (kCount == 1)
+		for (int b = tid; b <= gx; b += kSortThreads) s_col[b] = 0;
+	if (n_dev) n = *n_dev;
 	__syncthreads();
 	const uint32_t tile = sm.tile;
+	if ((uint64_t)tile * kSortItemsPerBlock >= n && !(tile == 0 && n == 0)) return;   // uniform
 	const uint32_t base = tile * (uint32_t)kSortItemsPerBlock + tid * kSortItems; // blocked arrangement
 
 	uint32_t v[kSortItems];
@@ -441,7 +494,28 @@ __global__ void __launch_bounds__(kSortThreads) gather_scan_kernel(
 #pragma unroll
 	for (int k = 0; k < kSortItems; k++) {
 		uint32_t i = base + k;
-		v[k] = (i < n) ? counts[order[i]] : 0u;
+		v[k] = 0u;
+		if (i < n) {
+			const uint32_t g = order[i];
+			if (kCount == 0) {
+				v[k] = counts[g];
+			} else if (kCount == 1) {
+				if (counts[g] > 0u) {
+					const uint2 rc = rect[g];
+					const int x0 = (int)(rc.x & 0xFFFFu), x1 = (int)(rc.x >> 16);
+					v[k] = (uint32_t)(x1 - x0);
+					atomicAdd(&s_col[x0], 1);
+					atomicAdd(&s_col[min(x1, gx)], -1);
+					if (x1 > gx) {               // the part of a seam-wrapping rect that starts again at column 0
+						atomicAdd(&s_col[0], 1);
+						atomicAdd(&s_col[x1 - gx], -1);
+					}
+				}
+			} else {
+				const uint2 rc = rect[g];
+				v[k] = (rc.y >> 16) - (rc.y & 0xFFFFu);
+			}
+		}
 		sum += v[k];
 	}
 	uint32_t incl = sum;
@@ -452,6 +526,9 @@ __global__ void __launch_bounds__(kSortThreads) gather_scan_kernel(
 	}
 	if ((tid & 31) == 31) sm.warp_tmp[tid >> 5] = incl;
 	__syncthreads();
+	if (kCount == 1)
+		for (int b = tid; b <= gx; b += kSortThreads)
+			if (s_col[b]) atomicAdd(&col_diff[b], s_col[b]);
 	uint32_t warp_off = 0, tile_total = 0;
 #pragma unroll
 	for (int w = 0; w < kSortThreads / 32; w++) {
@@ -489,6 +566,30 @@ __global__ void __launch_bounds__(kSortThreads) gather_scan_kernel(
 		run += v[k];
 		if (i == n - 1) out[n] = run;
 	}
+}
+
+// x digit starts of the column-segment pass: difference array -> coverage counts -> exclusive prefix.  One block.
+__global__ void __launch_bounds__(kMaxBins) col_starts_kernel(const int* __restrict__ col_diff, int gx, uint32_t* __restrict__ starts)
+{
+	__shared__ uint32_t s_w[kMaxBins / 32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	auto block_inclusive = [&](uint32_t v) {
+		uint32_t incl = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += u;
+		}
+		__syncthreads();
+		if (lane == 31) s_w[warp] = incl;
+		__syncthreads();
+		uint32_t off = 0;
+		for (int w = 0; w < warp; w++) off += s_w[w];
+		return incl + off;
+	};
+	const uint32_t cover = block_inclusive(tid < gx ? (uint32_t)col_diff[tid] : 0u);   // segments that cover column tid
+	const uint32_t c = tid < gx ? cover : 0u;
+	starts[tid] = block_inclusive(c) - c;
 }
 
 // ------------------------------------------------------------------ tile counts -> ranges + digit histograms
@@ -540,6 +641,41 @@ __global__ void __launch_bounds__(1024) tile_ranges_kernel(
 		}
 	}
 	__syncthreads();
+	// column-segment path: y digit starts = exclusive prefix of the rows' instance counts (row sums of tile_count)
+	if (plan.segments) {
+		__shared__ uint32_t s_row[kMaxBins];
+		for (int y = warp; y < kMaxBins; y += nwarps) {
+			uint32_t part = 0;
+			if (y < gy)
+				for (int x = lane; x < gx; x += 32) part += tile_count[y * gx + x];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+			if (lane == 0) s_row[y] = part;
+		}
+		__syncthreads();
+		if (warp == 0) {
+			constexpr int kPerLane = kMaxBins / 32;
+			uint32_t v[kPerLane], sum = 0;
+#pragma unroll
+			for (int k = 0; k < kPerLane; k++) {
+				v[k] = s_row[lane * kPerLane + k];
+				sum += v[k];
+			}
+			uint32_t incl = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= o) incl += u;
+			}
+			uint32_t run = incl - sum;
+#pragma unroll
+			for (int k = 0; k < kPerLane; k++) {
+				tile_hist[kRowStartsRow * kMaxBins + lane * kPerLane + k] = run;
+				run += v[k];
+			}
+		}
+		__syncthreads();
+	}
 	// exclusive scan over T tiles (row-major): contiguous chunk per thread
 	const int chunk = (T + nthreads - 1) / nthreads;
 	const int begin = min(T, tid * chunk), end = min(T, begin + chunk);
@@ -592,29 +728,6 @@ __global__ void __launch_bounds__(1024) tile_ranges_kernel(
 	}
 }
 
-// ------------------------------------------------------------------ load-balanced emission (stand-alone)
-// Materialises the unsorted (tile key, Gaussian id) list.  Each block produces kEmitPerBlock consecutive slots, so work
-// is even no matter how many tiles a single (e.g. polar) Gaussian covers, and all stores are fully coalesced.  The
-// frame path does not launch it any more (the first tile-sort pass emits on the fly, onesweep_pass_kernel<B, true>);
-// it remains for OGS_FUSED_EMIT=0 A/B measurements.
-__global__ void __launch_bounds__(kSortThreads) emit_instances_kernel(
-	const uint32_t* __restrict__ emit_offset /*P+1*/, const uint32_t* __restrict__ order /*P*/,
-	const uint2* __restrict__ rect, const uint32_t* __restrict__ first_src, uint32_t R, int gx,
-	uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ values)
-{
-	__shared__ EmitSmem em;
-	const uint32_t o0 = blockIdx.x * (uint32_t)kEmitPerBlock;
-	if (o0 >= R) return;
-	const uint32_t o1 = min(R, o0 + (uint32_t)kEmitPerBlock);
-	emit_prepare(em, blockIdx.x, o0, o1, emit_offset, order, rect, first_src);
-	for (uint32_t o = o0 + threadIdx.x; o < o1; o += kSortThreads) {
-		uint32_t key, gid;
-		emit_slot(em, o, o0, gx, key, gid);
-		tile_keys[o] = key;
-		values[o] = gid;
-	}
-}
-
 // ------------------------------------------------------------------ test-only: rebuild the 64-bit keys
 __global__ void rebuild_keys_kernel(const uint2* __restrict__ ranges, int T, const uint32_t* __restrict__ point_list,
                                     const float* __restrict__ depth, unsigned long long* __restrict__ keys)
@@ -641,6 +754,11 @@ TileSortPlan make_tile_sort_plan(int W, int H)
 		if (p.bits[i] < 1) p.bits[i] = 1;
 		s += p.bits[i];
 	}
+	// column-segment path: needs x and y to be one digit each; pays off when the classic plan has two or more passes
+	static const bool want = [] { const char* e = getenv("OGS_SEGMENT_SORT"); return e ? atoi(e) != 0 : true; }();
+	p.bits_x = (int)higher_msb((uint32_t)(gx > 1 ? gx - 1 : 1));
+	p.bits_y = (int)higher_msb((uint32_t)(gy > 1 ? gy - 1 : 1));
+	p.segments = (want && p.passes >= 2 && gx <= kMaxBins && gy <= kMaxBins) ? 1 : 0;
 	return p;
 }
 
@@ -650,8 +768,10 @@ static cudaError_t ensure_onesweep_smem()
 	const int bytes = (int)kOnesweepSmemBytes;
 	cudaError_t e = cudaSuccess;
 #define OGS_SET(B)                                                                                                          \
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_kernel<B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_kernel<B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_kernel<B, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_kernel<B, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_kernel<B, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_pass_kernel<B, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 	OGS_SET(1) OGS_SET(2) OGS_SET(3) OGS_SET(4) OGS_SET(5) OGS_SET(6) OGS_SET(7) OGS_SET(8) OGS_SET(9)
 #undef OGS_SET
 	return e;
@@ -675,7 +795,7 @@ int launch_depth_order(const GeomState& g, int P, cudaStream_t st)
 		uint32_t* vout = g.sort_val[(p + 1) & 1];
 		onesweep_pass_kernel<8><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(
 			kin, vin, kout, vout, n, 8 * p, g.depth_hist + 256 * p,
-			g.depth_status + (size_t)p * tiles * 256, tickets + p, EmitSource{}, false);
+			g.depth_status + (size_t)p * tiles * 256, tickets + p, EmitSource{}, false, nullptr);
 	}
 	// 4 passes: result back in buffer 0
 	OGS_CUDA_TRY(cudaGetLastError());
@@ -692,6 +812,14 @@ int launch_tile_ranges(const ImageState& img, int W, int H, cudaStream_t st)
 }
 
 // Emission + tile-id sort (stage 2).  Leaves the sorted Gaussian list in b.point_list.
+#define OGS_BITS_SWITCH(bits, CALL)                                                                     \
+	switch (bits) {                                                                                     \
+	case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break;     \
+	case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; case 8: CALL(8); break;     \
+	case 9: CALL(9); break;                                                                             \
+	default: return fail(OGS_ERR_INVALID_ARG, "bad radix digit width");                                 \
+	}
+
 int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const BinningState& b,
                               int P, int64_t R, int W, int H, cudaStream_t st)
 {
@@ -700,39 +828,62 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
 	const int gx = ceil_div(W, kTile);
 	const TileSortPlan plan = make_tile_sort_plan(W, H);
 	const uint32_t n = (uint32_t)R;
-	prof_begin(OGS_PROF_EMIT, st);
+	const int tiles = (int)((R + kSortItemsPerBlock - 1) / kSortItemsPerBlock);
 	// ticket and look-back words of the emission-offset scan are zeroed HERE (not only in stage 1), so stage 2 may run
 	// again on the same buffers
 	const size_t scan_tiles = (size_t)ceil_div(P, kSortItemsPerBlock);
 	unsigned int* scan_ticket = reinterpret_cast<unsigned int*>(g.scan_status + scan_tiles + 1);
 	OGS_CUDA_TRY(cudaMemsetAsync(g.scan_status, 0, sizeof(unsigned long long) * (scan_tiles + 2), st));
-	gather_scan_kernel<<<ceil_div(P, kSortItemsPerBlock), kSortThreads, 0, st>>>(
-		g.tiles_touched, g.sort_val[0], (uint32_t)P, g.emit_offset, g.scan_status, scan_ticket, b.first_src, g.scalars);
-	// OGS_FUSED_EMIT=0 materialises the unsorted list first (A/B measurements); default: pass 0 emits on the fly
-	static const bool fused = [] { const char* e = getenv("OGS_FUSED_EMIT"); return e ? atoi(e) != 0 : true; }();
-	if (!fused)
-		emit_instances_kernel<<<(unsigned)((R + kEmitPerBlock - 1) / kEmitPerBlock), kSortThreads, 0, st>>>(
-			g.emit_offset, g.sort_val[0], g.rect, b.first_src, n, gx, b.key[0], b.val[0]);
+
+	if (plan.segments) {
+		// ---- column-segment path: scan widths -> x pass over segments -> scan heights -> y pass over instances ----
+		const uint32_t* n_segments = g.emit_offset + P;            // device value S, written by the first scan
+		uint32_t* seg_gid = b.key[0];                              // x-sorted segments: Gaussian ids
+		uint32_t* seg_offset = b.key[1];                           // their emission offsets (S + 1)
+		unsigned int* seg_scan_ticket = reinterpret_cast<unsigned int*>(b.seg_scan_status + tiles + 1);
+		prof_begin(OGS_PROF_EMIT, st);
+		gather_scan_kernel<1><<<(int)scan_tiles, kSortThreads, 0, st>>>(
+			g.tiles_touched, g.sort_val[0], (uint32_t)P, nullptr, g.rect, gx, b.col_diff, g.emit_offset, g.scan_status,
+			scan_ticket, b.first_src, g.scalars + 1);
+		col_starts_kernel<<<1, kMaxBins, 0, st>>>(b.col_diff, gx, img.tile_hist + kColStartsRow * kMaxBins);
+		prof_end(OGS_PROF_EMIT, st);
+		prof_begin(OGS_PROF_TILE_SORT, st);
+		const EmitSource ex{ g.emit_offset, g.sort_val[0], g.rect, b.first_src, gx };
+#define OGS_X_PASS(B) onesweep_pass_kernel<B, 2><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(                 \
+		nullptr, nullptr, nullptr, seg_gid, n, 0, img.tile_hist + kColStartsRow * kMaxBins, b.status, b.tickets + 0, ex, true, n_segments)
+		OGS_BITS_SWITCH(plan.bits_x, OGS_X_PASS)
+#undef OGS_X_PASS
+		gather_scan_kernel<2><<<tiles, kSortThreads, 0, st>>>(
+			nullptr, seg_gid, 0u, n_segments, g.rect, gx, nullptr, seg_offset, b.seg_scan_status, seg_scan_ticket, b.first_src,
+			g.scalars);
+		const EmitSource ey{ seg_offset, seg_gid, g.rect, b.first_src, gx };
+		uint32_t* status_y = b.status + ((size_t)tiles << plan.bits_x);
+#define OGS_Y_PASS(B) onesweep_pass_kernel<B, 3><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(                 \
+		nullptr, nullptr, nullptr, b.point_list, n, 0, img.tile_hist + kRowStartsRow * kMaxBins, status_y, b.tickets + 1, ey, true, nullptr)
+		OGS_BITS_SWITCH(plan.bits_y, OGS_Y_PASS)
+#undef OGS_Y_PASS
+		prof_end(OGS_PROF_TILE_SORT, st);
+		OGS_CUDA_TRY(cudaGetLastError());
+		return OGS_OK;
+	}
+
+	prof_begin(OGS_PROF_EMIT, st);
+	gather_scan_kernel<0><<<(int)scan_tiles, kSortThreads, 0, st>>>(
+		g.tiles_touched, g.sort_val[0], (uint32_t)P, nullptr, nullptr, gx, nullptr, g.emit_offset, g.scan_status, scan_ticket,
+		b.first_src, g.scalars);
 	prof_end(OGS_PROF_EMIT, st);
 	prof_begin(OGS_PROF_TILE_SORT, st);
-	const int tiles = (int)((R + kSortItemsPerBlock - 1) / kSortItemsPerBlock);
 	const EmitSource es{ g.emit_offset, g.sort_val[0], g.rect, b.first_src, gx };
 	size_t status_off = 0;
 	for (int p = 0; p < plan.passes; p++) {
 		const bool last = (p == plan.passes - 1);
 #define OGS_SORT_ARGS                                                                                          \
 	b.key[p & 1], b.val[p & 1], last ? nullptr : b.key[(p + 1) & 1], b.val[(p + 1) & 1], n, plan.shift[p],     \
-		img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p, es, true
+		img.tile_hist + p * kMaxBins, b.status + status_off, b.tickets + p, es, true, nullptr
 #define OGS_SORT_CASE(B)                                                                                      \
-	case B:                                                                                                   \
-		if (p == 0 && fused) onesweep_pass_kernel<B, true><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(OGS_SORT_ARGS); \
-		else onesweep_pass_kernel<B, false><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(OGS_SORT_ARGS);  \
-		break;
-		switch (plan.bits[p]) {
-			OGS_SORT_CASE(1) OGS_SORT_CASE(2) OGS_SORT_CASE(3) OGS_SORT_CASE(4) OGS_SORT_CASE(5)
-			OGS_SORT_CASE(6) OGS_SORT_CASE(7) OGS_SORT_CASE(8) OGS_SORT_CASE(9)
-		default: return fail(OGS_ERR_INVALID_ARG, "bad radix digit width");
-		}
+	if (p == 0) onesweep_pass_kernel<B, 1><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(OGS_SORT_ARGS);   \
+	else onesweep_pass_kernel<B, 0><<<tiles, kSortThreads, kOnesweepSmemBytes, st>>>(OGS_SORT_ARGS)
+		OGS_BITS_SWITCH(plan.bits[p], OGS_SORT_CASE)
 #undef OGS_SORT_CASE
 #undef OGS_SORT_ARGS
 		status_off += (size_t)tiles << plan.bits[p];

@@ -6,6 +6,7 @@
 #include "ogs_common.cuh"
 #include "launchers.cuh"
 #include <cmath>
+#include <algorithm>
 
 #include <cstdlib>
 #include <mutex>
@@ -135,8 +136,8 @@ BinningState carve_binning(char* base, int64_t R, int W, int H, size_t* total)
 	BinningState b{};
 	const size_t r = (size_t)(R > 0 ? R : 0);
 	const TileSortPlan plan = make_tile_sort_plan(W, H);
-	b.key[0] = c.take<uint32_t>(r);
-	b.key[1] = c.take<uint32_t>(r);
+	b.key[0] = c.take<uint32_t>(r + 4);    // + 4: the segment path keeps S + 1 <= R + 1 emission offsets in key[1]
+	b.key[1] = c.take<uint32_t>(r + 4);
 	b.val[0] = c.take<uint32_t>(r);
 	b.val[1] = c.take<uint32_t>(r);
 	b.point_list = b.val[plan.passes & 1];
@@ -144,9 +145,12 @@ BinningState carve_binning(char* base, int64_t R, int W, int H, size_t* total)
 	size_t status_words = 0;
 	const int tiles = sort_tiles(R);
 	for (int p = 0; p < plan.passes; p++) status_words += (size_t)tiles << plan.bits[p];
+	if (plan.segments) status_words = std::max(status_words, ((size_t)tiles << plan.bits_x) + ((size_t)tiles << plan.bits_y));
 	b.status = c.take<uint32_t>(status_words);
 	b.zero_begin = reinterpret_cast<char*>(b.status);
 	b.tickets = c.take<unsigned int>(kMaxTilePasses);
+	b.seg_scan_status = c.take<unsigned long long>((size_t)tiles + 2);
+	b.col_diff = c.take<int>(kMaxBins + 1);
 	c.off = align_up(c.off, kAlign);
 	b.zero_bytes = (size_t)((base + c.off) - b.zero_begin);
 	if (total) *total = c.off + kAlign;

@@ -95,7 +95,12 @@ struct TileSortPlan {            // how the tile-id bits are split into radix pa
 	int passes;
 	int shift[kMaxTilePasses];
 	int bits[kMaxTilePasses];
+	// column-segment path (binning.cu): one pass over the Gaussians' column segments on x, one over the instances on y
+	int segments;                // 1 when the grid fits (gx, gy <= 512) and the classic plan needs two passes
+	int bits_x, bits_y;
 };
+constexpr int kColStartsRow = 2;         // rows of ImageState::tile_hist that hold the digit starts of the segment path
+constexpr int kRowStartsRow = 3;
 TileSortPlan make_tile_sort_plan(int W, int H);
 
 struct BinningState {            // per tile instance, R-sized
@@ -105,6 +110,9 @@ struct BinningState {            // per tile instance, R-sized
 	uint32_t* first_src;         // R/2048 + 2: depth-ordered source owning the first slot of each emit block
 	uint32_t* status;            // look-back status, passes x tiles x bins
 	unsigned int* tickets;       // one dynamic-tile-id counter per pass
+	// column-segment path: key[0] holds the x-sorted segments' Gaussian ids, key[1] their emission offsets
+	unsigned long long* seg_scan_status;   // look-back words of the scan over the sorted segments
+	int* col_diff;               // kMaxBins + 1: difference array of the segments' x coverage
 	char* zero_begin;
 	size_t zero_bytes;
 	static size_t bytes(int64_t R, int W, int H);

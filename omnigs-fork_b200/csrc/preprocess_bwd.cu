@@ -36,8 +36,10 @@ constexpr int kPreBwdThreads = 128;
 
 // kMode as in preprocess_fwd.cu: 0 plain SH rows, 1 bulk SH rows, 2 raw parameters (bulk), 3 raw parameters (plain)
 // kPinhole: the perspective camera's covariance and screen-position branches (backward.cu:156-292, :583-597).
+// resident CTAs per SM the kernel is compiled for: 6 (<= 85 registers) measured 0.119 ms at C2 against 0.138 ms unbounded
+// (96-110 registers, 4-5 CTAs per SM) — profiles/r02_optimisation_log.md
 #ifndef OGS_PREBWD_MINBLOCKS
-#define OGS_PREBWD_MINBLOCKS 1
+#define OGS_PREBWD_MINBLOCKS 6
 #endif
 template <int kMode, bool kPinhole = false>
 __global__ void __launch_bounds__(kPreBwdThreads, OGS_PREBWD_MINBLOCKS) preprocess_lonlat_bwd_kernel(const PreprocessBwdArgs a)

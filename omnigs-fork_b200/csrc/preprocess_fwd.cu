@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 	__shared__ float sP[kPinhole ? 16 : 1];
 	__shared__ float sCam[3];
 	__shared__ unsigned long long s_block_tiles;
+	__shared__ unsigned int s_block_cols;     // sum of the rects' widths: the number of column segments (binning.cu)
 	__shared__ __align__(16) float s_sh[kBulkSH ? kPreThreads * kShPitchFloats : 4];
 	__shared__ __align__(8) uint64_t s_bar;
 
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 	if (tid < 3) sCam[tid] = a.campos[tid];
 	if (tid == 0) {
 		s_block_tiles = 0ull;
+		s_block_cols = 0u;
 		if (kBulkSH) {
 			const int rows = min(kPreThreads, a.P - (int)blockIdx.x * kPreThreads);
 			mbar_init(&s_bar, 1);
@@ -261,12 +263,21 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_lonlat_fwd_kernel(cons
 	}
 
 	// block total of tiles_touched -> one 64-bit atomic
-	uint32_t wsum = my_tiles;
+	uint32_t wsum = my_tiles, csum = emits ? (uint32_t)(x1 - x0) : 0u;
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-	if ((tid & 31) == 0 && wsum) atomicAdd(&s_block_tiles, (unsigned long long)wsum);
+	for (int o = 16; o > 0; o >>= 1) {
+		wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+		csum += __shfl_xor_sync(0xffffffffu, csum, o);
+	}
+	if ((tid & 31) == 0 && wsum) {
+		atomicAdd(&s_block_tiles, (unsigned long long)wsum);
+		atomicAdd(&s_block_cols, csum);
+	}
 	__syncthreads();
-	if (tid == 0 && s_block_tiles) atomicAdd(a.total_tiles, s_block_tiles);
+	if (tid == 0 && s_block_tiles) {
+		atomicAdd(a.total_tiles, s_block_tiles);
+		atomicAdd(a.total_tiles + 1, (unsigned long long)s_block_cols);
+	}
 	if (tid == 0 && blockIdx.x == 0) a.total_tiles[7] = (unsigned long long)a.seam_wrap;
 }
 

@@ -26,6 +26,13 @@
 
 namespace ogs {
 
+#ifdef OGS_TILE_TIMELINE
+static __device__ unsigned long long* g_bwd_tile_clock = nullptr;
+#define OGS_BWD_CLOCK g_bwd_tile_clock
+#else
+#define OGS_BWD_CLOCK ((unsigned long long*)nullptr)
+#endif
+
 constexpr int kBwdThreads = 64;                 // two warps per tile
 constexpr int kBwdSlots = 4;                    // pixels per lane (one per 8x4 sub-block)
 #ifndef OGS_BWD_BATCH
@@ -74,7 +81,7 @@ OGS_D float ex2_approx(float x)
 
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
-	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
+	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx, int gy, int order,
 	const float* __restrict__ bg_color,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float2* __restrict__ gb,
 	const unsigned long long* __restrict__ scalars,
@@ -88,7 +95,8 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 	__shared__ int s_warp_cnt[kBwdThreads / 32];
 	__shared__ int s_max_contrib;
 
-	const int tile = blockIdx.x;
+	const int tile = tile_of_block(blockIdx.x, gx, gy, order);
+	OGS_TILE_CLOCK(OGS_BWD_CLOCK, tile, 0);
 	const int tile_x = tile % gx, tile_y = tile / gx;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const size_t HW = (size_t)H * W;
@@ -303,7 +311,15 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 			}
 		}
 	}
+	OGS_TILE_CLOCK(OGS_BWD_CLOCK, tile, 1);
 }
+
+#ifdef OGS_TILE_TIMELINE
+extern "C" __attribute__((visibility("default"))) int ogs_debug_set_bwd_tile_clock(unsigned long long* p)
+{
+	return cudaMemcpyToSymbol(g_bwd_tile_clock, &p, sizeof(p)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, int H, const float* bg,
                       const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars,
@@ -313,7 +329,8 @@ int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, in
 	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
 	// resident CTAs per SM the kernel is compiled for (register budget); OGS_BWD_MINBLOCKS is a tuning knob
 	static const int variant = [] { const char* e = getenv("OGS_BWD_MINBLOCKS"); return e ? atoi(e) : 16; }();
-#define OGS_BWD_LAUNCH(MB) render_bwd_kernel<MB><<<gx * gy, kBwdThreads, 0, st>>>(ranges, point_list, W, H, gx, bg, g0, g1, gb, \
+	static const int order = [] { const char* e = getenv("OGS_TILE_ORDER"); return e ? atoi(e) : 0; }();
+#define OGS_BWD_LAUNCH(MB) render_bwd_kernel<MB><<<gx * gy, kBwdThreads, 0, st>>>(ranges, point_list, W, H, gx, gy, order, bg, g0, g1, gb, \
 	                                                                      scalars, final_T, n_contrib, dL_dpix, grad_acc)
 	switch (variant) {
 	case 8: OGS_BWD_LAUNCH(8); break;

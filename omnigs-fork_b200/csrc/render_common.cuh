@@ -52,7 +52,10 @@ OGS_D bool gaussian_touches_box(float mx, float my, float A, float B, float C, f
 	const bool in_x = (dx_lo <= 0.f) && (dx_hi >= 0.f);
 	const bool in_y = (dy_lo <= 0.f) && (dy_hi >= 0.f);
 	if (in_x && in_y) return true;
-	if (!(A > 0.f && C > 0.f && A * C - B * B > 0.f)) return true; // not provably positive definite
+	// not provably positive definite -> keep.  The lower bound also keeps rcp.approx.ftz below in its normal range (a
+	// denormal conic entry would flush to 0 and the clamped point would no longer be the face minimiser); conic entries
+	// never exceed 1 / 0.3 (the 0.3 px blur bounds the eigenvalues of cov2D from below), so no upper guard is needed.
+	if (!(A > 1e-30f && C > 1e-30f && A * C - B * B > 0.f)) return true;
 	float qmin = INFINITY;
 	if (!in_x) {
 		const float dx = (dx_lo > 0.f) ? dx_lo : dx_hi;
@@ -88,6 +91,34 @@ OGS_D float nearest_copy_x(float mx, float tile_cx, float Wf)
 	const float d = mx - tile_cx;
 	return d > 0.5f * Wf ? mx - Wf : (d < -0.5f * Wf ? mx + Wf : mx);
 }
+
+// Which tile a CTA works on.  order 0: row-major (blockIdx.x).  order 1 (OGS_TILE_ORDER=1, measurement): tile rows
+// alternately from the top and the bottom of the frame — at an equirectangular pole the lists are longest, so the heavy rows
+// are dispatched first and the equator drains the tail; row-major inside a row.
+OGS_D int tile_of_block(int block, int gx, int gy, int order)
+{
+	if (order == 0) return block;
+	const int r = block / gx, x = block - r * gx;
+	const int row = (r & 1) ? (gy - 1 - (r >> 1)) : (r >> 1);
+	return row * gx + x;
+}
+
+// Per-tile start / end timestamps (OGS_TILE_TIMELINE builds only; tools/tile_timeline.py): what the tail of a blend
+// kernel costs is measured, not guessed.
+#ifdef OGS_TILE_TIMELINE
+OGS_D unsigned long long global_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+#define OGS_TILE_CLOCK(ptr, tile, which)                                                   \
+	do {                                                                                   \
+		if (threadIdx.x == 0 && (ptr) != nullptr) (ptr)[2 * (size_t)(tile) + (which)] = global_ns(); \
+	} while (0)
+#else
+#define OGS_TILE_CLOCK(ptr, tile, which) do { } while (0)
+#endif
 
 // One staged list entry in shared memory (48 bytes, a single base address per inner-loop iteration):
 //   a = (mean.x, mean.y, conic.x, conic.y)

@@ -19,6 +19,18 @@
 
 namespace ogs {
 
+#ifdef OGS_TILE_TIMELINE
+static __device__ unsigned long long* g_fwd_tile_clock = nullptr;
+#define OGS_FWD_CLOCK g_fwd_tile_clock
+#else
+#define OGS_FWD_CLOCK ((unsigned long long*)nullptr)
+#endif
+static int tile_order_env()
+{
+	static const int v = [] { const char* e = getenv("OGS_TILE_ORDER"); return e ? atoi(e) : 0; }();
+	return v;
+}
+
 // resident CTAs per SM: with the 52-instruction blend loop 8 (32 registers, full occupancy) measures best at C2
 // (4: 0.547, 5: 0.504, 6: 0.495, 8: 0.486 ms); with the earlier 60-instruction loop it was 5 (4: 0.598, 5: 0.558,
 // 6: 0.562, 8: 0.577)
@@ -26,7 +38,7 @@ namespace ogs {
 #define OGS_FWD_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_kernel(
-	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx,
+	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx, int gy, int order,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float2* __restrict__ gb,
 	const unsigned long long* __restrict__ scalars, const float* __restrict__ bg_color,
 	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)
@@ -34,7 +46,8 @@ __global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_
 	__shared__ StagedEntry s_e[kBatch];
 	__shared__ uint32_t s_warp_cnt[kRenderThreads / 32];
 
-	const int tile = blockIdx.x;
+	const int tile = tile_of_block(blockIdx.x, gx, gy, order);
+	OGS_TILE_CLOCK(OGS_FWD_CLOCK, tile, 0);
 	const int tile_x = tile % gx, tile_y = tile / gx;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int sub_x0 = tile_x * kTile + (warp & 1) * kSubW;
@@ -139,6 +152,7 @@ __global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_
 		out_color[1 * HW + pix_id] = __fmaf_rn(bg_color[1], T, C[1]);
 		out_color[2 * HW + pix_id] = __fmaf_rn(bg_color[2], T, C[2]);
 	}
+	OGS_TILE_CLOCK(OGS_FWD_CLOCK, tile, 1);
 }
 
 // ------------------------------------------------------------------ experiment: asynchronous staging of the Gaussian batches
@@ -366,6 +380,13 @@ int launch_pair_count(const uint2* ranges, const uint32_t* point_list, int W, in
 	return OGS_OK;
 }
 
+#ifdef OGS_TILE_TIMELINE
+extern "C" __attribute__((visibility("default"))) int ogs_debug_set_fwd_tile_clock(unsigned long long* p)
+{
+	return cudaMemcpyToSymbol(g_fwd_tile_clock, &p, sizeof(p)) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
                       const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars, const float* bg,
                       float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st)
@@ -383,8 +404,8 @@ int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, in
 		render_fwd_async_kernel<2><<<gx * gy, kRenderThreads, 0, st>>>(ranges, point_list, W, H, gx, g0, g1, gb, scalars, bg,
 		                                                              final_T, n_contrib, out_color);
 	else
-		render_fwd_kernel<<<gx * gy, kRenderThreads, 0, st>>>(ranges, point_list, W, H, gx, g0, g1, gb, scalars, bg,
-		                                                     final_T, n_contrib, out_color);
+		render_fwd_kernel<<<gx * gy, kRenderThreads, 0, st>>>(ranges, point_list, W, H, gx, gy, tile_order_env(), g0, g1, gb,
+		                                                     scalars, bg, final_T, n_contrib, out_color);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }

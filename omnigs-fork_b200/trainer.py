@@ -33,7 +33,7 @@ class OptimizationParams:
 
     def __init__(self, position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01,
                  position_lr_max_steps=30000, feature_lr=0.0025, opacity_lr=0.05, scaling_lr=0.005,
-                 rotation_lr=0.001, lambda_dssim=0.2):
+                 rotation_lr=0.001, lambda_dssim=0.2, densify_until_iter=15000):
         self.position_lr_init = position_lr_init
         self.position_lr_final = position_lr_final
         self.position_lr_delay_mult = position_lr_delay_mult
@@ -43,6 +43,7 @@ class OptimizationParams:
         self.scaling_lr = scaling_lr
         self.rotation_lr = rotation_lr
         self.lambda_dssim = lambda_dssim
+        self.densify_until_iter = densify_until_iter
 
 
 def expon_lr(step, lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, max_steps=1000000):
@@ -202,19 +203,48 @@ def densify_stats(pc, radii, dL_dmeans2D):
 
 
 def train_for_one_iteration(pc, viewmatrix, campos, gt_image, bg_color, iteration, mask=None, rows_used=None,
-                            allreduce=None):
+                            group=None):
     """One training iteration on one view (GaussianMapper::trainForOneIteration, gaussian_mapper.cpp:300-470,
-    without densification / pruning): lr schedule, render, loss, backward, densification statistics, Adam.
-    ``allreduce(grads)`` (optional) is called on the list of six gradient tensors between backward and Adam
-    (data-parallel training).  Returns (loss_out[3] device tensor, rendered image)."""
+    without densification / pruning): lr schedule, render, loss, backward, densification statistics (while
+    iteration < densify_until_iter, as :427), Adam.  Under torch.distributed with more than one rank in `group` every
+    rank renders its own view and the six gradients are summed, the two summed statistics added and the radii maxed over
+    the ranks BEFORE they are applied, so parameters AND statistics stay identical on all replicas (the fast path for
+    that is parallel.GradientBucket; this is the plain collective form).  Returns (loss_out[3] device tensor, rendered)."""
+    import torch.distributed as dist
     H, W = int(gt_image.size(1)), int(gt_image.size(2))
     pc.updateLearningRate(iteration)
     rendered, radii, ctx = render_lonlat_raw(pc, viewmatrix, campos, H, W, bg_color)
     loss_out, dL = photometric_loss(rendered, gt_image, pc.opt.lambda_dssim, mask, rows_used)
     m2d, grads = backward_lonlat_raw(pc, ctx, dL)
-    densify_stats(pc, radii, m2d)
-    if allreduce is not None:
-        allreduce(grads)
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    track = iteration < pc.opt.densify_until_iter
+    if not distributed:
+        if track:
+            densify_stats(pc, radii, m2d)
+    else:
+        work = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in grads if g.numel()]
+        if track:
+            lib = load_library()
+            P, dev = int(pc.xyz_.size(0)), pc.xyz_.device
+            gn, vis, rad = (torch.empty((P,), dtype=torch.float32, device=dev) for _ in range(3))
+            with torch.cuda.device(dev):
+                check(lib.ogs_view_stats(P, _ptr(radii), _ptr(m2d), _ptr(gn), _ptr(vis), _ptr(rad), _stream(dev)))
+            work += [dist.all_reduce(gn, op=dist.ReduceOp.SUM, group=group, async_op=True),
+                     dist.all_reduce(vis, op=dist.ReduceOp.SUM, group=group, async_op=True),
+                     dist.all_reduce(rad, op=dist.ReduceOp.MAX, group=group, async_op=True)]
+        for w in work:
+            w.wait()
+        if track:
+            apply_view_stats(pc, gn, vis, rad)
     pc.step_count += 1
     adam_step(pc.params(), grads, pc.exp_avg, pc.exp_avg_sq, pc.lr, pc.step_count)
     return loss_out, rendered
+
+
+def apply_view_stats(pc, grad_norm, visible, radius):
+    """Apply statistics summed / maxed over several views (ranks) of one step: what ogs_densify_stats does per view,
+    gaussian_mapper.cpp:427-434 and gaussian_model.cpp:839-853, for all of them at once."""
+    seen = visible > 0
+    pc.max_radii2D_.copy_(torch.where(seen, torch.maximum(pc.max_radii2D_, radius), pc.max_radii2D_))
+    pc.xyz_gradient_accum_.add_(grad_norm.view_as(pc.xyz_gradient_accum_))
+    pc.denom_.add_(visible.view_as(pc.denom_))

@@ -278,7 +278,7 @@ def parity_report(scene, view, mode="sh", bg=(0.0, 0.0, 0.0), degree=3, verbose=
     return report
 
 
-def assert_gradient_parity(rep, tag="", floor=1e-4, excess_c=4e-6):
+def assert_gradient_parity(rep, tag="", floor=1e-4, excess_c=4e-6, excess_factor=4.0):
     """The gradient bars of tests/test_parity_gpu.py on a parity_report (see that module's docstring)."""
     for n, row in rep["tensors"].items():
         o, r = row["ours_vs_ref"], row["ref_vs_ref"]
@@ -292,8 +292,10 @@ def assert_gradient_parity(rep, tag="", floor=1e-4, excess_c=4e-6):
                 bound = max(bound, 2.0 * row["ref_vs_double"]["rel"])
                 assert row["ours_vs_double"]["rel"] <= floor, (tag, n, "ours vs double", row["ours_vs_double"]["rel"])
         else:
-            # per element: |a-b| <= 1e-4|b| + 5e-6 max|b|  (excess is measured against 1e-6 max|b|)
-            assert o["excess"] <= excess_c, (tag, n, "per-element excess", o["excess"], "reference vs itself", r["excess"])
+            # per element: |a-b| <= 1e-4|b| + c max|b| with c = 5e-6, or four times what the reference needs against ITSELF on
+            # this input if that is more (excess is measured against c = 1e-6; dL_dmeans3D carries the covariance branch
+            # and reaches 4e-6 reference-vs-reference on single views of C1)
+            assert o["excess"] <= max(excess_c, excess_factor * r["excess"]), (tag, n, "per-element excess", o["excess"], "reference vs itself", r["excess"])
             if "ours_vs_double" in row:
                 assert row["ours_vs_double"]["rel"] <= 2e-5, (tag, n, row["ours_vs_double"]["rel"])
         assert o["rel"] <= bound, (tag, n, o["rel"], bound)

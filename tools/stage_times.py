@@ -6,7 +6,7 @@ import _harness as h
 sm = h.scene_mod
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
 scene = sm.make_config_scene(cfg)
-d = h.torch_inputs(scene, sm.random_view(21))
+d = h.torch_inputs(scene, sm.random_view(21) if cfg in ("C1", "C2", "C3") else sm.identity_view())
 dL = torch.from_numpy(sm.make_grad_image(scene.W, scene.H, 99)).cuda()
 lib = h.pkg.load_library()
 names = ["preprocess_fwd", "depth_order", "tile_ranges", "emit", "tile_sort", "render_fwd", "render_bwd", "preprocess_bwd"]
