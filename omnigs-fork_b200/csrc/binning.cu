@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(1024) tile_ranges_kernel(
 	__syncthreads();
 	// the sort passes want digit STARTS (exclusive prefix of the counts): one warp per pass scans its kMaxBins counts
 	// here once instead of every one of the passes' thousands of CTAs doing it
-	if (warp < kMaxTilePasses) {
+	if (warp < plan.passes) {   // (rows kColStartsRow / kRowStartsRow belong to the column-segment path: passes <= 3 there)
 		constexpr int kPerLane = kMaxBins / 32;
 		uint32_t* hp = s_hist + warp * kMaxBins;
 		uint32_t v[kPerLane], sum = 0;

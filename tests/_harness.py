@@ -290,7 +290,12 @@ def assert_gradient_parity(rep, tag="", floor=1e-4, excess_c=4e-6, excess_factor
             # backward.cu:270-283, and joins the ill-conditioned tensors)
             if "ref_vs_double" in row:
                 bound = max(bound, 2.0 * row["ref_vs_double"]["rel"])
-                assert row["ours_vs_double"]["rel"] <= floor, (tag, n, "ours vs double", row["ours_vs_double"]["rel"])
+                # lonlat: ours within 1e-4 of the double evaluation.  Perspective camera (f-4): the clamped-frustum Jacobian puts
+                # 1/z^2, 1/z^3 next to the near plane into every chain output, where float itself is the limit — there the bar
+                # is "no farther from the double evaluation than the reference is from its own"
+                truth_bar = max(floor, row["ref_vs_double"]["rel"]) if tag.startswith("pin") else floor
+                assert row["ours_vs_double"]["rel"] <= truth_bar, (tag, n, "ours vs double", row["ours_vs_double"]["rel"],
+                                                                    "reference vs double", row["ref_vs_double"]["rel"])
         else:
             # per element: |a-b| <= 1e-4|b| + c max|b| with c = 5e-6, or four times what the reference needs against ITSELF on
             # this input if that is more (excess is measured against c = 1e-6; dL_dmeans3D carries the covariance branch
