@@ -723,9 +723,10 @@ def main():
                               "stage_ms": stage_ms, "frame_ms": frame_ms}
     if world == 1:
         line["train_step"] = training_iteration_bench(h, scene, views, dev, K, Wm, None)
-    # fwd: preprocess, hist, 4 + 2 onesweep (the first tile pass emits), scan, ranges, render = 11; bwd: 2; data parallel adds
-    # the colour kernel, the all-reduce (sum + max sections) and the dL_dsh rebuild
-    line["gpu_launches"] = K * (11 + 2 + (4 if (distributed and bucket.factored) else (2 if distributed else 0)))
+    # fwd: preprocess, histogram, 4 depth passes, tile ranges, width scan, column starts, x pass over segments, height scan,
+    # y pass over instances, render = 13; bwd: 2; data parallel adds the colour kernel, the all-reduce (sum + max sections)
+    # and the dL_dsh rebuild
+    line["gpu_launches"] = K * (13 + 2 + (4 if (distributed and bucket.factored) else (2 if distributed else 0)))
     line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port_baseline(scene, views[Wm], dL_np)
