@@ -167,7 +167,7 @@ def reference_training_iteration(rasterize, ref, leaves, adam, stats, viewmatrix
 
 
 # ------------------------------------------------------------------ gradient parity with a double-precision arbiter
-ILL_CONDITIONED = ("dL_dcov3D", "dL_dscales", "dL_drotations")
+ILL_CONDITIONED = ("dL_dmeans3D", "dL_dcov3D", "dL_dscales", "dL_drotations")
 CHAIN_OUTPUTS = ("dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations")
 
 
@@ -207,7 +207,7 @@ def config_parity_report(name, verbose=False):
     return parity_report(scene, view, verbose=verbose)
 
 
-def parity_report(scene, view, mode="sh", bg=(0.0, 0.0, 0.0), degree=3, verbose=False, dL_seed=99):
+def parity_report(scene, view, mode="sh", bg=(0.0, 0.0, 0.0), degree=3, verbose=False, dL_seed=99, noise_runs=3):
     """Parity of one scene / view against the live reference (oracle/_ref), with two yardsticks beside the raw gradient
     difference: the reference's own run-to-run noise (second backward on the same forward state: unordered float
     atomics) and, for the per-Gaussian chain, the distance of EACH implementation from a double evaluation of the chain
@@ -243,7 +243,13 @@ def parity_report(scene, view, mode="sh", bg=(0.0, 0.0, 0.0), degree=3, verbose=
     gr = ref.backward_with_conic(d["background"], d["means3D"], fr[2], d["colors"], d["scales"], d["rotations"], 1.0,
                                  d["cov3D_precomp"], d["viewmatrix"], d["projmatrix"], float(d["tan_fovx"]), float(d["tan_fovy"]),
                                  dL, d["sh"], degree, d["campos"], fr[3], fr[0], fr[4], fr[5], d["camera_type"])
-    gr2 = run_backward(ref, d, fr, dL)
+    # the reference's own run-to-run noise: the worst of `noise_runs` further backward runs against the first
+    ref_noise = None
+    for _ in range(noise_runs):
+        gr2 = run_backward(ref, d, fr, dL)
+        st = {n: grad_stats(b, a) for n, a, b in zip(GRAD_NAMES, gr, gr2)}
+        ref_noise = st if ref_noise is None else {n: {k: max(st[n][k], ref_noise[n][k]) for k in st[n]} for n in st}
+        del gr2
     torch.cuda.synchronize()
     T = ((scene.W + 15) // 16) * ((scene.H + 15) // 16)
     rgeom = ref.unpack_geom(fr[3], P)
@@ -263,8 +269,12 @@ def parity_report(scene, view, mode="sh", bg=(0.0, 0.0, 0.0), degree=3, verbose=
                         use_sh, use_scales)
     t_ours = chain_truth(scene, view, cpu(ours["radii"]), ours["clamped"], ours["cov3D"], cpu(go[0]), ours["conic"], cpu(go[1]),
                          degree, pin, use_sh, use_scales)
+    # the intermediate the chain consumes beside dL_dmeans2D / dL_dcolors: with it bounded like the other blend-level sums,
+    # "blend outputs within tolerance" + "chain within tolerance of its double evaluation" covers the whole backward
+    report["tensors"]["dL_dconic"] = {"ours_vs_ref": grad_stats(torch.from_numpy(ours["conic"]), gr[8]),
+                                      "ref_vs_ref": dict(rel=0.0, excess=0.0, frac_over=0.0, scale=0.0)}
     for i, n in enumerate(GRAD_NAMES):
-        row = {"ours_vs_ref": grad_stats(go[i], gr[i]), "ref_vs_ref": grad_stats(gr2[i], gr[i]), "ours_vs_ours": own_noise[n]}
+        row = {"ours_vs_ref": grad_stats(go[i], gr[i]), "ref_vs_ref": ref_noise[n], "ours_vs_ours": own_noise[n]}
         if n in CHAIN_OUTPUTS and gr[i].numel():
             row["ref_vs_double"] = grad_stats(gr[i], torch.from_numpy(t_ref[n].reshape(tuple(gr[i].shape))))
             row["ours_vs_double"] = grad_stats(go[i], torch.from_numpy(t_ours[n].reshape(tuple(go[i].shape))))
@@ -278,29 +288,33 @@ def parity_report(scene, view, mode="sh", bg=(0.0, 0.0, 0.0), degree=3, verbose=
     return report
 
 
-def assert_gradient_parity(rep, tag="", floor=1e-4, excess_c=4e-6, excess_factor=4.0):
-    """The gradient bars of tests/test_parity_gpu.py on a parity_report (see that module's docstring)."""
+BLEND_LEVEL = ("dL_dmeans2D", "dL_dconic", "dL_dcolors", "dL_dopacity", "dL_dsh")
+
+
+def assert_gradient_parity(rep, tag="", floor=1e-4, excess_c=4e-6):
+    """The gradient bars of tests/test_parity_gpu.py on a parity_report (see that module's docstring; calibrated on
+    profiles/r02_parity_spread.json and profiles/r02_grad_noise.json)."""
+    pin = tag.startswith("pin")
     for n, row in rep["tensors"].items():
         o, r = row["ours_vs_ref"], row["ref_vs_ref"]
         if o["scale"] < 1e-9:
             continue
-        bound = max(floor, 2.0 * r["rel"])
-        if n in ILL_CONDITIONED or (tag.startswith("pin") and n == "dL_dmeans3D"):
-            # (perspective camera: dL/dmean carries 1/z^2, 1/z^3 factors for Gaussians just behind the near plane,
-            # backward.cu:270-283, and joins the ill-conditioned tensors)
-            if "ref_vs_double" in row:
-                bound = max(bound, 2.0 * row["ref_vs_double"]["rel"])
-                # lonlat: ours within 1e-4 of the double evaluation.  Perspective camera (f-4): the clamped-frustum Jacobian puts
-                # 1/z^2, 1/z^3 next to the near plane into every chain output, where float itself is the limit — there the bar
-                # is "no farther from the double evaluation than the reference is from its own"
-                truth_bar = max(floor, row["ref_vs_double"]["rel"]) if tag.startswith("pin") else floor
-                assert row["ours_vs_double"]["rel"] <= truth_bar, (tag, n, "ours vs double", row["ours_vs_double"]["rel"],
-                                                                    "reference vs double", row["ref_vs_double"]["rel"])
-        else:
-            # per element: |a-b| <= 1e-4|b| + c max|b| with c = 5e-6, or four times what the reference needs against ITSELF on
-            # this input if that is more (excess is measured against c = 1e-6; dL_dmeans3D carries the covariance branch
-            # and reaches 4e-6 reference-vs-reference on single views of C1)
-            assert o["excess"] <= max(excess_c, excess_factor * r["excess"]), (tag, n, "per-element excess", o["excess"], "reference vs itself", r["excess"])
+        if n in BLEND_LEVEL:
+            # sums of per-pixel terms and the (linear) SH rows: the stated tolerance as it stands, in the max norm AND
+            # per element (|a-b| <= 1e-4|b| + 5e-6 max|b|; `excess` is measured against 1e-6 max|b|)
+            assert o["rel"] <= floor, (tag, n, o["rel"])
+            assert o["excess"] <= excess_c, (tag, n, "per-element excess", o["excess"], "reference vs itself", r["excess"])
             if "ours_vs_double" in row:
                 assert row["ours_vs_double"]["rel"] <= 2e-5, (tag, n, row["ours_vs_double"]["rel"])
+            continue
+        # outputs of the per-Gaussian chain through cov2D (division by det^2, differences of nearly equal entries; the
+        # perspective camera adds 1/z^2, 1/z^3 next to the near plane): the reference differs from ITSELF by more than
+        # 1e-4 on them.  (i) ours is within 1e-4 of the double evaluation of the chain, or at least no farther from it
+        # than the reference is from its own; (ii) triangle inequality: ours-vs-reference <= ours-vs-double +
+        # reference-vs-double + the blend-level noise of both sides carried through the chain (F x the reference's own
+        # run-to-run difference, worst of `noise_runs` re-runs; F = 2, 4 for the perspective camera, whose noise is heavy-tailed)
+        od, rd = row["ours_vs_double"]["rel"], row["ref_vs_double"]["rel"]
+        truth_bar = max(floor, rd) if pin else floor
+        assert od <= truth_bar, (tag, n, "ours vs double", od, "reference vs double", rd)
+        bound = max(floor, od + rd + (4.0 if pin else 2.0) * r["rel"])
         assert o["rel"] <= bound, (tag, n, o["rel"], bound)
