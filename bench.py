@@ -287,10 +287,16 @@ def bands_block(h, par, dev, rank, world, distributed, steps=6, warmup=2, config
     loads = [sum(rows[a:b]) for a, b in bands]
     ex = par.BandExchange(P, scene.W, scene.H, dev) if distributed else None
 
+    # OGS_BAND_GATHER=full all-gathers whole bands (every rank ends with the whole frame); the default exchanges the 5-row
+    # halos a band-wise L1 + SSIM loss needs (11-tap window).  OGS_BAND_CHUNKS: ranges of the pipelined accumulator exchange.
+    halo = None if os.environ.get("OGS_BAND_GATHER", "halo") == "full" else 5
+    chunks = int(os.environ.get("OGS_BAND_CHUNKS", "4"))
+
     def step():
-        img, fwd = par.render_band_forward(rasterize, band, scene.H, exchange=ex)
+        img, fwd = par.render_band_forward(rasterize, band, scene.H, exchange=ex, halo=halo)
         if ex is not None:
-            h.run_backward(h.pkg, d, fwd, dL, accumulators=ex.acc, reduce_accumulators=lambda t: ex.reduce_accumulators())
+            h.run_backward(h.pkg, d, fwd, dL, accumulators=ex.acc, reduce_accumulators=ex.reduce_accumulators,
+                           accumulator_chunks=chunks)
         else:
             h.run_backward(h.pkg, d, fwd, dL)
         return fwd[0]
@@ -314,8 +320,9 @@ def bands_block(h, par, dev, rank, world, distributed, steps=6, warmup=2, config
            "higher_is_better": False, "scaling": "strong", "steps": steps, "warmup": warmup,
            "config": {"workload": config, "gaussians": P, "image": [scene.W, scene.H], "num_rendered": R_full, "bands": bands,
                       "band_instances": loads, "max_over_mean_band_load": max(loads) / (sum(loads) / world),
-                      "exchange": (("all-gather of band rows (peer stores) + all-reduce of the [P,12] accumulators (peer / multimem kernel)"
-                                    if ex.peer else "NCCL all_gather of band rows + all_reduce of the [P,12] accumulators")
+                      "exchange": ((("5-row halos of the band" if halo else "all-gather of band rows") + " (peer stores) + all-reduce of the "
+                                     f"[P,12] accumulators in {chunks} ranges pipelined with the per-Gaussian backward (peer / multimem kernel)"
+                                     if ex.peer else "NCCL all_gather of band rows / halos + all_reduce of the [P,12] accumulators")
                                    if distributed else "none")}}
     del ex, d, dL
     torch.cuda.empty_cache()

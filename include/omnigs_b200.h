@@ -180,6 +180,16 @@ OGS_API int ogs_lonlat_backward_finish_from(
 	const float* grad_acc,
 	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
 	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream);
+/* ..._finish_from over Gaussians [first, first + count) only (first a multiple of 128; count 0 = up to P): lets the band
+ * ranks pipeline the accumulator exchange — chunk k+1 is being summed over NVLink while chunk k is differentiated.
+ * All pointers are the full arrays' bases. */
+OGS_API int ogs_lonlat_backward_finish_range(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* campos, const int* radii, char* geom_buffer,
+	const float* grad_acc, int first, int count,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream);
 
 /*
  * One view of a multi-view / data-parallel training step (the reference trains one view per step

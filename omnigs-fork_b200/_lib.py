@@ -64,6 +64,7 @@ SYMBOLS = {
     "ogs_lonlat_forward_colors": (_c_int, [_c_int] * 3 + [_p] * 5 + [_p]),
     "ogs_lonlat_backward_render_into": (_c_int, [_c_int, _c_i64, _c_int, _c_int] + [_p] * 6 + [_p]),
     "ogs_lonlat_backward_finish_from": (_c_int, [_c_int] * 5 + [_p] * 3 + [_c_f] + [_p] * 6 + [_p] + [_p] * 9 + [_p]),
+    "ogs_lonlat_backward_finish_range": (_c_int, [_c_int] * 5 + [_p] * 3 + [_c_f] + [_p] * 6 + [_p, _c_int, _c_int] + [_p] * 9 + [_p]),
     "ogs_lonlat_backward_view": (_c_int, [_c_int] * 3 + [_c_i64, _c_int, _c_int] + [_p] * 4 + [_c_f] + [_p] * 4 + [_p] * 4
                                  + [_c_int] + [_p] * 9 + [_p]),
     "ogs_sh_gradient_from_views": (_c_int, [_c_int] * 4 + [_p] * 6 + [_p]),

@@ -554,6 +554,7 @@ OGS_API int ogs_lonlat_backward_render_into(
 // Backward, part 2: the fused per-Gaussian backward from the (possibly all-reduced) accumulators.
 struct FinishExtras {            // multi-view / data-parallel mode and external accumulators (all optional)
 	const float* grad_acc = nullptr;
+	int first = 0, count = 0;    // Gaussian sub-range (count 0 = to the end)
 	int accumulate = 0;
 	float* dL_drgb_view = nullptr;
 	float* stat_grad_norm = nullptr;
@@ -586,6 +587,9 @@ static int backward_finish_impl(
 	a.cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
 	a.viewmatrix = viewmatrix; a.campos = campos; a.radii = radii; a.clamped = g.clamped;
 	a.grad_acc = x.grad_acc ? x.grad_acc : g.grad_acc;
+	if (x.first < 0 || x.count < 0 || (x.first % 128) != 0) return fail(OGS_ERR_INVALID_ARG, "Gaussian range: first must be a non-negative multiple of 128");
+	a.first_block = x.first / 128;
+	a.num_blocks = x.count > 0 ? (x.count + 127) / 128 : 0;
 	a.g0 = g.g0; a.g1 = g.g1;
 	a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dopacity = dL_dopacity; a.dL_dcolor = dL_dcolor;
 	a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = shs ? dL_dsh : nullptr;
@@ -623,6 +627,22 @@ OGS_API int ogs_lonlat_backward_finish_from(
 	if (P > 0 && (!dL_dmean2D || !dL_dcolor || !dL_dcov3D || !grad_acc)) return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
 	FinishExtras x;
 	x.grad_acc = grad_acc;
+	return backward_finish_impl(P, D, M, W, H, means3D, shs, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
+	                            campos, radii, geom_buffer, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D,
+	                            dL_dcov3D, dL_dsh, dL_dscale, dL_drot, x, (cudaStream_t)stream);
+}
+
+OGS_API int ogs_lonlat_backward_finish_range(
+	int P, int D, int M, int W, int H,
+	const float* means3D, const float* shs, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* campos, const int* radii, char* geom_buffer,
+	const float* grad_acc, int first, int count,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream)
+{
+	if (P > 0 && (!dL_dmean2D || !dL_dcolor || !dL_dcov3D || !grad_acc)) return fail(OGS_ERR_INVALID_ARG, "a required pointer is NULL");
+	FinishExtras x;
+	x.grad_acc = grad_acc; x.first = first; x.count = count;
 	return backward_finish_impl(P, D, M, W, H, means3D, shs, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix,
 	                            campos, radii, geom_buffer, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D,
 	                            dL_dcov3D, dL_dsh, dL_dscale, dL_drot, x, (cudaStream_t)stream);

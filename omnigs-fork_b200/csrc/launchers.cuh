@@ -55,6 +55,7 @@ struct PreprocessBwdArgs {
 	const int* radii;
 	const uint8_t* clamped;
 	const float* grad_acc;   // [P,12] raw render-backward sums
+	int first_block, num_blocks;   // sub-range of the 128-Gaussian blocks to process (num_blocks 0 = all from first_block)
 	const float4* g0;        // conic.xy in .zw
 	const float4* g1;        // conic.z in .x, activated opacity in .y
 	// raw-parameter mode (raw != 0): scales / rotations are the stored tensors, the SH row is split, and the

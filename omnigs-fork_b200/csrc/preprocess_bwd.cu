@@ -53,11 +53,13 @@ __global__ void __launch_bounds__(kPreBwdThreads, OGS_PREBWD_MINBLOCKS) preproce
 	__shared__ __align__(8) uint64_t s_bar;
 	__shared__ __align__(8) uint64_t s_rows_done;   // raw mode: counts the CTA's gradient rows written to shared memory
 	const int tid = threadIdx.x;
-	const int idx = blockIdx.x * kPreBwdThreads + tid;
+	// a.first_block > 0: a launch over a sub-range of the Gaussians (chunks of a pipelined accumulator exchange)
+	const int blk = (int)blockIdx.x + a.first_block;
+	const int idx = blk * kPreBwdThreads + tid;
 	if (tid < 16) sV[tid] = a.viewmatrix[tid];
 	if (tid < 3) sCam[tid] = a.campos[tid];
 	if (kPinhole && tid < 16) sP[tid] = a.projmatrix[tid];
-	const int rows = min(kPreBwdThreads, a.P - (int)blockIdx.x * kPreBwdThreads);
+	const int rows = min(kPreBwdThreads, a.P - blk * kPreBwdThreads);
 	const int rows4 = rows & ~3;   // raw mode: rows covered by the per-CTA bulk copies (sizes stay multiples of 16 B)
 	if (kBulkSH && tid == 0) {
 		mbar_init(&s_bar, 1);
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(kPreBwdThreads, OGS_PREBWD_MINBLOCKS) preproce
 			mbar_init(&s_rows_done, (uint32_t)rows);
 			mbar_arrive_expect_tx(&s_bar, (uint32_t)rows4 * kShRowFloats * 4u);
 			if (rows4) {
-				const size_t first = (size_t)blockIdx.x * kPreBwdThreads;
+				const size_t first = (size_t)blk * kPreBwdThreads;
 				bulk_load(&s_sh[0], a.features_rest + first * kRawRestFloats, (uint32_t)rows4 * kRawRestFloats * 4u, &s_bar);
 				bulk_load(&s_sh[kRawDcOffset], a.features_dc + first * 3, (uint32_t)rows4 * 12u, &s_bar);
 			}
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(kPreBwdThreads, OGS_PREBWD_MINBLOCKS) preproce
 			mbar_arrive(&s_rows_done);
 			if (tid == 0 && rows4) {
 				mbar_wait(&s_rows_done, 0);
-				const size_t first = (size_t)blockIdx.x * kPreBwdThreads;
+				const size_t first = (size_t)blk * kPreBwdThreads;
 				bulk_store(a.dL_dfeatures_rest + first * kRawRestFloats, &s_sh[0], (uint32_t)rows4 * kRawRestFloats * 4u);
 				bulk_store(a.dL_dfeatures_dc + first * 3, &s_sh[kRawDcOffset], (uint32_t)rows4 * 12u);
 				bulk_commit();
@@ -420,7 +422,10 @@ int launch_sh_gradient_from_views(const ShFromViewsArgs& a, cudaStream_t st)
 
 int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st)
 {
-	const int blocks = ceil_div(a.P, kPreBwdThreads);
+	const int all_blocks = ceil_div(a.P, kPreBwdThreads);
+	if (a.first_block < 0 || a.first_block > all_blocks || a.num_blocks < 0) return fail(OGS_ERR_INVALID_ARG, "bad Gaussian block range");
+	const int blocks = a.num_blocks > 0 ? min(a.num_blocks, all_blocks - a.first_block) : all_blocks - a.first_block;
+	if (blocks <= 0) return OGS_OK;
 	if (a.pinhole) {
 		if (a.shs != nullptr && a.dL_dsh != nullptr && sh_rows_bulk_capable(a.shs, a.M) && sh_rows_bulk_capable(a.dL_dsh, a.M))
 			preprocess_lonlat_bwd_kernel<1, true><<<blocks, kPreBwdThreads, 0, st>>>(a);

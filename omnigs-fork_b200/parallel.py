@@ -227,6 +227,16 @@ def sh_gradient_from_views(means3D, campos_views, factors, degree, out):
     return out
 
 
+_trace = None   # tools/dp_trace.py sets this to a list: exchange_bucket appends (label, CUDA event) pairs of its phases
+
+
+def _mark(label, stream):
+    if _trace is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        _trace.append((label, ev))
+
+
 def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=3, sh_stream=None):
     """Sum the bucket's summed section and max-reduce its radii over ranks, in place: one kernel over NVLink peer
     memory / the multicast address when the bucket lives in symmetric memory (csrc/peer_collective.cu), NCCL / gloo
@@ -249,11 +259,9 @@ def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=
         import ctypes
         from ._lib import load_library, check
         stream = ctypes.c_void_p(cur.cuda_stream)
+        _mark("backward_done", cur)
         pr["handle"].barrier(channel=0)      # every rank's bucket (and factors) of this step are written
-        fork = None
-        if bucket.factored and sh_stream is not None:
-            fork = torch.cuda.Event()
-            fork.record(cur)
+        _mark("barrier0", cur)
         if pr.get("multicast") and pr.get("use_multimem", pr["world"] > 4):
             # NVSwitch in-switch reduction: one inbound copy per element instead of world - 1.  Measured on a 244 MB
             # bucket: peer loads/stores win up to four ranks, the multicast path beyond (profiles/r01_peer_allreduce_*.log)
@@ -261,6 +269,14 @@ def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=
         else:
             arr = (ctypes.c_void_p * pr["world"])(*pr["ptrs"])
             check(load_library().ogs_peer_allreduce(arr, pr["world"], pr["rank"], cs, cm, stream))
+        _mark("allreduce", cur)
+        fork = None
+        if bucket.factored and sh_stream is not None:
+            # the dL_dsh rebuild starts BEHIND the all-reduce: run side by side the two share NVLink and the all-reduce — the
+            # one the optimiser waits for — takes 0.36 ms instead of 0.15 (profiles/r02_dp_trace_n8.log); behind it the
+            # rebuild overlaps the next step's geometry / depth order / tile sort instead
+            fork = torch.cuda.Event()
+            fork.record(cur)
         if bucket.factored:
             off = bucket.offsets["dL_drgb"] * 4
             step = bucket.P * 3 * 4
@@ -271,11 +287,15 @@ def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=
                 return None
             sh_stream.wait_event(fork)
             with torch.cuda.stream(sh_stream):
+                _mark("sh_fork", sh_stream)
                 sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
+                _mark("sh_rebuild", sh_stream)
                 pr["handle"].barrier(channel=2)   # every rank has read this rank's factors
+                _mark("sh_barrier2", sh_stream)
                 done = torch.cuda.Event()
                 done.record(sh_stream)
             pr["handle"].barrier(channel=1)       # all sums stored
+            _mark("barrier1", cur)
             return done
         pr["handle"].barrier(channel=1)
         return None
@@ -346,12 +366,16 @@ class BandExchange:
         self.image = self.flat[n_acc:].view(3, self.H, self.W)
         self._img_off = n_acc * 4
 
-    def gather_image(self, band_image, band):
+    def gather_image(self, band_image, band, halo=None):
         """band_image: this rank's render [3,H,W] (valid in its rows); band = (ty0, ty1) tile rows.  Returns the full
-        frame (every rank's rows in place)."""
+        frame (every rank's rows in place).  halo = h: a band-wise loss needs only the h pixel rows either side of the
+        band (5 for the 11-tap SSIM window, loss_utils.h:73-131) — every rank then publishes just the first and last h
+        rows of its band and band_image is returned with its neighbours' rows [y0 - h, y0) and [y1, y1 + h) filled in."""
         y0, y1 = min(self.H, band[0] * 16), min(self.H, band[1] * 16)
         if not self.distributed:
             return band_image
+        if halo is not None:
+            return self._exchange_halo(band_image, y0, y1, int(halo))
         if self.peer is not None:
             import ctypes
             from ._lib import load_library, check
@@ -374,9 +398,45 @@ class BandExchange:
             self.image[:, a:b] = part[:, :b - a]
         return self.image
 
-    def reduce_accumulators(self, acc=None):
+    def _exchange_halo(self, band_image, y0, y1, h):
+        top = (y0, min(y0 + h, y1))                # my first rows: the halo of the band above
+        bottom = (max(y1 - h, top[1]), y1)         # my last rows (not overlapping `top` on bands shorter than 2h)
+        if self.peer is not None:
+            import ctypes
+            from ._lib import load_library, check
+            pr = self.peer
+            imgs = (ctypes.c_void_p * pr["world"])(*[p + self._img_off for p in pr["ptrs"]])
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+            for a, b in (top, bottom):
+                if b > a:
+                    check(load_library().ogs_band_rows_allgather(imgs, pr["world"], pr["rank"], ctypes.c_void_p(band_image.data_ptr()),
+                                                                 self.W, self.H, a, b, stream))
+            pr["handle"].barrier(channel=3)
+        else:
+            world = dist.get_world_size(self.group)
+            mine = band_image.new_zeros((3, 2 * h, self.W))
+            mine[:, :top[1] - top[0]] = band_image[:, top[0]:top[1]]
+            mine[:, h:h + bottom[1] - bottom[0]] = band_image[:, bottom[0]:bottom[1]]
+            spans = [None] * world
+            dist.all_gather_object(spans, (top, bottom), group=self.group)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=self.group)
+            for (t, b), part in zip(spans, parts):
+                self.image[:, t[0]:t[1]] = part[:, :t[1] - t[0]]
+                self.image[:, b[0]:b[1]] = part[:, h:h + b[1] - b[0]]
+        lo, hi = max(0, y0 - h), min(self.H, y1 + h)
+        band_image[:, lo:y0] = self.image[:, lo:y0]
+        band_image[:, y1:hi] = self.image[:, y1:hi]
+        return band_image
+
+    def reduce_accumulators(self, acc=None, ranges=None):
         """Sum self.acc over the ranks, in place (call between the two backward kernels:
-        RasterizeGaussiansBackwardCUDA(..., accumulators=ex.acc, reduce_accumulators=ex.reduce_accumulators))."""
+        RasterizeGaussiansBackwardCUDA(..., accumulators=ex.acc, reduce_accumulators=ex.reduce_accumulators)).
+        With `ranges` ([(first Gaussian, count)], accumulator_chunks > 1 of that call) the ranges are summed one after the
+        other on a stream of their own and one event per range is returned: the caller differentiates range k while
+        range k+1 crosses NVLink."""
+        if ranges is not None:
+            return self._reduce_ranges(ranges)
         if not self.distributed:
             return
         if self.peer is not None:
@@ -396,7 +456,46 @@ class BandExchange:
             dist.all_reduce(self.acc, op=dist.ReduceOp.SUM, group=self.group)
 
 
-def render_band_forward(rasterize, band, H, group=None, exchange=None):
+    def _reduce_ranges(self, ranges):
+        if not self.distributed:
+            return [None] * len(ranges)
+        if self.peer is None:
+            # NCCL / gloo: asynchronous all-reduces of the row slices; the "event" is the work handle's completion
+            events = []
+            for first, count in ranges:
+                dist.all_reduce(self.acc[first:first + count], op=dist.ReduceOp.SUM, group=self.group)
+                events.append(None)
+            return events
+        import ctypes
+        from ._lib import load_library, check
+        pr = self.peer
+        cur = torch.cuda.current_stream(self.flat.device)
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream(self.flat.device)
+        pr["handle"].barrier(channel=0)                      # every rank's render backward has written its partial sums
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self._comm.wait_event(ready)
+        events = []
+        multimem = pr.get("multicast") and pr.get("use_multimem", pr["world"] > 4)
+        with torch.cuda.stream(self._comm):
+            stream = ctypes.c_void_p(self._comm.cuda_stream)
+            for first, count in ranges:
+                off, n = first * 48, -(-12 * count // 4) * 4
+                if multimem:
+                    check(load_library().ogs_multimem_allreduce(ctypes.c_void_p(pr["multicast"] + off), pr["world"], pr["rank"], n, 0, stream))
+                else:
+                    arr = (ctypes.c_void_p * pr["world"])(*[p + off for p in pr["ptrs"]])
+                    check(load_library().ogs_peer_allreduce(arr, pr["world"], pr["rank"], n, 0, stream))
+                # a range's sums are complete on THIS rank once every rank has stored its slice of it
+                pr["handle"].barrier(channel=1)
+                ev = torch.cuda.Event()
+                ev.record(self._comm)
+                events.append(ev)
+        return events
+
+
+def render_band_forward(rasterize, band, H, group=None, exchange=None, halo=None):
     """Latitude-band forward for this rank.  `rasterize(band)` must call RasterizeGaussiansCUDA(...,
     band=band) and return its 6-tuple.  With a BandExchange the ranks all-gather their pixel rows (each pixel crosses
     NVLink once per peer); without one, rows outside the band are zeroed and the per-rank images are summed
@@ -405,7 +504,7 @@ def render_band_forward(rasterize, band, H, group=None, exchange=None):
     fwd = rasterize(band)
     img = fwd[1]
     if exchange is not None:
-        return exchange.gather_image(img, band), fwd
+        return exchange.gather_image(img, band, halo=halo), fwd
     y0, y1 = min(H, band[0] * 16), min(H, band[1] * 16)
     full = torch.zeros_like(img)
     full[:, y0:y1] = img[:, y0:y1]

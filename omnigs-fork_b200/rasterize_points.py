@@ -131,7 +131,7 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                                    cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                    dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
                                    imageBuffer, camera_type=PINHOLE, reduce_accumulators=None, out=None,
-                                   accumulators=None, conic_out=None):
+                                   accumulators=None, conic_out=None, accumulator_chunks=0):
     """reference src/rasterize_points.cu:166-285.
 
     Returns (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P,1], dL_dmeans3D[P,3], dL_dcov3D[P,6],
@@ -145,6 +145,11 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
     ``accumulators`` (with ``reduce_accumulators``): a caller-owned [P,12] float32 tensor to use instead of the
     geometry buffer's (e.g. ``parallel.BandExchange`` keeps it in symmetric memory and sums it with the library's own
     NVLink kernel).
+
+    ``accumulator_chunks`` (with ``accumulators``): n > 1 pipelines exchange and differentiation — ``reduce_accumulators``
+    is then called as ``reduce_accumulators(accumulators, ranges)`` with n Gaussian ranges [(first, count)] (multiples of
+    128) and returns one CUDA event (or None) per range; the per-Gaussian backward of a range is queued behind its event
+    (ogs_lonlat_backward_finish_range), so range k+1 is summed over NVLink while range k is differentiated.
 
     ``conic_out`` (tests): a [P,4] float32 tensor that receives the reference's intermediate dL_dconic (.x, .y, .w used).
 
@@ -202,11 +207,23 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                 check(lib.ogs_lonlat_backward_render_into(
                     P, int(R), W, H, _ptr(background), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
                     _ptr(dL), _ptr(accumulators), _stream(device)))
-                reduce_accumulators(accumulators)
-                check(lib.ogs_lonlat_backward_finish_from(
-                    P, int(degree), M, W, H, _ptr(means3D_c), _ptr(sh), _ptr(scales), float(scale_modifier),
-                    _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(campos), _ptr(radii_c),
-                    _ptr(geomBuffer), _ptr(accumulators), *outs, _stream(device)))
+                if accumulator_chunks and accumulator_chunks > 1:
+                    ranges = gaussian_ranges(P, int(accumulator_chunks))
+                    events = reduce_accumulators(accumulators, ranges)
+                    cur = torch.cuda.current_stream(device)
+                    for (first, count), ev in zip(ranges, events):
+                        if ev is not None:
+                            cur.wait_event(ev)
+                        check(lib.ogs_lonlat_backward_finish_range(
+                            P, int(degree), M, W, H, _ptr(means3D_c), _ptr(sh), _ptr(scales), float(scale_modifier),
+                            _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(campos), _ptr(radii_c),
+                            _ptr(geomBuffer), _ptr(accumulators), first, count, *outs, _stream(device)))
+                else:
+                    reduce_accumulators(accumulators)
+                    check(lib.ogs_lonlat_backward_finish_from(
+                        P, int(degree), M, W, H, _ptr(means3D_c), _ptr(sh), _ptr(scales), float(scale_modifier),
+                        _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(campos), _ptr(radii_c),
+                        _ptr(geomBuffer), _ptr(accumulators), *outs, _stream(device)))
             else:
                 check(lib.ogs_lonlat_backward_render(
                     P, int(R), W, H, _ptr(background), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
@@ -220,6 +237,21 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
             if M == 0:
                 dL_dsh = torch.zeros((P, 0, 3), **opts)
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def gaussian_ranges(P, n):
+    """Split [0, P) into at most n contiguous ranges whose starts are multiples of 128 (the per-Gaussian kernels' CTA size):
+    [(first, count)], the last one runs to P."""
+    blocks = -(-int(P) // 128)
+    n = max(1, min(int(n), blocks))
+    per = -(-blocks // n)
+    out = []
+    for k in range(n):
+        first = k * per * 128
+        if first >= P:
+            break
+        out.append((first, min(per * 128, P - first)))
+    return out
 
 
 def RasterizeGaussiansBackwardView(background, means3D, radii, scales, rotations, scale_modifier, viewmatrix,

@@ -11,6 +11,7 @@ import torch.multiprocessing as mp
 import _harness as h  # noqa: F401  (registers the package)
 
 par = importlib.import_module("omnigs-fork_b200.parallel")
+rp = importlib.import_module("omnigs-fork_b200.rasterize_points")
 NAMES = h.GRAD_NAMES
 
 
@@ -265,7 +266,18 @@ def _band_worker(rank, world, port, out):
     full, _ = par.render_band_forward(lambda b: (0, mine, None, None, None, None), bands[rank], H, exchange=ex)
     ex.acc.copy_(torch.randn((P, 12), generator=torch.Generator().manual_seed(50 + rank)))
     ex.reduce_accumulators()
-    torch.save({"image": full.clone(), "acc": ex.acc.clone()}, out + f".{rank}")
+    summed = ex.acc.clone()
+    # pipelined variant: the same sums range by range (ranges as RasterizeGaussiansBackwardCUDA(accumulator_chunks=3) cuts them)
+    ex.acc.copy_(torch.randn((P, 12), generator=torch.Generator().manual_seed(50 + rank)))
+    ranges = rp.gaussian_ranges(P, 3)
+    events = ex.reduce_accumulators(ex.acc, ranges)
+    assert len(events) == len(ranges)
+    # band-wise loss: only the 5-row halos cross ranks
+    halo_in = torch.full((3, H, W), float("nan"))
+    halo_in[:, y0:y1] = frame[:, y0:y1]
+    halo_img, _ = par.render_band_forward(lambda b: (0, halo_in, None, None, None, None), bands[rank], H, exchange=ex, halo=5)
+    torch.save({"image": full.clone(), "acc": summed, "acc_ranges": ex.acc.clone(), "halo": halo_img.clone(), "rows": (y0, y1),
+                "ranges": ranges}, out + f".{rank}")
     dist.barrier()
     dist.destroy_process_group()
 
@@ -279,6 +291,13 @@ def test_band_exchange_world2_gloo(tmp_path):
         got = torch.load(out + f".{r}")
         assert torch.equal(got["image"], frame)
         assert torch.allclose(got["acc"], acc, atol=1e-6)
+        assert torch.equal(got["acc_ranges"], got["acc"])
+        assert got["ranges"] == [(0, 128), (128, 128), (256, 44)]
+        y0, y1 = got["rows"]
+        lo, hi = max(0, y0 - 5), min(100, y1 + 5)
+        assert torch.equal(got["halo"][:, lo:hi], frame[:, lo:hi])            # own rows + both neighbours' halos
+        rest = torch.cat([got["halo"][:, :lo], got["halo"][:, hi:]], dim=1)
+        assert bool(torch.isnan(rest).all())                                   # nothing else was exchanged
 
 
 def test_band_rows_properties_hold_for_arbitrary_row_loads():

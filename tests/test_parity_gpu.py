@@ -534,6 +534,29 @@ def test_band_gradients_sum_to_full_frame_gradients():
     for n, a, b in zip(h.GRAD_NAMES, g_sum, g_full):
         assert_own_runs_close(n, a, b, 2e-5)
 
+    # pipelined exchange (ogs_lonlat_backward_finish_range): the per-Gaussian backward run range by range on caller-owned
+    # accumulators gives the same bits as one launch over all Gaussians
+    acc_a = torch.empty((scene.P, 12), device="cuda")
+    acc_b = torch.empty((scene.P, 12), device="cuda")
+    seen = []
+    whole = h.run_backward(h.pkg, d, full, dL, accumulators=acc_a, reduce_accumulators=lambda t: None)
+    def per_range(t, ranges):
+        seen.append(ranges)
+        return [None] * len(ranges)
+    chunked = h.run_backward(h.pkg, d, full, dL, accumulators=acc_b, reduce_accumulators=per_range, accumulator_chunks=5)
+    assert len(seen) == 1 and len(seen[0]) == 5 and sum(c for _, c in seen[0]) == scene.P
+    assert all(f % 128 == 0 for f, _ in seen[0])
+    for n, a, b in zip(h.GRAD_NAMES, chunked, whole):
+        if n in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dsh"):
+            assert_own_runs_close(n, a, b, 2e-5)       # two render backwards: atomic order differs
+    # same accumulators, whole vs ranges: bit-identical
+    lib = h.pkg.load_library()
+    again = h.run_backward(h.pkg, d, full, dL, accumulators=acc_b, reduce_accumulators=lambda t: t.copy_(acc_a))
+    ranged = h.run_backward(h.pkg, d, full, dL, accumulators=acc_b,
+                            reduce_accumulators=lambda t, r: (t.copy_(acc_a), [None] * len(r))[1], accumulator_chunks=7)
+    for n, a, b in zip(h.GRAD_NAMES, ranged, again):
+        assert torch.equal(bits(a), bits(b)), n
+
 
 def test_caller_streams_and_side_stream_ordering():
     """The library forks tile_ranges onto its own side stream and joins it back (csrc/c_api.cu): frames issued back
