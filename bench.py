@@ -201,7 +201,7 @@ def dp_views_block(h, par, dev, rank, world, distributed, steps=8, warmup=3, con
     poses = [[(torch.from_numpy(a).to(dev), torch.from_numpy(c).to(dev)) for a, c in st] for st in poses]
     bucket = par.GradientBucket(P, 16, dev, views_per_rank=vpr)
     side = torch.cuda.Stream()
-    pending = [None]
+    pending, deferred = [None], [None]
     cur = torch.cuda.current_stream()
 
     def step(s):
@@ -210,9 +210,10 @@ def dp_views_block(h, par, dev, rank, world, distributed, steps=8, warmup=3, con
         for k, v in enumerate(mine):
             vm, cp = poses[s][v]
             if k == 0:
-                # the previous step's SH gradients may still be in flight: only the colours wait for them
+                # the previous step's dL_dsh rebuild is queued once this step's per-Gaussian kernel has finished (it runs
+                # under the sorts); only the colours wait for it
                 st = h.pkg.RasterizeGaussiansGeometry(d["means3D"], d["opacity"], d["scales"], d["rotations"], 1.0,
-                                                      d["cov3D_precomp"], vm, cp, scene.H, scene.W)
+                                                      d["cov3D_precomp"], vm, cp, scene.H, scene.W, after_stage1=launch_pending)
                 if pending[0] is not None:
                     cur.wait_event(pending[0])
                 fwd = h.pkg.RasterizeGaussiansBlend(st, d["background"], d["sh"], 3)
@@ -221,12 +222,21 @@ def dp_views_block(h, par, dev, rank, world, distributed, steps=8, warmup=3, con
                 fwd = h.run_forward(h.pkg, d)
             h.pkg.RasterizeGaussiansBackwardView(d["background"], d["means3D"], fwd[2], d["scales"], d["rotations"], 1.0, vm,
                                                  dL, d["sh"], 3, cp, fwd[3], fwd[0], fwd[4], fwd[5], bucket, k)
-        if not mine and pending[0] is not None:
-            cur.wait_event(pending[0])
-        pending[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3,
-                                         sh_stream=side if distributed else None)
+        if not mine:
+            launch_pending()
+            if pending[0] is not None:
+                cur.wait_event(pending[0])
+        pending[0] = None
+        deferred[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3,
+                                          sh_stream=side if distributed else None, defer_sh=distributed)
+
+    def launch_pending():
+        if deferred[0] is not None:
+            pending[0] = deferred[0]()
+            deferred[0] = None
 
     def drain():
+        launch_pending()
         if pending[0] is not None:
             cur.wait_event(pending[0])
             pending[0] = None
@@ -316,7 +326,32 @@ def bands_block(h, par, dev, rank, world, distributed, steps=6, warmup=2, config
     if distributed:
         dist.barrier()
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    out = {"metric": "lonlat_band_parallel_ms_per_frame", "value": float(ms), "unit": "ms", "n_gpus": world,
+    # where the frame goes on rank 0: the library's per-stage events (3 frames) and the forward / backward split
+    lib = h.pkg.load_library()
+    lib.ogs_profile_enable(1)
+    acc8, buf8 = np.zeros(8), (ctypes.c_float * 8)()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    fwd_ms = bwd_ms = 0.0
+    for _ in range(3):
+        ev[0].record()
+        img, fwd = par.render_band_forward(rasterize, band, scene.H, exchange=ex, halo=halo)
+        ev[1].record()
+        if ex is not None:
+            h.run_backward(h.pkg, d, fwd, dL, accumulators=ex.acc, reduce_accumulators=ex.reduce_accumulators,
+                           accumulator_chunks=chunks)
+        else:
+            h.run_backward(h.pkg, d, fwd, dL)
+        ev[2].record()
+        lib.ogs_profile_read(buf8, 8)
+        acc8 += np.array(list(buf8))
+        torch.cuda.synchronize()
+        fwd_ms += ev[0].elapsed_time(ev[1]) / 3
+        bwd_ms += ev[1].elapsed_time(ev[2]) / 3
+    lib.ogs_profile_enable(0)
+    stage_names = ["preprocess_fwd", "depth_order", "tile_ranges", "emit", "tile_sort", "render_fwd", "render_bwd", "preprocess_bwd"]
+    rank0 = {"forward_ms": fwd_ms, "backward_ms": bwd_ms, "band_instances": int(fwd[0]),
+             "stage_ms": {n: float(v) / 3 for n, v in zip(stage_names, acc8)}}
+    out = {"metric": "lonlat_band_parallel_ms_per_frame", "value": float(ms), "unit": "ms", "n_gpus": world, "rank0": rank0,
            "higher_is_better": False, "scaling": "strong", "steps": steps, "warmup": warmup,
            "config": {"workload": config, "gaussians": P, "image": [scene.W, scene.H], "num_rendered": R_full, "bands": bands,
                       "band_instances": loads, "max_over_mean_band_load": max(loads) / (sum(loads) / world),
@@ -394,8 +429,9 @@ def main():
     # data parallel (one view per rank and step): the per-Gaussian backward writes the four geometry gradients, the
     # densification statistics and the view's dL/dRGB factor into a factored bucket; ONE kernel all-reduces the 14 floats per
     # Gaussian, and the dL_dsh rebuild (which reads the peers' 3-float factors over NVLink) runs on a side stream underneath
-    # the next step's geometry / depth order / tile sort — only the colours of the next step wait for it, as they would
-    # wait for Adam on the SH coefficients in a trainer.  OGS_DP_EXCHANGE=nccl forces the NCCL transport, =dense the
+    # the next step's depth order / tile sort (queued once that step's per-Gaussian kernel has finished: both are
+    # bandwidth bound) — only the colours of the next step wait for it, as they would wait for Adam on the SH coefficients
+    # in a trainer.  OGS_DP_EXCHANGE=nccl forces the NCCL transport, =dense the
     # round-1 exchange (244 B/Gaussian in one all-reduce, nothing overlapped).
     dp_mode = os.environ.get("OGS_DP_EXCHANGE", "peer")
     bucket = None
@@ -406,21 +442,23 @@ def main():
     campos_all = [torch.from_numpy(np.stack([sm.random_view(1000 + 97 * s + r)[1] for r in range(world)])).to(dev)
                   for s in range(K + Wm)] if distributed else None
     side = torch.cuda.Stream() if distributed else None
-    sh_pending = [None]
+    sh_pending, sh_deferred = [None], [None]
 
     def dp_step(s, dL_img, vm, cp):
         """forward + backward + exchange of one data-parallel step; dL_img: upstream gradient or a callable(image)."""
         cur = torch.cuda.current_stream()
         if bucket.factored:
             st = h.pkg.RasterizeGaussiansGeometry(d["means3D"], d["opacity"], d["scales"], d["rotations"], 1.0,
-                                                  d["cov3D_precomp"], vm, cp, H, W)
+                                                  d["cov3D_precomp"], vm, cp, H, W, after_stage1=sh_launch)
             if sh_pending[0] is not None:
                 cur.wait_event(sh_pending[0])
             fwd = h.pkg.RasterizeGaussiansBlend(st, d["background"], d["sh"], 3)
             g_img = dL_img(fwd[1]) if callable(dL_img) else dL_img
             m2d = h.pkg.RasterizeGaussiansBackwardView(d["background"], d["means3D"], fwd[2], d["scales"], d["rotations"], 1.0,
                                                        vm, g_img, d["sh"], 3, cp, fwd[3], fwd[0], fwd[4], fwd[5], bucket, 0)
-            sh_pending[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3, sh_stream=side)
+            sh_pending[0] = None
+            sh_deferred[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3,
+                                                 sh_stream=side, defer_sh=True)
             return fwd, m2d
         d["viewmatrix"], d["campos"], d["projmatrix"] = vm, cp, vm
         fwd = h.run_forward(mod, d)
@@ -429,7 +467,14 @@ def main():
         par.allreduce_bucket(bucket, g[0], fwd[2])
         return fwd, g
 
+    def sh_launch():
+        """queue the previous step's dL_dsh rebuild (called by the geometry half once its per-Gaussian kernel is done)"""
+        if sh_deferred[0] is not None:
+            sh_pending[0] = sh_deferred[0]()
+            sh_deferred[0] = None
+
     def dp_drain():
+        sh_launch()
         if sh_pending[0] is not None:
             torch.cuda.current_stream().wait_event(sh_pending[0])
             sh_pending[0] = None

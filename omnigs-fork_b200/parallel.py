@@ -237,14 +237,19 @@ def _mark(label, stream):
         _trace.append((label, ev))
 
 
-def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=3, sh_stream=None):
+def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=3, sh_stream=None, defer_sh=False):
     """Sum the bucket's summed section and max-reduce its radii over ranks, in place: one kernel over NVLink peer
     memory / the multicast address when the bucket lives in symmetric memory (csrc/peer_collective.cu), NCCL / gloo
     all-reduce otherwise.  Factored buckets then rebuild bucket["dL_dsh"] from every rank's view factors (means3D and
     campos_views [views_per_rank * world, 3], view v = slot * world + rank, are needed for the directions).  With
     `sh_stream` the rebuild runs on that stream underneath whatever the caller queues next on the current one; the
     returned event marks dL_dsh ready AND every rank done reading this rank's factors — wait for it before reading
-    dL_dsh and before the next step's backward.  A no-op on a single rank (apart from the rebuild)."""
+    dL_dsh and before the next step's backward.  With `defer_sh` (and `sh_stream`) a callable is returned instead: it
+    queues the rebuild when called and returns that event.  The rebuild is a bandwidth-bound kernel; queued right behind
+    the all-reduce it runs into the next step's per-Gaussian forward, which is bandwidth-bound too (measured: +70 us on
+    that kernel for a 116 us rebuild) — called after the next step's stage 1 has returned
+    (RasterizeGaussiansGeometry(after_stage1=...)) it runs underneath the depth and tile sorts, which are not.
+    A no-op on a single rank (apart from the rebuild)."""
     group = group if group is not None else bucket.group
     if group is not bucket.group:
         raise RuntimeError("exchange_bucket: the bucket was built for another process group")
@@ -285,18 +290,28 @@ def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=
                 sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
                 pr["handle"].barrier(channel=1)   # all sums stored, all factors read
                 return None
-            sh_stream.wait_event(fork)
-            with torch.cuda.stream(sh_stream):
-                _mark("sh_fork", sh_stream)
-                sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
-                _mark("sh_rebuild", sh_stream)
-                pr["handle"].barrier(channel=2)   # every rank has read this rank's factors
-                _mark("sh_barrier2", sh_stream)
-                done = torch.cuda.Event()
-                done.record(sh_stream)
+            trace = _trace
+
+            def launch_rebuild():
+                def mark(label):
+                    if trace is not None:
+                        ev = torch.cuda.Event(enable_timing=True)
+                        ev.record(sh_stream)
+                        trace.append((label, ev))
+                sh_stream.wait_event(fork)
+                with torch.cuda.stream(sh_stream):
+                    mark("sh_fork")
+                    sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
+                    mark("sh_rebuild")
+                    pr["handle"].barrier(channel=2)   # every rank has read this rank's factors
+                    mark("sh_barrier2")
+                    done = torch.cuda.Event()
+                    done.record(sh_stream)
+                return done
+            done = None if defer_sh else launch_rebuild()
             pr["handle"].barrier(channel=1)       # all sums stored
             _mark("barrier1", cur)
-            return done
+            return launch_rebuild if defer_sh else done
         pr["handle"].barrier(channel=1)
         return None
     if distributed:
@@ -314,7 +329,7 @@ def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=
         factor_srcs = [bucket["dL_drgb"][s] for s in range(bucket.views_per_rank)]
     if bucket.factored:
         sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
-    return None
+    return (lambda: None) if defer_sh else None
 
 
 def allreduce_bucket(bucket, dL_dmeans2D, radii, group=None):

@@ -19,7 +19,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 fn = {"bands": bench.bands_block, "dp_views": bench.dp_views_block}[which]
 out = fn(h, par, dev, rank, world, distributed, steps=steps)
 if rank == 0:
-    print(json.dumps({"block": which, "value": out["value"], "unit": out["unit"], "n_gpus": world,
+    print(json.dumps({"block": which, "value": out["value"], "unit": out["unit"], "n_gpus": world, "rank0": out.get("rank0"),
                       "env": {k: v for k, v in os.environ.items() if k.startswith("OGS_")}, "config": out["config"]}), flush=True)
 if distributed:
     dist.destroy_process_group()

@@ -25,7 +25,8 @@ campos_all = [torch.from_numpy(np.stack([sm.random_view(1000 + 97 * s + r)[1] fo
 dL = torch.from_numpy(sm.make_grad_image(W, H, 99)).to(dev)
 bucket = par.GradientBucket(P, 16, dev, views_per_rank=1)
 side = torch.cuda.Stream()
-pending = [None]
+pending, deferred, prev_trace = [None], [None], [None]
+DEFER = os.environ.get("OGS_DP_DEFER", "1") != "0"
 cur = torch.cuda.current_stream()
 rows, hosts = [], []
 
@@ -38,7 +39,14 @@ def step(s, trace):
     par._trace = tr
     t = [time.perf_counter()]
     if trace: mark(tr, "start")
-    st = h.pkg.RasterizeGaussiansGeometry(d["means3D"], d["opacity"], d["scales"], d["rotations"], 1.0, d["cov3D_precomp"], vm, cp, H, W)
+    def launch():
+        if deferred[0] is not None:
+            par._trace = prev_trace[0]
+            pending[0] = deferred[0]()
+            deferred[0] = None
+            par._trace = tr
+    st = h.pkg.RasterizeGaussiansGeometry(d["means3D"], d["opacity"], d["scales"], d["rotations"], 1.0, d["cov3D_precomp"], vm, cp, H, W,
+                                          after_stage1=launch if DEFER else None)
     t.append(time.perf_counter())
     if trace: mark(tr, "geometry_sort")
     if pending[0] is not None:
@@ -50,7 +58,12 @@ def step(s, trace):
     h.pkg.RasterizeGaussiansBackwardView(d["background"], d["means3D"], fwd[2], d["scales"], d["rotations"], 1.0, vm, dL, d["sh"], 3, cp,
                                          fwd[3], fwd[0], fwd[4], fwd[5], bucket, 0)
     t.append(time.perf_counter())
-    pending[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3, sh_stream=side)
+    if DEFER:
+        pending[0] = None
+        deferred[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3, sh_stream=side, defer_sh=True)
+        prev_trace[0] = tr
+    else:
+        pending[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3, sh_stream=side)
     t.append(time.perf_counter())
     par._trace = None
     if trace:
@@ -63,6 +76,10 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record()
 for s in range(steps):
     step(warm + s, True)
+if deferred[0] is not None:
+    par._trace = prev_trace[0]
+    pending[0] = deferred[0]()
+    par._trace = None
 cur.wait_event(pending[0])
 e1.record()
 torch.cuda.synchronize()
@@ -77,6 +94,18 @@ out["gpu_us"]["gap_to_next_start"] = 1e3 * float(np.mean([dict(rows[i])["barrier
 for i, n in enumerate(["geometry_call (blocks on num_rendered)", "blend_call", "backward_call", "exchange_call"]):
     out["host_us"][n] = 1e6 * float(np.mean([t[i + 1] - t[i] for t in hosts]))
 out["host_us"]["step_total"] = 1e6 * float(np.mean([hosts[i + 1][0] - hosts[i][0] for i in range(len(hosts) - 1)]))
+out["defer_sh"] = DEFER
+import ctypes
+lib = h.pkg.load_library()
+names = ["preprocess_fwd", "depth_order", "tile_ranges", "emit", "tile_sort", "render_fwd", "render_bwd", "preprocess_bwd"]
+lib.ogs_profile_enable(1)
+acc = np.zeros(8); buf = (ctypes.c_float * 8)()
+for s in range(5):
+    step(warm + s, False)
+    lib.ogs_profile_read(buf, 8); acc += np.array(list(buf))
+lib.ogs_profile_enable(0)
+torch.cuda.synchronize()
+out["stage_us"] = {n: round(200.0 * v, 1) for n, v in zip(names, acc)}
 for r in range(world):
     if r == rank:
         print(json.dumps(out), flush=True)
