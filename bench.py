@@ -201,7 +201,7 @@ def dp_views_block(h, par, dev, rank, world, distributed, steps=8, warmup=3, con
     poses = [[(torch.from_numpy(a).to(dev), torch.from_numpy(c).to(dev)) for a, c in st] for st in poses]
     bucket = par.GradientBucket(P, 16, dev, views_per_rank=vpr)
     side = torch.cuda.Stream()
-    pending, deferred = [None], [None]
+    pending = [None]
     cur = torch.cuda.current_stream()
 
     def step(s):
@@ -210,10 +210,9 @@ def dp_views_block(h, par, dev, rank, world, distributed, steps=8, warmup=3, con
         for k, v in enumerate(mine):
             vm, cp = poses[s][v]
             if k == 0:
-                # the previous step's dL_dsh rebuild is queued once this step's per-Gaussian kernel has finished (it runs
-                # under the sorts); only the colours wait for it
+                # the previous step's SH gradients may still be in flight: only the colours wait for them
                 st = h.pkg.RasterizeGaussiansGeometry(d["means3D"], d["opacity"], d["scales"], d["rotations"], 1.0,
-                                                      d["cov3D_precomp"], vm, cp, scene.H, scene.W, after_stage1=launch_pending)
+                                                      d["cov3D_precomp"], vm, cp, scene.H, scene.W)
                 if pending[0] is not None:
                     cur.wait_event(pending[0])
                 fwd = h.pkg.RasterizeGaussiansBlend(st, d["background"], d["sh"], 3)
@@ -222,21 +221,12 @@ def dp_views_block(h, par, dev, rank, world, distributed, steps=8, warmup=3, con
                 fwd = h.run_forward(h.pkg, d)
             h.pkg.RasterizeGaussiansBackwardView(d["background"], d["means3D"], fwd[2], d["scales"], d["rotations"], 1.0, vm,
                                                  dL, d["sh"], 3, cp, fwd[3], fwd[0], fwd[4], fwd[5], bucket, k)
-        if not mine:
-            launch_pending()
-            if pending[0] is not None:
-                cur.wait_event(pending[0])
-        pending[0] = None
-        deferred[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3,
-                                          sh_stream=side if distributed else None, defer_sh=distributed)
-
-    def launch_pending():
-        if deferred[0] is not None:
-            pending[0] = deferred[0]()
-            deferred[0] = None
+        if not mine and pending[0] is not None:
+            cur.wait_event(pending[0])
+        pending[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3,
+                                         sh_stream=side if distributed else None)
 
     def drain():
-        launch_pending()
         if pending[0] is not None:
             cur.wait_event(pending[0])
             pending[0] = None
@@ -288,13 +278,18 @@ def bands_block(h, par, dev, rank, world, distributed, steps=6, warmup=2, config
                                             d["sh"], 3, d["campos"], False, 3, False, band=band)
     full = rasterize(None)            # "previous frame": its per-row loads balance the bands
     R_full = full[0]
-    rows = par.tile_row_counts(h.pkg.export_forward_state(P, scene.W, scene.H, R_full, full[3], full[4], full[5], want_keys=False)["ranges"],
-                               scene.W, scene.H)
-    del full
+    prev = h.pkg.export_forward_state(P, scene.W, scene.H, R_full, full[3], full[4], full[5], want_keys=False)
+    rows = par.tile_row_counts(prev["ranges"], scene.W, scene.H)
+    # bands are balanced on estimated cost (instances for the binning, visited list entries for the blend);
+    # OGS_BAND_BALANCE=instances balances on instances alone
+    costs = rows if os.environ.get("OGS_BAND_BALANCE", "cost") == "instances" else \
+        par.tile_row_costs(prev["ranges"], prev["n_contrib"], scene.W, scene.H)
+    del full, prev
     torch.cuda.empty_cache()
-    bands = par.band_rows(rows, world)
+    bands = par.band_rows(costs, world)
     band = bands[rank]
     loads = [sum(rows[a:b]) for a, b in bands]
+    cost_share = [sum(costs[a:b]) / sum(costs) for a, b in bands]
     ex = par.BandExchange(P, scene.W, scene.H, dev) if distributed else None
 
     # OGS_BAND_GATHER=full all-gathers whole bands (every rank ends with the whole frame); the default exchanges the 5-row
@@ -348,13 +343,32 @@ def bands_block(h, par, dev, rank, world, distributed, steps=6, warmup=2, config
         fwd_ms += ev[0].elapsed_time(ev[1]) / 3
         bwd_ms += ev[1].elapsed_time(ev[2]) / 3
     lib.ogs_profile_enable(0)
+    # OGS_BANDS_TRACE=1: every rank's phase timeline (microseconds between successive marks of the exchange code, one frame)
+    trace_all = None
+    if os.environ.get("OGS_BANDS_TRACE") and ex is not None:
+        marks = []
+        par._trace = marks
+        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e_start.record()
+        step()
+        e_end.record()
+        par._trace = None
+        torch.cuda.synchronize()
+        mine_t = {"frame": round(1e3 * e_start.elapsed_time(e_end))}
+        mine_t.update({lab: round(1e3 * e_start.elapsed_time(evm)) for lab, evm in marks})
+        trace_all = [None] * world
+        dist.all_gather_object(trace_all, mine_t)
     stage_names = ["preprocess_fwd", "depth_order", "tile_ranges", "emit", "tile_sort", "render_fwd", "render_bwd", "preprocess_bwd"]
     rank0 = {"forward_ms": fwd_ms, "backward_ms": bwd_ms, "band_instances": int(fwd[0]),
              "stage_ms": {n: float(v) / 3 for n, v in zip(stage_names, acc8)}}
+    if trace_all is not None:
+        rank0["timeline_us_since_frame_start_per_rank"] = trace_all
     out = {"metric": "lonlat_band_parallel_ms_per_frame", "value": float(ms), "unit": "ms", "n_gpus": world, "rank0": rank0,
            "higher_is_better": False, "scaling": "strong", "steps": steps, "warmup": warmup,
            "config": {"workload": config, "gaussians": P, "image": [scene.W, scene.H], "num_rendered": R_full, "bands": bands,
                       "band_instances": loads, "max_over_mean_band_load": max(loads) / (sum(loads) / world),
+                      "band_cost_share": cost_share,
                       "exchange": ((("5-row halos of the band" if halo else "all-gather of band rows") + " (peer stores) + all-reduce of the "
                                      f"[P,12] accumulators in {chunks} ranges pipelined with the per-Gaussian backward (peer / multimem kernel)"
                                      if ex.peer else "NCCL all_gather of band rows / halos + all_reduce of the [P,12] accumulators")
@@ -429,9 +443,9 @@ def main():
     # data parallel (one view per rank and step): the per-Gaussian backward writes the four geometry gradients, the
     # densification statistics and the view's dL/dRGB factor into a factored bucket; ONE kernel all-reduces the 14 floats per
     # Gaussian, and the dL_dsh rebuild (which reads the peers' 3-float factors over NVLink) runs on a side stream underneath
-    # the next step's depth order / tile sort (queued once that step's per-Gaussian kernel has finished: both are
-    # bandwidth bound) — only the colours of the next step wait for it, as they would wait for Adam on the SH coefficients
-    # in a trainer.  OGS_DP_EXCHANGE=nccl forces the NCCL transport, =dense the
+    # the next step's geometry / depth order / tile sort (started right behind the all-reduce; later starts and a capped
+    # grid measured slower, profiles/r02_dp_rebuild_sweep_n4.log) — only the colours of the next step wait for it, as they
+    # would wait for Adam on the SH coefficients in a trainer.  OGS_DP_EXCHANGE=nccl forces the NCCL transport, =dense the
     # round-1 exchange (244 B/Gaussian in one all-reduce, nothing overlapped).
     dp_mode = os.environ.get("OGS_DP_EXCHANGE", "peer")
     bucket = None
@@ -442,23 +456,21 @@ def main():
     campos_all = [torch.from_numpy(np.stack([sm.random_view(1000 + 97 * s + r)[1] for r in range(world)])).to(dev)
                   for s in range(K + Wm)] if distributed else None
     side = torch.cuda.Stream() if distributed else None
-    sh_pending, sh_deferred = [None], [None]
+    sh_pending = [None]
 
     def dp_step(s, dL_img, vm, cp):
         """forward + backward + exchange of one data-parallel step; dL_img: upstream gradient or a callable(image)."""
         cur = torch.cuda.current_stream()
         if bucket.factored:
             st = h.pkg.RasterizeGaussiansGeometry(d["means3D"], d["opacity"], d["scales"], d["rotations"], 1.0,
-                                                  d["cov3D_precomp"], vm, cp, H, W, after_stage1=sh_launch)
+                                                  d["cov3D_precomp"], vm, cp, H, W)
             if sh_pending[0] is not None:
                 cur.wait_event(sh_pending[0])
             fwd = h.pkg.RasterizeGaussiansBlend(st, d["background"], d["sh"], 3)
             g_img = dL_img(fwd[1]) if callable(dL_img) else dL_img
             m2d = h.pkg.RasterizeGaussiansBackwardView(d["background"], d["means3D"], fwd[2], d["scales"], d["rotations"], 1.0,
                                                        vm, g_img, d["sh"], 3, cp, fwd[3], fwd[0], fwd[4], fwd[5], bucket, 0)
-            sh_pending[0] = None
-            sh_deferred[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3,
-                                                 sh_stream=side, defer_sh=True)
+            sh_pending[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3, sh_stream=side)
             return fwd, m2d
         d["viewmatrix"], d["campos"], d["projmatrix"] = vm, cp, vm
         fwd = h.run_forward(mod, d)
@@ -467,14 +479,7 @@ def main():
         par.allreduce_bucket(bucket, g[0], fwd[2])
         return fwd, g
 
-    def sh_launch():
-        """queue the previous step's dL_dsh rebuild (called by the geometry half once its per-Gaussian kernel is done)"""
-        if sh_deferred[0] is not None:
-            sh_pending[0] = sh_deferred[0]()
-            sh_deferred[0] = None
-
     def dp_drain():
-        sh_launch()
         if sh_pending[0] is not None:
             torch.cuda.current_stream().wait_event(sh_pending[0])
             sh_pending[0] = None

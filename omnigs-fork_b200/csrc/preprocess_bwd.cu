@@ -29,6 +29,7 @@
 #include "gaussian_grad.cuh"
 #include "launchers.cuh"
 #include "async_copy.cuh"
+#include <cstdlib>
 
 namespace ogs {
 
@@ -354,68 +355,88 @@ __global__ void __launch_bounds__(kPreBwdThreads, OGS_PREBWD_MINBLOCKS) preproce
 // in that order).  drgb[v] may be a peer GPU's buffer (NVLink loads: the transfer IS this kernel's input stream).
 // One warp per 32 Gaussians: the 48-float rows are staged in shared memory and leave as fully coalesced 128-bit stores.
 constexpr int kShViewsThreads = 128;
+constexpr int kShViewsBatch = 4;   // views whose factors are loaded together (independent NVLink loads in flight per thread)
 __global__ void __launch_bounds__(kShViewsThreads) sh_gradient_from_views_kernel(const ShFromViewsArgs a)
 {
 	__shared__ float s_rows[kShViewsThreads / 32][kShRowFloats * 33];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int first = (blockIdx.x * (kShViewsThreads / 32) + warp) * 32;   // first Gaussian of this warp
-	if (first >= a.P) return;
-	const int idx = first + lane;
 	const int n = (a.D + 1) * (a.D + 1);
-	float acc[kShRowFloats];
+	float* s = s_rows[warp];
+	// grid-stride over groups of 32 Gaussians
+	const int groups = (a.P + 31) / 32;
+	for (int grp = blockIdx.x * (kShViewsThreads / 32) + warp; grp < groups; grp += gridDim.x * (kShViewsThreads / 32)) {
+		const int first = grp * 32;
+		const int idx = first + lane;
+		float acc[kShRowFloats];
 #pragma unroll
-	for (int k = 0; k < kShRowFloats; k++) acc[k] = 0.f;
-	if (idx < a.P) {
-		const float mx = a.means3D[3 * (size_t)idx], my = a.means3D[3 * (size_t)idx + 1], mz = a.means3D[3 * (size_t)idx + 2];
-		for (int v = 0; v < a.n_views; v++) {
-			const float* dv = a.drgb[v] + 3 * (size_t)idx;
-			const float d0 = dv[0], d1 = dv[1], d2 = dv[2];
-			if (d0 == 0.f && d1 == 0.f && d2 == 0.f) continue;   // not visible in this view (or fully clamped): adds exact zeros
-			const float vx = mx - a.campos[3 * v], vy = my - a.campos[3 * v + 1], vz = mz - a.campos[3 * v + 2];
-			const float len = sqrtf(vx * vx + vy * vy + vz * vz);
-			float b[16];
-			grad::sh_weights<float>(a.D, vx / len, vy / len, vz / len, b);
+		for (int k = 0; k < kShRowFloats; k++) acc[k] = 0.f;
+		if (idx < a.P) {
+			const float mx = a.means3D[3 * (size_t)idx], my = a.means3D[3 * (size_t)idx + 1], mz = a.means3D[3 * (size_t)idx + 2];
+			for (int v0 = 0; v0 < a.n_views; v0 += kShViewsBatch) {
+				float dd[kShViewsBatch][3];
 #pragma unroll
-			for (int k = 0; k < 16; k++) {
-				if (k < n) {
-					acc[3 * k + 0] = __fadd_rn(acc[3 * k + 0], grad::mul1(b[k], d0));
-					acc[3 * k + 1] = __fadd_rn(acc[3 * k + 1], grad::mul1(b[k], d1));
-					acc[3 * k + 2] = __fadd_rn(acc[3 * k + 2], grad::mul1(b[k], d2));
+				for (int j = 0; j < kShViewsBatch; j++) {
+					const bool have = v0 + j < a.n_views;
+					const float* dv = a.drgb[have ? v0 + j : 0] + 3 * (size_t)idx;
+					dd[j][0] = have ? dv[0] : 0.f;
+					dd[j][1] = have ? dv[1] : 0.f;
+					dd[j][2] = have ? dv[2] : 0.f;
+				}
+#pragma unroll
+				for (int j = 0; j < kShViewsBatch; j++) {
+					const float d0 = dd[j][0], d1 = dd[j][1], d2 = dd[j][2];
+					if (d0 == 0.f && d1 == 0.f && d2 == 0.f) continue;   // not visible in this view (or fully clamped): adds exact zeros
+					const int v = v0 + j;
+					const float vx = mx - a.campos[3 * v], vy = my - a.campos[3 * v + 1], vz = mz - a.campos[3 * v + 2];
+					const float len = sqrtf(vx * vx + vy * vy + vz * vz);
+					float b[16];
+					grad::sh_weights<float>(a.D, vx / len, vy / len, vz / len, b);
+#pragma unroll
+					for (int k = 0; k < 16; k++) {
+						if (k < n) {
+							acc[3 * k + 0] = __fadd_rn(acc[3 * k + 0], grad::mul1(b[k], d0));
+							acc[3 * k + 1] = __fadd_rn(acc[3 * k + 1], grad::mul1(b[k], d1));
+							acc[3 * k + 2] = __fadd_rn(acc[3 * k + 2], grad::mul1(b[k], d2));
+						}
+					}
 				}
 			}
 		}
-	}
-	// transposed staging at a 33-word pitch: element (row r, float k) at s[k * 33 + r] — lane-per-row writes and
-	// lane-per-output-float reads are both conflict-free
-	const int rows = min(32, a.P - first);
-	float* s = s_rows[warp];
+		// transposed staging at a 33-word pitch: element (row r, float k) at s[k * 33 + r] — lane-per-row writes and
+		// lane-per-output-float reads are both conflict-free
+		const int rows = min(32, a.P - first);
 #pragma unroll
-	for (int k = 0; k < kShRowFloats; k++) s[k * 33 + lane] = acc[k];
-	__syncwarp();
-	if (a.dL_dsh) {
-		// [P,16,3]: the warp's rows are rows * 48 contiguous floats, stored as 128-bit words
-		float4* out = reinterpret_cast<float4*>(a.dL_dsh + (size_t)first * kShRowFloats);
-		for (int i = lane; i < rows * (kShRowFloats / 4); i += 32) {
-			const int f = 4 * i, r = f / kShRowFloats, k = f - r * kShRowFloats;   // 48 is a multiple of 4: one row per word
-			out[i] = make_float4(s[k * 33 + r], s[(k + 1) * 33 + r], s[(k + 2) * 33 + r], s[(k + 3) * 33 + r]);
+		for (int k = 0; k < kShRowFloats; k++) s[k * 33 + lane] = acc[k];
+		__syncwarp();
+		if (a.dL_dsh) {
+			// [P,16,3]: the warp's rows are rows * 48 contiguous floats, stored as 128-bit words
+			float4* out = reinterpret_cast<float4*>(a.dL_dsh + (size_t)first * kShRowFloats);
+			for (int i = lane; i < rows * (kShRowFloats / 4); i += 32) {
+				const int f = 4 * i, r = f / kShRowFloats, k = f - r * kShRowFloats;   // 48 is a multiple of 4: one row per word
+				out[i] = make_float4(s[k * 33 + r], s[(k + 1) * 33 + r], s[(k + 2) * 33 + r], s[(k + 3) * 33 + r]);
+			}
+		} else {
+			// split layout (raw-parameter trainer): dL/dfeatures_rest rows of 45 floats, dL/dfeatures_dc rows of 3
+			float* rest = a.dL_dfeatures_rest + (size_t)first * kRawRestFloats;
+			float* dc = a.dL_dfeatures_dc + (size_t)first * 3;
+			for (int i = lane; i < rows * kRawRestFloats; i += 32) {
+				const int r = i / kRawRestFloats, k = i - r * kRawRestFloats;
+				rest[i] = s[(3 + k) * 33 + r];
+			}
+			for (int i = lane; i < rows * 3; i += 32) dc[i] = s[(i % 3) * 33 + i / 3];
 		}
-	} else {
-		// split layout (raw-parameter trainer): dL/dfeatures_rest rows of 45 floats, dL/dfeatures_dc rows of 3
-		float* rest = a.dL_dfeatures_rest + (size_t)first * kRawRestFloats;
-		float* dc = a.dL_dfeatures_dc + (size_t)first * 3;
-		for (int i = lane; i < rows * kRawRestFloats; i += 32) {
-			const int r = i / kRawRestFloats, k = i - r * kRawRestFloats;
-			rest[i] = s[(3 + k) * 33 + r];
-		}
-		for (int i = lane; i < rows * 3; i += 32) dc[i] = s[(i % 3) * 33 + i / 3];
+		__syncwarp();   // the staging rows are reused by the next group
 	}
 }
 
 int launch_sh_gradient_from_views(const ShFromViewsArgs& a, cudaStream_t st)
 {
 	if (a.P <= 0) return OGS_OK;
-	const int per_block = kShViewsThreads;   // Gaussians per block
-	sh_gradient_from_views_kernel<<<ceil_div(a.P, per_block), kShViewsThreads, 0, st>>>(a);
+	const int per_block = kShViewsThreads;   // Gaussians per block and trip
+	// one trip per block: a capped, slower grid was measured on four B200s (profiles/r02_dp_rebuild_sweep_n4.log) — it
+	// disturbs the latency-bound sort passes it overlaps for longer and the step gets slower
+	const int blocks = ceil_div(a.P, per_block);
+	sh_gradient_from_views_kernel<<<blocks, kShViewsThreads, 0, st>>>(a);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }

@@ -237,18 +237,17 @@ def _mark(label, stream):
         _trace.append((label, ev))
 
 
-def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=3, sh_stream=None, defer_sh=False):
+def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=3, sh_stream=None):
     """Sum the bucket's summed section and max-reduce its radii over ranks, in place: one kernel over NVLink peer
     memory / the multicast address when the bucket lives in symmetric memory (csrc/peer_collective.cu), NCCL / gloo
     all-reduce otherwise.  Factored buckets then rebuild bucket["dL_dsh"] from every rank's view factors (means3D and
     campos_views [views_per_rank * world, 3], view v = slot * world + rank, are needed for the directions).  With
     `sh_stream` the rebuild runs on that stream underneath whatever the caller queues next on the current one; the
     returned event marks dL_dsh ready AND every rank done reading this rank's factors — wait for it before reading
-    dL_dsh and before the next step's backward.  With `defer_sh` (and `sh_stream`) a callable is returned instead: it
-    queues the rebuild when called and returns that event.  The rebuild is a bandwidth-bound kernel; queued right behind
-    the all-reduce it runs into the next step's per-Gaussian forward, which is bandwidth-bound too (measured: +70 us on
-    that kernel for a 116 us rebuild) — called after the next step's stage 1 has returned
-    (RasterizeGaussiansGeometry(after_stage1=...)) it runs underneath the depth and tile sorts, which are not.
+    dL_dsh and before the next step's backward.  (Measured on four B200s, profiles/r02_dp_rebuild_sweep_n4.log: the rebuild is
+    a bandwidth-bound kernel and costs about its own duration wherever it overlaps the next step's per-Gaussian forward or
+    sorts; queueing it later — after that step's stage 1 — or capping its grid so that it trickles along both measured
+    slower than starting it right behind the all-reduce.)
     A no-op on a single rank (apart from the rebuild)."""
     group = group if group is not None else bucket.group
     if group is not bucket.group:
@@ -290,28 +289,18 @@ def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=
                 sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
                 pr["handle"].barrier(channel=1)   # all sums stored, all factors read
                 return None
-            trace = _trace
-
-            def launch_rebuild():
-                def mark(label):
-                    if trace is not None:
-                        ev = torch.cuda.Event(enable_timing=True)
-                        ev.record(sh_stream)
-                        trace.append((label, ev))
-                sh_stream.wait_event(fork)
-                with torch.cuda.stream(sh_stream):
-                    mark("sh_fork")
-                    sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
-                    mark("sh_rebuild")
-                    pr["handle"].barrier(channel=2)   # every rank has read this rank's factors
-                    mark("sh_barrier2")
-                    done = torch.cuda.Event()
-                    done.record(sh_stream)
-                return done
-            done = None if defer_sh else launch_rebuild()
+            sh_stream.wait_event(fork)
+            with torch.cuda.stream(sh_stream):
+                _mark("sh_fork", sh_stream)
+                sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
+                _mark("sh_rebuild", sh_stream)
+                pr["handle"].barrier(channel=2)   # every rank has read this rank's factors
+                _mark("sh_barrier2", sh_stream)
+                done = torch.cuda.Event()
+                done.record(sh_stream)
             pr["handle"].barrier(channel=1)       # all sums stored
             _mark("barrier1", cur)
-            return launch_rebuild if defer_sh else done
+            return done
         pr["handle"].barrier(channel=1)
         return None
     if distributed:
@@ -329,7 +318,7 @@ def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=
         factor_srcs = [bucket["dL_drgb"][s] for s in range(bucket.views_per_rank)]
     if bucket.factored:
         sh_gradient_from_views(means3D, campos_views, factor_srcs, degree, bucket["dL_dsh"])
-    return (lambda: None) if defer_sh else None
+    return None
 
 
 def allreduce_bucket(bucket, dL_dmeans2D, radii, group=None):
@@ -348,6 +337,22 @@ def tile_row_counts(ranges, W, H):
     gx, gy = (W + 15) // 16, (H + 15) // 16
     lens = (ranges[:, 1] - ranges[:, 0]).to(torch.int64).view(gy, gx)
     return lens.sum(dim=1).tolist()
+
+
+def tile_row_costs(ranges, n_contrib, W, H, ps_per_instance=15.0, ps_per_visited_pair=1.3):
+    """Estimated cost of every tile row of a frame from the previous frame's state: binning work goes with the row's
+    instances, blending work with the list entries its pixels walk (sum of n_contrib).  An equatorial instance costs about
+    twice a polar one in the blend kernels (profiles/r02_tile_timeline.json), so bands balanced on instances alone leave the
+    polar ranks waiting.  The two weights are the C2 frame's measured picoseconds per instance (emission + tile sort) and per
+    visited pair (both blend kernels); only their ratio matters.  Returns a list of gy floats for band_rows."""
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    inst = (ranges[:, 1] - ranges[:, 0]).to(torch.float64).view(gy, gx).sum(dim=1)
+    nc = n_contrib.view(H, W).to(torch.float64).sum(dim=1)
+    pad = gy * 16 - H
+    if pad:
+        nc = torch.cat([nc, nc.new_zeros(pad)])
+    visited = nc.view(gy, 16).sum(dim=1)
+    return (ps_per_instance * inst + ps_per_visited_pair * visited).tolist()
 
 
 class BandExchange:
@@ -422,11 +427,14 @@ class BandExchange:
             pr = self.peer
             imgs = (ctypes.c_void_p * pr["world"])(*[p + self._img_off for p in pr["ptrs"]])
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+            _mark("band_rendered", torch.cuda.current_stream(self.flat.device))
             for a, b in (top, bottom):
                 if b > a:
                     check(load_library().ogs_band_rows_allgather(imgs, pr["world"], pr["rank"], ctypes.c_void_p(band_image.data_ptr()),
                                                                  self.W, self.H, a, b, stream))
+            _mark("halo_sent", torch.cuda.current_stream(self.flat.device))
             pr["handle"].barrier(channel=3)
+            _mark("halo_barrier", torch.cuda.current_stream(self.flat.device))
         else:
             world = dist.get_world_size(self.group)
             mine = band_image.new_zeros((3, 2 * h, self.W))
@@ -487,7 +495,9 @@ class BandExchange:
         cur = torch.cuda.current_stream(self.flat.device)
         if getattr(self, "_comm", None) is None:
             self._comm = torch.cuda.Stream(self.flat.device)
+        _mark("render_bwd_done", cur)
         pr["handle"].barrier(channel=0)                      # every rank's render backward has written its partial sums
+        _mark("acc_barrier0", cur)
         ready = torch.cuda.Event()
         ready.record(cur)
         self._comm.wait_event(ready)
@@ -503,7 +513,9 @@ class BandExchange:
                     arr = (ctypes.c_void_p * pr["world"])(*[p + off for p in pr["ptrs"]])
                     check(load_library().ogs_peer_allreduce(arr, pr["world"], pr["rank"], n, 0, stream))
                 # a range's sums are complete on THIS rank once every rank has stored its slice of it
+                _mark(f"acc_range{len(events)}_reduced", self._comm)
                 pr["handle"].barrier(channel=1)
+                _mark(f"acc_range{len(events)}_barrier", self._comm)
                 ev = torch.cuda.Event()
                 ev.record(self._comm)
                 events.append(ev)
@@ -547,7 +559,7 @@ def band_rows(row_instance_counts, world):
     """Split tile rows [0, gy) into `world` contiguous bands with balanced instance counts.
     row_instance_counts[y] = number of tile instances in tile row y.  Returns [(y0, y1)] * world;
     bands may be empty when world > gy."""
-    counts = [int(c) for c in row_instance_counts]
+    counts = [float(c) for c in row_instance_counts]
     gy, total = len(counts), sum(counts)
     bands, y, acc = [], 0, 0
     for g in range(world):

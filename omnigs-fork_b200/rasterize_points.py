@@ -288,13 +288,10 @@ def RasterizeGaussiansBackwardView(background, means3D, radii, scales, rotations
 
 
 def RasterizeGaussiansGeometry(means3D, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, campos,
-                               image_height, image_width, after_stage1=None):
+                               image_height, image_width):
     """First half of a pipelined lonlat forward (extension for data-parallel training): everything that does not read
     the SH coefficients — per-Gaussian geometry, depth order, emission and tile sort (ogs_lonlat_forward_stage1_geometry
-    + ogs_lonlat_forward_bin).  Returns the state RasterizeGaussiansBlend completes.  ``after_stage1``: a callable run
-    between the two library calls, i.e. once the per-Gaussian kernel has finished (stage 1 returns with num_rendered on
-    the host) and the depth order is queued: the place to queue bandwidth-bound side work (the data-parallel dL_dsh
-    rebuild) so that it runs under the sorts instead of under the per-Gaussian kernel."""
+    + ogs_lonlat_forward_bin).  Returns the state RasterizeGaussiansBlend completes."""
     _require_cuda(means3D, "means3D")
     lib = load_library()
     device = means3D.device
@@ -313,8 +310,6 @@ def RasterizeGaussiansGeometry(means3D, opacity, scales, rotations, scale_modifi
             _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(campos), _ptr(radii), _ptr(geomBuffer), _ptr(imgBuffer),
             ctypes.byref(n), st))
         rendered = int(n.value)
-        if after_stage1 is not None:
-            after_stage1()
         need = lib.ogs_binning_bytes(rendered, W, H)
         binningBuffer = torch.empty((-(-need // _BINNING_GRANULE) * _BINNING_GRANULE,), **byte_opts)
         check(lib.ogs_lonlat_forward_bin(P, W, H, rendered, _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), st))

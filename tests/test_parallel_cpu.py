@@ -106,22 +106,6 @@ def test_allreduce_is_identity_on_one_rank():
     assert stats["denom"].sum() == (radii > 0).sum()
 
 
-def test_deferred_sh_rebuild_on_one_rank_gives_the_same_rows():
-    """exchange_bucket(defer_sh=True) hands back a callable (the caller queues the rebuild later); off the NVLink path
-    the rows are rebuilt at once and the callable has nothing left to do."""
-    P = 50
-    g = torch.Generator().manual_seed(3)
-    means, campos = torch.randn((P, 3), generator=g), torch.randn((2, 3), generator=g)
-    outs = []
-    for defer in (False, True):
-        b = par.GradientBucket(P, 16, "cpu", views_per_rank=2)
-        b["dL_drgb"].copy_(torch.randn((2, P, 3), generator=torch.Generator().manual_seed(4)))
-        ret = par.exchange_bucket(b, means3D=means, campos_views=campos, degree=3, defer_sh=defer)
-        assert (ret is None) if not defer else (callable(ret) and ret() is None)
-        outs.append(b["dL_dsh"].clone())
-    assert torch.equal(outs[0], outs[1]) and float(outs[0].abs().max()) > 0
-
-
 def test_views_round_robin():
     assert par.views_for_rank(8, 1, 4) == [1, 5]
     assert sorted(sum((par.views_for_rank(8, r, 3) for r in range(3)), [])) == list(range(8))

@@ -26,7 +26,7 @@ dL = torch.from_numpy(sm.make_grad_image(W, H, 99)).to(dev)
 bucket = par.GradientBucket(P, 16, dev, views_per_rank=1)
 side = torch.cuda.Stream()
 pending, deferred, prev_trace = [None], [None], [None]
-DEFER = os.environ.get("OGS_DP_DEFER", "1") != "0"
+DEFER = False
 cur = torch.cuda.current_stream()
 rows, hosts = [], []
 
@@ -45,8 +45,7 @@ def step(s, trace):
             pending[0] = deferred[0]()
             deferred[0] = None
             par._trace = tr
-    st = h.pkg.RasterizeGaussiansGeometry(d["means3D"], d["opacity"], d["scales"], d["rotations"], 1.0, d["cov3D_precomp"], vm, cp, H, W,
-                                          after_stage1=launch if DEFER else None)
+    st = h.pkg.RasterizeGaussiansGeometry(d["means3D"], d["opacity"], d["scales"], d["rotations"], 1.0, d["cov3D_precomp"], vm, cp, H, W)
     t.append(time.perf_counter())
     if trace: mark(tr, "geometry_sort")
     if pending[0] is not None:
@@ -60,7 +59,7 @@ def step(s, trace):
     t.append(time.perf_counter())
     if DEFER:
         pending[0] = None
-        deferred[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3, sh_stream=side, defer_sh=True)
+        raise RuntimeError("deferred rebuild was removed (measured slower)")
         prev_trace[0] = tr
     else:
         pending[0] = par.exchange_bucket(bucket, means3D=d["means3D"], campos_views=campos_all[s], degree=3, sh_stream=side)
