@@ -306,6 +306,27 @@ def bands_block(h, par, dev, rank, world, distributed, steps=6, warmup=2, config
             h.run_backward(h.pkg, d, fwd, dL)
         return fwd[0]
 
+    # feedback balancing (a trainer does this as it goes): three calibration frames, each followed by a re-cut of the bands
+    # from the ranks' measured band-dependent kernel times (the library's own stage events)
+    lib = h.pkg.load_library()
+    band_ms_history = []
+    if distributed and os.environ.get("OGS_BAND_FEEDBACK", "1") != "0":
+        buf8 = (ctypes.c_float * 8)()
+        for _ in range(3):
+            lib.ogs_profile_enable(1)
+            step()
+            lib.ogs_profile_read(buf8, 8)
+            lib.ogs_profile_enable(0)
+            mine_ms = float(buf8[3] + buf8[4] + buf8[5] + buf8[6])     # emit, tile_sort, render_fwd, render_bwd
+            got = [None] * world
+            dist.all_gather_object(got, mine_ms)
+            band_ms_history.append(got)
+            costs = par.rescale_row_costs(costs, bands, got)
+            bands = par.band_rows(costs, world)
+            band = bands[rank]
+        loads = [sum(rows[a:b]) for a, b in bands]
+        cost_share = [sum(costs[a:b]) / sum(costs) for a, b in bands]
+
     for _ in range(warmup):
         Rb = step()
     torch.cuda.synchronize()
@@ -322,7 +343,6 @@ def bands_block(h, par, dev, rank, world, distributed, steps=6, warmup=2, config
         dist.barrier()
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     # where the frame goes on rank 0: the library's per-stage events (3 frames) and the forward / backward split
-    lib = h.pkg.load_library()
     lib.ogs_profile_enable(1)
     acc8, buf8 = np.zeros(8), (ctypes.c_float * 8)()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -346,17 +366,19 @@ def bands_block(h, par, dev, rank, world, distributed, steps=6, warmup=2, config
     # OGS_BANDS_TRACE=1: every rank's phase timeline (microseconds between successive marks of the exchange code, one frame)
     trace_all = None
     if os.environ.get("OGS_BANDS_TRACE") and ex is not None:
-        marks = []
-        par._trace = marks
-        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        frames = []
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-        e_start.record()
-        step()
-        e_end.record()
+        for _ in range(5):          # back to back like the timed loop; the last frame is reported
+            marks = []
+            par._trace = marks
+            par._mark("frame_start", torch.cuda.current_stream())
+            step()
+            par._mark("frame_end", torch.cuda.current_stream())
+            frames.append(marks)
         par._trace = None
         torch.cuda.synchronize()
-        mine_t = {"frame": round(1e3 * e_start.elapsed_time(e_end))}
-        mine_t.update({lab: round(1e3 * e_start.elapsed_time(evm)) for lab, evm in marks})
+        t0 = frames[-1][0][1]
+        mine_t = {lab: round(1e3 * t0.elapsed_time(evm)) for lab, evm in frames[-1][1:]}
         trace_all = [None] * world
         dist.all_gather_object(trace_all, mine_t)
     stage_names = ["preprocess_fwd", "depth_order", "tile_ranges", "emit", "tile_sort", "render_fwd", "render_bwd", "preprocess_bwd"]
@@ -368,7 +390,7 @@ def bands_block(h, par, dev, rank, world, distributed, steps=6, warmup=2, config
            "higher_is_better": False, "scaling": "strong", "steps": steps, "warmup": warmup,
            "config": {"workload": config, "gaussians": P, "image": [scene.W, scene.H], "num_rendered": R_full, "bands": bands,
                       "band_instances": loads, "max_over_mean_band_load": max(loads) / (sum(loads) / world),
-                      "band_cost_share": cost_share,
+                      "band_cost_share": cost_share, "band_kernel_ms_during_calibration": band_ms_history,
                       "exchange": ((("5-row halos of the band" if halo else "all-gather of band rows") + " (peer stores) + all-reduce of the "
                                      f"[P,12] accumulators in {chunks} ranges pipelined with the per-Gaussian backward (peer / multimem kernel)"
                                      if ex.peer else "NCCL all_gather of band rows / halos + all_reduce of the [P,12] accumulators")
