@@ -293,9 +293,11 @@ def bands_block(h, par, dev, rank, world, distributed, steps=6, warmup=2, config
     ex = par.BandExchange(P, scene.W, scene.H, dev) if distributed else None
 
     # OGS_BAND_GATHER=full all-gathers whole bands (every rank ends with the whole frame); the default exchanges the 5-row
-    # halos a band-wise L1 + SSIM loss needs (11-tap window).  OGS_BAND_CHUNKS: ranges of the pipelined accumulator exchange.
+    # halos a band-wise L1 + SSIM loss needs (11-tap window).  OGS_BAND_CHUNKS > 1 pipelines the accumulator exchange with the
+    # per-Gaussian backward in Gaussian ranges (measured on four B200s: 5.61 ms with four ranges, 5.55 ms with one — the all-reduce
+    # kernel fills the SMs, so the ranges do not overlap usefully; profiles/r02_bands_trace_n4.log).
     halo = None if os.environ.get("OGS_BAND_GATHER", "halo") == "full" else 5
-    chunks = int(os.environ.get("OGS_BAND_CHUNKS", "4"))
+    chunks = int(os.environ.get("OGS_BAND_CHUNKS", "1"))
 
     def step():
         img, fwd = par.render_band_forward(rasterize, band, scene.H, exchange=ex, halo=halo)
