@@ -458,7 +458,9 @@ int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st)
 			preprocess_lonlat_bwd_kernel<2><<<blocks, kPreBwdThreads, 0, st>>>(a);
 		else
 			preprocess_lonlat_bwd_kernel<3><<<blocks, kPreBwdThreads, 0, st>>>(a);
-	} else if (a.shs != nullptr && a.dL_dsh != nullptr && sh_rows_bulk_capable(a.shs, a.M) && sh_rows_bulk_capable(a.dL_dsh, a.M))
+	} else if (a.shs != nullptr && sh_rows_bulk_capable(a.shs, a.M) &&
+	           ((a.dL_dsh != nullptr && sh_rows_bulk_capable(a.dL_dsh, a.M)) || (a.dL_dsh == nullptr && a.dL_drgb_view != nullptr)))
+		// (multi-view mode leaves dL/dRGB instead of the dL/dsh row: the SH rows still come in through the bulk path)
 		preprocess_lonlat_bwd_kernel<1><<<blocks, kPreBwdThreads, 0, st>>>(a);
 	else
 		preprocess_lonlat_bwd_kernel<0><<<blocks, kPreBwdThreads, 0, st>>>(a);

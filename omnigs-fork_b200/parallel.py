@@ -277,7 +277,7 @@ def exchange_bucket(bucket, group=None, means3D=None, campos_views=None, degree=
         fork = None
         if bucket.factored and sh_stream is not None:
             # the dL_dsh rebuild starts BEHIND the all-reduce: run side by side the two share NVLink and the all-reduce — the
-            # one the optimiser waits for — takes 0.36 ms instead of 0.15 (profiles/r02_dp_trace_n8.log); behind it the
+            # one the optimiser waits for — takes 0.36 ms instead of 0.15 (profiles/r02_dp_trace_n8_before.log); behind it the
             # rebuild overlaps the next step's geometry / depth order / tile sort instead
             fork = torch.cuda.Event()
             fork.record(cur)
