@@ -471,8 +471,9 @@ OGS_API int ogs_lonlat_forward_blend(
 		b = BinningState::carve(binning_buffer, num_rendered, W, H);
 	}
 	prof_begin(OGS_PROF_RENDER_FWD, st);
+	// the tile-key array of the binning buffer is dead once the list is sorted: it takes the blend's hit bytes
 	const int rc = launch_render_fwd(img.ranges, b.point_list, W, H, g.g0, g.g1, g.gb, g.scalars, background,
-	                                 img.final_T, img.n_contrib, out_color, st);
+	                                 img.final_T, img.n_contrib, out_color, reinterpret_cast<uint8_t*>(b.key[0]), st);
 	prof_end(OGS_PROF_RENDER_FWD, st);
 	return rc;
 }
@@ -546,7 +547,7 @@ OGS_API int ogs_lonlat_backward_render_into(
 	OGS_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(float) * 12 * (size_t)P, st));
 	prof_begin(OGS_PROF_RENDER_BWD, st);
 	if (int rc = launch_render_bwd(img.ranges, b.point_list, W, H, background, g.g0, g.g1, g.gb, g.scalars,
-	                               img.final_T, img.n_contrib, dL_dpix, acc, st)) return rc;
+	                               img.final_T, img.n_contrib, dL_dpix, acc, reinterpret_cast<const uint8_t*>(b.key[0]), st)) return rc;
 	prof_end(OGS_PROF_RENDER_BWD, st);
 	return OGS_OK;
 }

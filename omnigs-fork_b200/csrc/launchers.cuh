@@ -1,6 +1,7 @@
 // launchers.cuh — kernel argument blocks and host-side launchers shared between the
 // translation units of libomnigs_b200.so.
 #pragma once
+#include <cstdlib>
 #include "ogs_common.cuh"
 
 namespace ogs {
@@ -114,15 +115,32 @@ int launch_emit_and_tile_sort(const GeomState& g, const ImageState& img, const B
                               int P, int64_t R, int W, int H, cudaStream_t st);
 int launch_rebuild_keys(const ImageState& img, const BinningState& b, const GeomState& g, int W, int H,
                         uint64_t* keys, cudaStream_t st);
+// hit_bytes: one byte per list entry (R bytes; the dead tile-key array of the binning buffer): bit w = the entry can reach
+// the 8x4 sub-block w of its tile, as decided by the forward blend; the backward blend consumes it
 int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
                       const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars, const float* bg,
-                      float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st);
+                      float* final_T, uint32_t* n_contrib, float* out_color, uint8_t* hit_bytes, cudaStream_t st);
+// OGS_FWD_STAGING=ldgsts|bulk: the asynchronous-staging experiment kernels (1 / 2), which do not write hit bytes
+inline int fwd_staging_mode()
+{
+	static const int v = [] {
+		const char* e = getenv("OGS_FWD_STAGING");
+		return !e ? 0 : (e[0] == 'l' ? 1 : (e[0] == 'b' ? 2 : 0));
+	}();
+	return v;
+}
+// the backward takes the forward's sub-block decisions unless the experiment forward ran or OGS_BWD_HITS=0 (A/B runs)
+inline bool render_hit_bytes_enabled()
+{
+	static const bool v = [] { const char* e = getenv("OGS_BWD_HITS"); return !(e && e[0] == '0'); }();
+	return v && fwd_staging_mode() == 0;
+}
 int launch_pair_count(const uint2* ranges, const uint32_t* point_list, int W, int H, const float4* g0, const float4* g1,
                       const uint32_t* n_contrib, unsigned long long* counts, cudaStream_t st);
 int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, int H, const float* bg,
                       const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
-                      float* grad_acc, cudaStream_t st);
+                      float* grad_acc, const uint8_t* hit_bytes, cudaStream_t st);
 int launch_preprocess_bwd(const PreprocessBwdArgs& a, cudaStream_t st);
 
 // ---- train_step.cu: the per-iteration work either side of the rasterizer

@@ -6,10 +6,13 @@
 // w.r.t. the Gaussian's 2-D mean, conic, opacity and colour are the same expressions.  The reference
 // then issues 9 global float atomics per (pixel, Gaussian) pair (backward.cu:805,829-840).  Here:
 //   * the tile list is cut at the tile's largest n_contrib (nothing behind it was blended);
-//   * entries are tile-culled and stably compacted into shared memory like in the forward;
+//   * the forward left one byte per list entry saying which of the tile's eight 8x4 sub-blocks the entry can reach
+//     (render_fwd.cu, hit_bytes): entries with a zero byte are neither gathered nor tested, the others are stably
+//     compacted into shared memory with their byte (without the bytes — OGS_BWD_HITS=0, or after the experiment forward
+//     kernels — the kernel runs the tile-level and sub-block tests itself: kHits = false);
 //   * a CTA is two warps; each warp owns a 16x8 half-tile and each LANE owns four pixels, one in each
-//     8x4 sub-block of that half.  The warp tests 32 staged entries at a time against its four
-//     sub-blocks (one entry per lane, four ballots) and visits only entries that can reach it;
+//     8x4 sub-block of that half.  The warp takes 32 staged entries at a time (one per lane, four ballots: a bit of
+//     the entry's byte per sub-block) and visits only entries that can reach it;
 //   * per visited entry every lane adds up, over its (up to four) contributing pixels, nine raw sums:
 //       u*dx, u*dy, u*dx^2, u*dx*dy, u*dy^2 (u = dL/dG * G), G*dL/dalpha and the three colour terms.
 //     They are reduced over the warp with ONE transposing butterfly (14 shuffles for 9 values) —
@@ -79,16 +82,21 @@ OGS_D float ex2_approx(float x)
 	return r;
 }
 
-template <int kMinBlocks>
+// kHits: the forward blend left one byte per list entry whose bit w says "can reach sub-block w of the tile" (the same
+// eight 8x4 sub-blocks: this kernel's warp W, slot s is the forward's warp 4W + s).  The tile-level and sub-block tests
+// below are then not repeated: entries with a zero byte are not even gathered, the others bring their ballots with them.
+// Bits are only ever missing for entries a sub-block's pixels had all finished before (no pixel blended them).
+template <int kMinBlocks, bool kHits>
 __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx, int gy, int order,
 	const float* __restrict__ bg_color,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float2* __restrict__ gb,
 	const unsigned long long* __restrict__ scalars,
 	const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
-	const float* __restrict__ dL_dpixels, float* __restrict__ grad_acc /*[P,12]*/)
+	const float* __restrict__ dL_dpixels, float* __restrict__ grad_acc /*[P,12]*/, const uint8_t* __restrict__ hit_bytes)
 {
 	__shared__ StagedEntry s_e[kBwdBatch];
+	__shared__ uint8_t s_mask[kHits ? kBwdBatch : 4];
 	// per (slot, thread): dL/dpixel (r, g, b) and -T_final * (bg . dL/dpixel) — read once per contributing pair with one
 	// conflict-free 128-bit load instead of living in 16 registers
 	__shared__ float4 s_pix[kBwdSlots][kBwdThreads];
@@ -170,22 +178,26 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 		int pos[kBwdPerThread];
 		bool keep[kBwdPerThread];
 		int my_keep = 0;
+		uint32_t hb[kBwdPerThread];
 #pragma unroll
 		for (int q = 0; q < kBwdPerThread; q++) {
 			pos[q] = n - 1 - (round * kBwdBatch + tid * kBwdPerThread + q);   // 0-based list position
-			id[q] = (pos[q] >= 0) ? point_list[range.x + pos[q]] : 0u;
+			hb[q] = (kHits && pos[q] >= 0) ? (uint32_t)hit_bytes[range.x + pos[q]] : 0u;
 		}
+#pragma unroll
+		for (int q = 0; q < kBwdPerThread; q++)
+			id[q] = (pos[q] >= 0 && (!kHits || hb[q] != 0u)) ? point_list[range.x + pos[q]] : 0u;
 #pragma unroll
 		for (int q = 0; q < kBwdPerThread; q++) {
 			keep[q] = false;
-			if (pos[q] >= 0) {
+			if (pos[q] >= 0 && (!kHits || hb[q] != 0u)) {
 				a[q] = g0[id[q]];
 				b[q] = g1[id[q]];
 				const float2 bt = gb[id[q]];
 				cb[q] = bt.x;
 				if (wrap_W > 0.f) a[q].x = nearest_copy_x(a[q].x, tx0 + 0.5f * (kTile - 1), wrap_W);
 				tau[q] = bt.y;
-				keep[q] = gaussian_touches_box(a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, tau[q], tx0, ty0, tx1, ty1);
+				keep[q] = kHits ? true : gaussian_touches_box(a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, tau[q], tx0, ty0, tx1, ty1);
 			}
 			my_keep += keep[q] ? 1 : 0;
 		}
@@ -206,6 +218,7 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 				s_e[slot].a = a[q];
 				s_e[slot].b = make_float4(b[q].x, tau[q], b[q].y, __int_as_float(pos[q]));
 				s_e[slot].c = make_float4(b[q].z, b[q].w, cb[q], __uint_as_float(id[q]));
+				if (kHits) s_mask[slot] = (uint8_t)hb[q];
 				slot++;
 			}
 		}
@@ -215,7 +228,11 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 		for (int base = 0; base < total; base += 32) {
 			const int e_idx = base + lane;
 			unsigned m[kBwdSlots];
-			{
+			if constexpr (kHits) {
+				const uint32_t mb = (e_idx < total) ? ((uint32_t)s_mask[e_idx] >> (4 * warp)) : 0u;
+#pragma unroll
+				for (int s = 0; s < kBwdSlots; s++) m[s] = __ballot_sync(0xffffffffu, (mb >> s) & 1u);
+			} else {
 				bool hit[kBwdSlots] = { false, false, false, false };
 				if (e_idx < total) {
 					const float4 ea = s_e[e_idx].a;
@@ -324,14 +341,20 @@ extern "C" __attribute__((visibility("default"))) int ogs_debug_set_bwd_tile_clo
 int launch_render_bwd(const uint2* ranges, const uint32_t* point_list, int W, int H, const float* bg,
                       const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars,
                       const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
-                      float* grad_acc, cudaStream_t st)
+                      float* grad_acc, const uint8_t* hit_bytes, cudaStream_t st)
 {
 	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
 	// resident CTAs per SM the kernel is compiled for (register budget); OGS_BWD_MINBLOCKS is a tuning knob
 	static const int variant = [] { const char* e = getenv("OGS_BWD_MINBLOCKS"); return e ? atoi(e) : 16; }();
 	static const int order = [] { const char* e = getenv("OGS_TILE_ORDER"); return e ? atoi(e) : 0; }();
-#define OGS_BWD_LAUNCH(MB) render_bwd_kernel<MB><<<gx * gy, kBwdThreads, 0, st>>>(ranges, point_list, W, H, gx, gy, order, bg, g0, g1, gb, \
-	                                                                      scalars, final_T, n_contrib, dL_dpix, grad_acc)
+	const bool hits = render_hit_bytes_enabled() && hit_bytes != nullptr;
+#define OGS_BWD_LAUNCH(MB)                                                                                                         \
+	do {                                                                                                                           \
+		if (hits) render_bwd_kernel<MB, true><<<gx * gy, kBwdThreads, 0, st>>>(ranges, point_list, W, H, gx, gy, order, bg, g0, g1, gb, \
+		                                                                       scalars, final_T, n_contrib, dL_dpix, grad_acc, hit_bytes); \
+		else render_bwd_kernel<MB, false><<<gx * gy, kBwdThreads, 0, st>>>(ranges, point_list, W, H, gx, gy, order, bg, g0, g1, gb,   \
+		                                                                    scalars, final_T, n_contrib, dL_dpix, grad_acc, hit_bytes); \
+	} while (0)
 	switch (variant) {
 	case 8: OGS_BWD_LAUNCH(8); break;
 	case 10: OGS_BWD_LAUNCH(10); break;

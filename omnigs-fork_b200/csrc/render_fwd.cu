@@ -10,7 +10,9 @@
 //     colours from global memory per contributing pixel (forward.cu:448);
 //   * each warp owns an 8x4 sub-tile and re-tests 32 staged entries at a time (one per lane),
 //     iterating only over the ballot of entries that can reach its 32 pixels;
-//   * pairs whose power is below the per-Gaussian threshold skip expf.
+//   * pairs whose power is below the per-Gaussian threshold skip expf;
+//   * the sub-block decisions are kept: one byte per list entry (bit w = warp w's sub-block can be reached) goes to
+//     hit_bytes, so that the backward blend does not gather or test what the forward already ruled out.
 // Skipped pairs are pairs the reference skips too, so results are unchanged.
 #include "render_common.cuh"
 #include "launchers.cuh"
@@ -41,10 +43,15 @@ __global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_
 	const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int gx, int gy, int order,
 	const float4* __restrict__ g0, const float4* __restrict__ g1, const float2* __restrict__ gb,
 	const unsigned long long* __restrict__ scalars, const float* __restrict__ bg_color,
-	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)
+	float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
+	uint8_t* __restrict__ hit_bytes)
 {
 	__shared__ StagedEntry s_e[kBatch];
 	__shared__ uint32_t s_warp_cnt[kRenderThreads / 32];
+	// bit w of s_hit[i]: entry i of the round can reach sub-block w (this kernel's warp w).  Flushed as one byte per list
+	// entry into hit_bytes: the backward walks the same lists against the same eight sub-blocks and takes the forward's
+	// decisions instead of repeating the tile-level and sub-block tests (render_bwd.cu).
+	__shared__ uint32_t s_hit[kBatch];
 
 	const int tile = tile_of_block(blockIdx.x, gx, gy, order);
 	OGS_TILE_CLOCK(OGS_FWD_CLOCK, tile, 0);
@@ -74,9 +81,17 @@ __global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_
 	uint32_t last_contributor = 0;
 	float C[3] = { 0.f, 0.f, 0.f };
 
+	int pending_round = -1;   // round whose hit bits still sit in shared memory (block-uniform)
 	for (int round = 0; round < rounds; round++) {
 		// all pixels of the tile saturated -> stop (forward.cu:399-401); also guards smem reuse
-		if (__syncthreads_count(lane_cut > 0.f) == kRenderThreads) break;
+		const int finished = __syncthreads_count(lane_cut > 0.f);
+		if (pending_round >= 0) {
+			const int pi = pending_round * kBatch + threadIdx.x;
+			if (pi < n) hit_bytes[range.x + pi] = (uint8_t)s_hit[threadIdx.x];
+		}
+		s_hit[threadIdx.x] = 0u;   // ordered against this round's atomicOr by the barrier after the compaction
+		pending_round = -1;
+		if (finished == kRenderThreads) break;
 
 		// ---- gather one entry per thread, tile-level cull ----
 		const int i = round * kBatch + threadIdx.x;
@@ -101,6 +116,7 @@ __global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_
 			s_e[slot].c = make_float4(b.z, b.w, cb, 0.f);
 		}
 		__syncthreads();
+		pending_round = round;
 
 		// ---- per-warp: sub-tile cull of 32 staged entries at a time, blend the survivors ----
 		for (int base = 0; base < total; base += 32) {
@@ -110,6 +126,8 @@ __global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_
 				const float4 ea = s_e[s].a;
 				const float4 eb = s_e[s].b;
 				hit = gaussian_touches_box(ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, sx0, sy0, sx1, sy1);
+				// list position within the round = (1-based position - 1) mod kBatch
+				if (hit) atomicOr(&s_hit[(__float_as_uint(eb.w) - 1u) & (uint32_t)(kBatch - 1)], 1u << warp);
 			}
 			unsigned m = __ballot_sync(0xffffffffu, hit);
 			if (__all_sync(0xffffffffu, lane_cut > 0.f)) break;
@@ -143,6 +161,11 @@ __global__ void __launch_bounds__(kRenderThreads, OGS_FWD_MINBLOCKS) render_fwd_
 		}
 	}
 
+	if (pending_round >= 0) {   // the last round that ran: its bits are complete once every warp has left its blend loop
+		__syncthreads();
+		const int pi = pending_round * kBatch + threadIdx.x;
+		if (pi < n) hit_bytes[range.x + pi] = (uint8_t)s_hit[threadIdx.x];
+	}
 	if (inside) {
 		const size_t pix_id = (size_t)W * py + px;
 		const size_t HW = (size_t)H * W;
@@ -389,14 +412,12 @@ extern "C" __attribute__((visibility("default"))) int ogs_debug_set_fwd_tile_clo
 
 int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, int H,
                       const float4* g0, const float4* g1, const float2* gb, const unsigned long long* scalars, const float* bg,
-                      float* final_T, uint32_t* n_contrib, float* out_color, cudaStream_t st)
+                      float* final_T, uint32_t* n_contrib, float* out_color, uint8_t* hit_bytes, cudaStream_t st)
 {
 	const int gx = ceil_div(W, kTile), gy = ceil_div(H, kTile);
-	// OGS_FWD_STAGING=ldgsts|bulk selects the asynchronous-staging experiment (A/B measurements only)
-	static const int staging = [] {
-		const char* e = getenv("OGS_FWD_STAGING");
-		return !e ? 0 : (e[0] == 'l' ? 1 : (e[0] == 'b' ? 2 : 0));
-	}();
+	// OGS_FWD_STAGING=ldgsts|bulk selects the asynchronous-staging experiment (A/B measurements only; it leaves no hit
+	// bytes, so the backward then runs its own tests: render_hit_bytes_enabled())
+	const int staging = fwd_staging_mode();
 	if (staging == 1)
 		render_fwd_async_kernel<1><<<gx * gy, kRenderThreads, 0, st>>>(ranges, point_list, W, H, gx, g0, g1, gb, scalars, bg,
 		                                                              final_T, n_contrib, out_color);
@@ -405,7 +426,7 @@ int launch_render_fwd(const uint2* ranges, const uint32_t* point_list, int W, in
 		                                                              final_T, n_contrib, out_color);
 	else
 		render_fwd_kernel<<<gx * gy, kRenderThreads, 0, st>>>(ranges, point_list, W, H, gx, gy, tile_order_env(), g0, g1, gb,
-		                                                     scalars, bg, final_T, n_contrib, out_color);
+		                                                     scalars, bg, final_T, n_contrib, out_color, hit_bytes);
 	OGS_CUDA_TRY(cudaGetLastError());
 	return OGS_OK;
 }

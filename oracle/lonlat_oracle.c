@@ -39,6 +39,16 @@ static const float SH_C3[7] = { -0.5900435899266435f, 2.890611442640554f, -0.457
 static int g_wrap = 0;
 void ogs_oracle_set_seam_wrap(int on) { g_wrap = on ? 1 : 0; }
 
+/* threads of the following calls (OpenMP builds; a no-op otherwise): bench.py's single-thread CPU row */
+void ogs_oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+	if (n > 0) omp_set_num_threads(n);
+#else
+	(void)n;
+#endif
+}
+
 int ogs_oracle_num_threads(void)
 {
 #ifdef _OPENMP

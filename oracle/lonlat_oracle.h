@@ -31,6 +31,7 @@ extern "C" {
 void ogs_oracle_set_seam_wrap(int on);
 
 /* threads the OpenMP build will use (1 when built without OpenMP) */
+void ogs_oracle_set_num_threads(int n);
 int ogs_oracle_num_threads(void);
 
 /* cuda_rasterizer/rasterizer_impl.cu:47-62 (getHigherMsb) */

@@ -42,6 +42,11 @@ def num_threads():
     return int(lib().ogs_oracle_num_threads())
 
 
+def set_num_threads(n):
+    """OpenMP threads of the following oracle calls (bench.py's single-thread CPU row)."""
+    lib().ogs_oracle_set_num_threads(int(n))
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
