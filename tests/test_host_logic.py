@@ -102,3 +102,19 @@ def test_emit_slot_float_division_is_exact_with_its_correction():
         qq = np.where(rem < 0, qq - 1, np.where(rem >= w, qq + 1, qq))
         rem = local - qq * w
         assert np.array_equal(qq, q) and bool(((rem >= 0) & (rem < w)).all())
+
+
+def test_committed_ncu_counters_belong_to_the_committed_kernels():
+    """profiles/kernel_counters.json (DRAM traffic, warp instructions, L2 reductions per launch: what bench.py's `roofline`
+    block quotes as `traffic`) is captured under ncu and stamped with a hash of csrc/*.cu, *.cuh.  A kernel change without a
+    fresh capture must not go unnoticed: bench.py withholds stale numbers, and this test fails."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, h.ROOT)
+    import bench
+    counters = json.load(open(os.path.join(h.ROOT, "profiles", "kernel_counters.json")))
+    assert counters["source_stamp"] == bench.source_stamp(), "re-capture profiles/kernel_counters.json (tools/ncu_summary.py full ...)"
+    for k in ("preprocess_fwd", "binning", "render_fwd", "render_bwd", "preprocess_bwd"):
+        assert counters["kernels"][k]["dram_bytes"] > 0 and counters["kernels"][k]["warp_instructions"] > 0
+    assert counters["kernels"]["render_bwd"]["l2_red_sectors"] > 0
