@@ -43,6 +43,10 @@ constexpr int kBwdSlots = 4;                    // pixels per lane (one per 8x4 
 #endif
 constexpr int kBwdBatch = OGS_BWD_BATCH;        // list entries staged per round
 constexpr int kBwdPerThread = kBwdBatch / kBwdThreads;
+#ifndef OGS_BWD_CHUNK
+#define OGS_BWD_CHUNK 256
+#endif
+constexpr int kBwdChunk = OGS_BWD_CHUNK;        // list positions whose hit bytes are scanned together (kHits)
 
 // Sum v[0..7] and v8 over the 32 lanes.  On return lane L holds in `z` the total of value (L>>2)
 // (replicated over the 4 lanes of a quad) and every lane holds the total of v8 in `z8`.
@@ -97,6 +101,8 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 {
 	__shared__ StagedEntry s_e[kBwdBatch];
 	__shared__ uint8_t s_mask[kHits ? kBwdBatch : 4];
+	__shared__ int s_pos[kHits ? kBwdChunk + kBwdBatch : 1];        // reachable list positions waiting to be staged, descending
+	__shared__ uint8_t s_posb[kHits ? kBwdChunk + kBwdBatch : 4];   // and their hit bytes
 	// per (slot, thread): dL/dpixel (r, g, b) and -T_final * (bg . dL/dpixel) — read once per contributing pair with one
 	// conflict-free 128-bit load instead of living in 16 registers
 	__shared__ float4 s_pix[kBwdSlots][kBwdThreads];
@@ -170,61 +176,8 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 	const int rounds = (n + kBwdBatch - 1) / kBwdBatch;
 	const float wrap_W = (n > 0 && scalars[7] != 0ull) ? (float)W : 0.f;   // > 0: seam wrap-around mode of this frame
 
-	for (int round = 0; round < rounds; round++) {
-		// ---- gather (reverse list order, 4 consecutive entries per thread), tile-level cull ----
-		float4 a[kBwdPerThread], b[kBwdPerThread];
-		float cb[kBwdPerThread], tau[kBwdPerThread];
-		uint32_t id[kBwdPerThread];
-		int pos[kBwdPerThread];
-		bool keep[kBwdPerThread];
-		int my_keep = 0;
-		uint32_t hb[kBwdPerThread];
-#pragma unroll
-		for (int q = 0; q < kBwdPerThread; q++) {
-			pos[q] = n - 1 - (round * kBwdBatch + tid * kBwdPerThread + q);   // 0-based list position
-			hb[q] = (kHits && pos[q] >= 0) ? (uint32_t)hit_bytes[range.x + pos[q]] : 0u;
-		}
-#pragma unroll
-		for (int q = 0; q < kBwdPerThread; q++)
-			id[q] = (pos[q] >= 0 && (!kHits || hb[q] != 0u)) ? point_list[range.x + pos[q]] : 0u;
-#pragma unroll
-		for (int q = 0; q < kBwdPerThread; q++) {
-			keep[q] = false;
-			if (pos[q] >= 0 && (!kHits || hb[q] != 0u)) {
-				a[q] = g0[id[q]];
-				b[q] = g1[id[q]];
-				const float2 bt = gb[id[q]];
-				cb[q] = bt.x;
-				if (wrap_W > 0.f) a[q].x = nearest_copy_x(a[q].x, tx0 + 0.5f * (kTile - 1), wrap_W);
-				tau[q] = bt.y;
-				keep[q] = kHits ? true : gaussian_touches_box(a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, tau[q], tx0, ty0, tx1, ty1);
-			}
-			my_keep += keep[q] ? 1 : 0;
-		}
-		// stable compaction: thread-major order == descending list position
-		int incl = my_keep;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const int u = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o) incl += u;
-		}
-		if (lane == 31) s_warp_cnt[warp] = incl;
-		__syncthreads();   // every warp has finished replaying the previous round's s_e
-		int slot = incl - my_keep + (warp == 1 ? s_warp_cnt[0] : 0);
-		const int total = s_warp_cnt[0] + s_warp_cnt[1];
-#pragma unroll
-		for (int q = 0; q < kBwdPerThread; q++) {
-			if (keep[q]) {
-				s_e[slot].a = a[q];
-				s_e[slot].b = make_float4(b[q].x, tau[q], b[q].y, __int_as_float(pos[q]));
-				s_e[slot].c = make_float4(b[q].z, b[q].w, cb[q], __uint_as_float(id[q]));
-				if (kHits) s_mask[slot] = (uint8_t)hb[q];
-				slot++;
-			}
-		}
-		__syncthreads();
-
-		// ---- per-warp replay over the entries that can reach this half-tile ----
+	// ---- per-warp replay over the staged entries that can reach this half-tile (entries [0, total) of s_e) ----
+	auto replay = [&](const int total) {
 		for (int base = 0; base < total; base += 32) {
 			const int e_idx = base + lane;
 			unsigned m[kBwdSlots];
@@ -273,11 +226,11 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 						// power >= the Gaussian's cut-off (eb.y) IS the forward's alpha >= 1/255 decision, so the gradient
 						// arithmetic itself is free to use ex2.approx (2 instructions instead of expf's 9): gradients are
 						// tolerance-bound, not bit-compared
-#ifdef OGS_BWD_EXACT_MATH   // A/B build (tools/grad_noise.py): the reference's own expf / IEEE division
+	#ifdef OGS_BWD_EXACT_MATH   // A/B build (tools/grad_noise.py): the reference's own expf / IEEE division
 						G = expf(power);
-#else
+	#else
 						G = ex2_approx(power * 1.4426950408889634f);   // ex2.approx.ftz: no denormal rescaling (power >= cut-off > -6)
-#endif
+	#endif
 						alpha = fminf(0.99f, __fmul_rn(eb.z, G));
 					}
 					if (valid) {
@@ -286,11 +239,11 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 						// divisions by (1 - alpha)
 						const float4 pix = lds_f4(pix_addr + (uint32_t)(s * kBwdThreads * sizeof(float4)));
 						const float dL_dpixel[3] = { pix.x, pix.y, pix.z };
-#ifdef OGS_BWD_EXACT_MATH
+	#ifdef OGS_BWD_EXACT_MATH
 						const float inv = __fdiv_rn(1.f, 1.f - alpha);
-#else
+	#else
 						const float inv = rcp_approx(1.f - alpha);
-#endif
+	#endif
 						T[s] = T[s] * inv;
 						const float dchannel_dcolor = alpha * T[s];
 						float dL_dalpha = 0.0f;
@@ -326,6 +279,151 @@ __global__ void __launch_bounds__(kBwdThreads, kMinBlocks) render_bwd_kernel(
 				if (red_lane)
 					red_add(lane_acc + (size_t)__float_as_uint(ec.w) * 12, (lane_bits == 1) ? z8 : z);
 			}
+		}
+	};
+	if constexpr (kHits) {
+		// The forward's hit bytes say which list positions matter.  A chunk of kBwdChunk positions is scanned first (bytes
+		// only) and its reachable positions are appended, in descending list order, to s_pos; whenever kBwdBatch of them
+		// wait there (or the list is exhausted) a batch is gathered and replayed — the gather latency and the two barriers
+		// of a batch are paid per kBwdBatch STAGED entries, where the loop below (own tests) pays them per kBwdBatch list
+		// positions, a quarter of which survive at C2.
+		const int chunks = (n + kBwdChunk - 1) / kBwdChunk;
+		// have: reachable positions waiting in s_pos[off, off + have); all three are block-uniform
+		int have = 0, off = 0, next_chunk = 0;
+		for (;;) {
+			if (have < kBwdBatch && next_chunk < chunks) {
+				// ---- scan the next chunk's hit bytes, append its reachable positions (a short remainder moves to the front) ----
+				if (off > 0) {
+					int mv[kBwdPerThread];
+					uint8_t mb[kBwdPerThread];
+#pragma unroll
+					for (int q = 0; q < kBwdPerThread; q++) {
+						const int j = q * kBwdThreads + tid;
+						mv[q] = (j < have) ? s_pos[off + j] : 0;
+						mb[q] = (j < have) ? s_posb[off + j] : (uint8_t)0;
+					}
+					__syncthreads();
+#pragma unroll
+					for (int q = 0; q < kBwdPerThread; q++) {
+						const int j = q * kBwdThreads + tid;
+						if (j < have) { s_pos[j] = mv[q]; s_posb[j] = mb[q]; }
+					}
+					off = 0;
+				}
+				constexpr int kPer = kBwdChunk / kBwdThreads;
+				uint32_t hb[kPer];
+				int my_keep = 0;
+				const int first_pos = n - 1 - (next_chunk * kBwdChunk + tid * kPer);   // this thread's highest list position
+#pragma unroll
+				for (int q = 0; q < kPer; q++) {
+					hb[q] = (first_pos - q >= 0) ? (uint32_t)hit_bytes[range.x + first_pos - q] : 0u;
+					my_keep += hb[q] != 0u ? 1 : 0;
+				}
+				int incl = my_keep;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const int u = __shfl_up_sync(0xffffffffu, incl, o);
+					if (lane >= o) incl += u;
+				}
+				__syncthreads();   // s_warp_cnt of the previous scan has been read by everybody
+				if (lane == 31) s_warp_cnt[warp] = incl;
+				__syncthreads();
+				int slot = have + incl - my_keep + (warp == 1 ? s_warp_cnt[0] : 0);
+				const int kept = s_warp_cnt[0] + s_warp_cnt[1];
+#pragma unroll
+				for (int q = 0; q < kPer; q++) {
+					if (hb[q] != 0u) {
+						s_pos[slot] = first_pos - q;
+						s_posb[slot] = (uint8_t)hb[q];
+						slot++;
+					}
+				}
+				have += kept;
+				next_chunk++;
+				__syncthreads();
+				continue;
+			}
+			if (have == 0) break;
+			// ---- gather and replay one batch ----
+			const int total = min(kBwdBatch, have);
+#pragma unroll
+			for (int q = 0; q < kBwdPerThread; q++) {
+				const int j = q * kBwdThreads + tid;   // s_pos is in descending list order, so is s_e
+				if (j < total) {
+					const int pos = s_pos[off + j];
+					const uint32_t id = point_list[range.x + pos];
+					float4 a = g0[id];
+					const float4 b = g1[id];
+					const float2 bt = gb[id];
+					if (wrap_W > 0.f) a.x = nearest_copy_x(a.x, tx0 + 0.5f * (kTile - 1), wrap_W);
+					s_e[j].a = a;
+					s_e[j].b = make_float4(b.x, bt.y, b.y, __int_as_float(pos));
+					s_e[j].c = make_float4(b.z, b.w, bt.x, __uint_as_float(id));
+					s_mask[j] = s_posb[off + j];
+				}
+			}
+			__syncthreads();
+			replay(total);
+			__syncthreads();   // s_e is rewritten by the next batch
+			off += total;
+			have -= total;
+		}
+	} else {
+		for (int round = 0; round < rounds; round++) {
+			// ---- gather (reverse list order, 4 consecutive entries per thread), tile-level cull ----
+			float4 a[kBwdPerThread], b[kBwdPerThread];
+			float cb[kBwdPerThread], tau[kBwdPerThread];
+			uint32_t id[kBwdPerThread];
+			int pos[kBwdPerThread];
+			bool keep[kBwdPerThread];
+			int my_keep = 0;
+			uint32_t hb[kBwdPerThread];
+#pragma unroll
+			for (int q = 0; q < kBwdPerThread; q++) {
+				pos[q] = n - 1 - (round * kBwdBatch + tid * kBwdPerThread + q);   // 0-based list position
+				hb[q] = (kHits && pos[q] >= 0) ? (uint32_t)hit_bytes[range.x + pos[q]] : 0u;
+			}
+#pragma unroll
+			for (int q = 0; q < kBwdPerThread; q++)
+				id[q] = (pos[q] >= 0 && (!kHits || hb[q] != 0u)) ? point_list[range.x + pos[q]] : 0u;
+#pragma unroll
+			for (int q = 0; q < kBwdPerThread; q++) {
+				keep[q] = false;
+				if (pos[q] >= 0 && (!kHits || hb[q] != 0u)) {
+					a[q] = g0[id[q]];
+					b[q] = g1[id[q]];
+					const float2 bt = gb[id[q]];
+					cb[q] = bt.x;
+					if (wrap_W > 0.f) a[q].x = nearest_copy_x(a[q].x, tx0 + 0.5f * (kTile - 1), wrap_W);
+					tau[q] = bt.y;
+					keep[q] = kHits ? true : gaussian_touches_box(a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, tau[q], tx0, ty0, tx1, ty1);
+				}
+				my_keep += keep[q] ? 1 : 0;
+			}
+			// stable compaction: thread-major order == descending list position
+			int incl = my_keep;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const int u = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= o) incl += u;
+			}
+			if (lane == 31) s_warp_cnt[warp] = incl;
+			__syncthreads();   // every warp has finished replaying the previous round's s_e
+			int slot = incl - my_keep + (warp == 1 ? s_warp_cnt[0] : 0);
+			const int total = s_warp_cnt[0] + s_warp_cnt[1];
+#pragma unroll
+			for (int q = 0; q < kBwdPerThread; q++) {
+				if (keep[q]) {
+					s_e[slot].a = a[q];
+					s_e[slot].b = make_float4(b[q].x, tau[q], b[q].y, __int_as_float(pos[q]));
+					s_e[slot].c = make_float4(b[q].z, b[q].w, cb[q], __uint_as_float(id[q]));
+					if (kHits) s_mask[slot] = (uint8_t)hb[q];
+					slot++;
+				}
+			}
+			__syncthreads();
+
+			replay(total);
 		}
 	}
 	OGS_TILE_CLOCK(OGS_BWD_CLOCK, tile, 1);
