@@ -192,6 +192,45 @@ def source_stamp():
     return hh.hexdigest()[:16]
 
 
+def exchange_check(par, bucket, means3D, campos_views, side, dev, rank, world):
+    """Outside every timed region: the data-parallel exchange on seeded per-rank data, (a) overlapped (dL_dsh rebuild on the
+    side stream) and (b) sequential — the two schedules must give the same bits on this rank —, (c) against NCCL's all-reduce
+    of the same data (another summation order: close, not equal) and (d) across ranks (every replica must hold the same
+    bits: checked with a MAX / MIN all-reduce of a checksum).  Returns a small report for the JSON line."""
+    import torch
+    import torch.distributed as dist
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    data = torch.randn(bucket.flat.shape, device=dev, generator=g)
+    data[bucket.count_sum:bucket.count_sum + bucket.count_max].abs_()          # the radii section is non-negative
+    results = []
+    for overlapped in (True, False):
+        bucket.flat.copy_(data)
+        ev = par.exchange_bucket(bucket, means3D=means3D, campos_views=campos_views, degree=3, sh_stream=side if overlapped else None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        results.append((bucket.flat[:bucket.count_sum + bucket.count_max].clone(), bucket["dL_dsh"].clone()))
+    same_schedule = bool(torch.equal(results[0][0], results[1][0]) and torch.equal(results[0][1], results[1][1]))
+    ref_sum = data[:bucket.count_sum].clone()
+    dist.all_reduce(ref_sum, op=dist.ReduceOp.SUM)
+    ref_max = data[bucket.count_sum:bucket.count_sum + bucket.count_max].clone()
+    dist.all_reduce(ref_max, op=dist.ReduceOp.MAX)
+    scale = float(ref_sum.abs().max())
+    sum_err = float((results[0][0][:bucket.count_sum] - ref_sum).abs().max()) / scale
+    max_equal = bool(torch.equal(results[0][0][bucket.count_sum:], ref_max))
+    # identical bits on every replica: min and max over ranks of an integer checksum agree
+    def checksum(t):
+        return t.contiguous().view(torch.int32).to(torch.int64).sum().reshape(1)
+    cs = torch.cat([checksum(results[0][0]), checksum(results[0][1])])
+    lo, hi = cs.clone(), cs.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return {"overlapped_equals_sequential_bitwise": same_schedule, "replicas_bitwise_equal": bool(torch.equal(lo, hi)),
+            "max_rel_difference_from_nccl_sum": sum_err, "radii_max_equals_nccl": max_equal,
+            "transport": "peer/multimem kernels" if bucket.peer else "NCCL"}
+
+
 def dp_views_block(h, par, dev, rank, world, distributed, steps=8, warmup=3, config="C3", views=8):
     """BASELINE configs[2]: one training step = 8 views of the C3 scene shared by the ranks (rank g renders views g, g+N, ...),
     every view accumulated into the step's factored bucket inside the per-Gaussian backward, ONE exchange per step.  Strong
@@ -673,6 +712,8 @@ def main():
     clocks.stop()
     # BASELINE configs[2] and [3] in the same process group (every rank takes part; rank 0 reports)
     extra = {}
+    if distributed and bucket.factored:
+        extra["exchange_check"] = exchange_check(par, bucket, d["means3D"], campos_all[0], side, dev, rank, world)
     if args.impl == "ours" and not args.no_extra:
         keep = (d, dL, gt_bufs, gt_dev)      # the C2 state stays alive for the per-stage section below
         extra["dp_views"] = dp_views_block(h, par, dev, rank, world, distributed)

@@ -9,8 +9,8 @@ python - <<PY
 import json
 d=json.loads(open('gpurun_out/dp_bench_n$N.json').read().strip().splitlines()[-1])
 print('N', d['n_gpus'], 'value', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e'].get('ms_per_step'))
-print(d['config']['gradient_exchange'])
-for k in ('dp_views','bands'):
+print(d['config']['gradient_exchange']); print('exchange_check', d.get('exchange_check'))
+for k in ("dp_views","bands"):
     if k in d: print(k, d[k]['value'], d[k]['unit'], d[k].get('ms_per_step'), json.dumps(d[k]['config'])[:400])
 PY
 if [ "$2" = "dense" ]; then
