@@ -1,5 +1,5 @@
 #!/bin/bash
-# multi-GPU bench exactly as the driver launches it:  gpurun --gpus N -- 'bash tools/gpu_call_dp.sh N'
+# multi-GPU bench exactly as the driver launches it:  gpurun --gpus N -- 'bash tools/bench_multi_gpu.sh N'
 N=${1:-2}
 mkdir -p gpurun_out
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
