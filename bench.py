@@ -32,6 +32,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# data-parallel step: colour kernel of step s+1 on the side stream behind the dL_dsh rebuild of step s (OGS_DP_COLOURS=main: on
+# the main stream, after an event wait)
+COLOURS_ON_SIDE = os.environ.get("OGS_DP_COLOURS", "side") != "main"
 METRIC = "lonlat_fwd_bwd_train_views_per_s"
 UNIT = "views/s"
 WORKLOAD = "C2"
@@ -261,9 +264,14 @@ def dp_views_block(h, par, dev, rank, world, distributed, steps=8, warmup=3, con
                 # the previous step's SH gradients may still be in flight: only the colours wait for them
                 st = h.pkg.RasterizeGaussiansGeometry(d["means3D"], d["opacity"], d["scales"], d["rotations"], 1.0,
                                                       d["cov3D_precomp"], vm, cp, scene.H, scene.W)
-                if pending[0] is not None:
-                    cur.wait_event(pending[0])
-                fwd = h.pkg.RasterizeGaussiansBlend(st, d["background"], d["sh"], 3)
+                # the colour kernel runs on the exchange's side stream, behind the dL_dsh rebuild it depends on and
+                # underneath this step's sorts; the blend waits for it
+                if distributed and COLOURS_ON_SIDE:
+                    fwd = h.pkg.RasterizeGaussiansBlend(st, d["background"], d["sh"], 3, colors_stream=side)
+                else:
+                    if pending[0] is not None:
+                        cur.wait_event(pending[0])
+                    fwd = h.pkg.RasterizeGaussiansBlend(st, d["background"], d["sh"], 3)
             else:
                 d["viewmatrix"], d["campos"], d["projmatrix"] = vm, cp, vm
                 fwd = h.run_forward(h.pkg, d)
@@ -536,9 +544,14 @@ def main():
         if bucket.factored:
             st = h.pkg.RasterizeGaussiansGeometry(d["means3D"], d["opacity"], d["scales"], d["rotations"], 1.0,
                                                   d["cov3D_precomp"], vm, cp, H, W)
-            if sh_pending[0] is not None:
-                cur.wait_event(sh_pending[0])
-            fwd = h.pkg.RasterizeGaussiansBlend(st, d["background"], d["sh"], 3)
+            if COLOURS_ON_SIDE:
+                # the colour kernel runs on the exchange's side stream, behind the dL_dsh rebuild it depends on and
+                # underneath this step's sorts; the blend waits for it
+                fwd = h.pkg.RasterizeGaussiansBlend(st, d["background"], d["sh"], 3, colors_stream=side)
+            else:
+                if sh_pending[0] is not None:
+                    cur.wait_event(sh_pending[0])
+                fwd = h.pkg.RasterizeGaussiansBlend(st, d["background"], d["sh"], 3)
             g_img = dL_img(fwd[1]) if callable(dL_img) else dL_img
             m2d = h.pkg.RasterizeGaussiansBackwardView(d["background"], d["means3D"], fwd[2], d["scales"], d["rotations"], 1.0,
                                                        vm, g_img, d["sh"], 3, cp, fwd[3], fwd[0], fwd[4], fwd[5], bucket, 0)

@@ -317,9 +317,12 @@ def RasterizeGaussiansGeometry(means3D, opacity, scales, rotations, scale_modifi
                 means3D=means3D_c, campos=campos)
 
 
-def RasterizeGaussiansBlend(state, background, sh, degree):
+def RasterizeGaussiansBlend(state, background, sh, degree, colors_stream=None, colors_after=None):
     """Second half: colours from the SH coefficients (ogs_lonlat_forward_colors) and the blend (ogs_lonlat_forward_blend).
-    Returns RasterizeGaussiansCUDA's 6-tuple; results are bit-identical to the one-call forward."""
+    Returns RasterizeGaussiansCUDA's 6-tuple; results are bit-identical to the one-call forward.
+    ``colors_stream``: run the colour kernel on that stream (after ``colors_after``, an event, if given) instead of the
+    current one — it only needs the per-Gaussian records, which are complete when RasterizeGaussiansGeometry returns, so it
+    can run underneath the depth and tile sorts still queued on the current stream; the blend waits for it."""
     lib = load_library()
     device = state["geom"].device
     P, H, W, R = state["P"], state["H"], state["W"], state["R"]
@@ -328,8 +331,20 @@ def RasterizeGaussiansBlend(state, background, sh, degree):
         background, sh = _f32c(background), _f32c(sh)
         st = _stream(device)
         M = int(sh.size(1)) if sh.size(0) != 0 else 0
-        check(lib.ogs_lonlat_forward_colors(P, int(degree), M, _ptr(state["means3D"]), _ptr(sh), _ptr(state["campos"]),
-                                            _ptr(state["radii"]), _ptr(state["geom"]), st))
+        if colors_stream is not None:
+            cur = torch.cuda.current_stream(device)
+            if colors_after is not None:
+                colors_stream.wait_event(colors_after)
+            check(lib.ogs_lonlat_forward_colors(P, int(degree), M, _ptr(state["means3D"]), _ptr(sh), _ptr(state["campos"]),
+                                                _ptr(state["radii"]), _ptr(state["geom"]),
+                                                ctypes.c_void_p(colors_stream.cuda_stream)))
+            done = torch.cuda.Event()
+            done.record(colors_stream)
+            cur.wait_event(done)
+            sh.record_stream(colors_stream)
+        else:
+            check(lib.ogs_lonlat_forward_colors(P, int(degree), M, _ptr(state["means3D"]), _ptr(sh), _ptr(state["campos"]),
+                                                _ptr(state["radii"]), _ptr(state["geom"]), st))
         check(lib.ogs_lonlat_forward_blend(P, W, H, R, _ptr(background), _ptr(state["geom"]), _ptr(state["binning"]),
                                            _ptr(state["img"]), _ptr(out_color), st))
     return R, out_color, state["radii"], state["geom"], state["binning"], state["img"]
