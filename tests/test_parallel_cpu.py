@@ -4,6 +4,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -104,6 +105,22 @@ def test_allreduce_is_identity_on_one_rank():
     for n in NAMES:
         assert torch.equal(out[n], ref[n])
     assert stats["denom"].sum() == (radii > 0).sum()
+
+
+def test_tile_row_costs_weigh_instances_and_visited_pairs():
+    """tile_row_costs: per tile row, 15 ps per instance (ranges) + 1.3 ps per list entry a pixel walks (n_contrib), with the
+    last tile row of an image whose height is not a multiple of 16 counted over its real pixel rows only."""
+    W, H = 48, 40                               # 3 x 3 tiles, the last tile row has 8 pixel rows
+    ranges = torch.tensor([[0, 10], [10, 10], [10, 30], [30, 31], [31, 31], [31, 40], [40, 40], [40, 40], [40, 100]], dtype=torch.int32)
+    n_contrib = torch.zeros((H, W), dtype=torch.int32)
+    n_contrib[0:16] = 2
+    n_contrib[16:32] = 1
+    n_contrib[32:40] = 5
+    costs = par.tile_row_costs(ranges, n_contrib.flatten(), W, H)
+    inst = [30, 10, 60]
+    visited = [2 * 16 * W, 1 * 16 * W, 5 * 8 * W]
+    assert costs == pytest.approx([15.0 * i + 1.3 * v for i, v in zip(inst, visited)])
+    assert par.tile_row_counts(ranges, W, H) == inst
 
 
 def test_feedback_rebalancing_moves_boundaries_towards_equal_times():
