@@ -118,3 +118,25 @@ def test_committed_ncu_counters_belong_to_the_committed_kernels():
     for k in ("preprocess_fwd", "binning", "render_fwd", "render_bwd", "preprocess_bwd"):
         assert counters["kernels"][k]["dram_bytes"] > 0 and counters["kernels"][k]["warp_instructions"] > 0
     assert counters["kernels"]["render_bwd"]["l2_red_sectors"] > 0
+
+
+def test_backward_staging_model_replays_every_reachable_position_once_in_descending_order():
+    """tools/proto_bwd_batching.py mirrors the control flow of render_bwd_kernel's hit-byte path (chunked scan, queue, batches,
+    remainder moves).  For random hit densities and list lengths around the chunk / batch boundaries the replayed positions
+    are exactly the reachable ones, descending; batches are full except the last; the queue stays inside its capacity."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(h.ROOT, "tools"))
+    from proto_bwd_batching import emulate
+    rng = np.random.default_rng(7)
+    chunk, batch = 256, 128
+    lengths = [0, 1, 63, 127, 128, 129, 255, 256, 257, 383, 384, 385, 511, 512, 513, 1000, 4097]
+    for n in lengths:
+        for density in (0.0, 0.02, 0.26, 0.5, 0.97, 1.0):
+            hits = (rng.random(n + 50) < density).astype(np.uint8) * rng.integers(1, 256, n + 50).astype(np.uint8)
+            batches, high = emulate(hits, n, chunk, batch)
+            want = [p for p in range(n - 1, -1, -1) if hits[p] != 0]
+            got = [p for b in batches for p in b]
+            assert got == want, (n, density)
+            assert all(len(b) == batch for b in batches[:-1]) and all(0 < len(b) <= batch for b in batches)
+            assert high < chunk + batch
