@@ -359,19 +359,17 @@ OGS_API int ogs_densify_stats(
 
 /*
  * Data-parallel gradient exchange over NVLink peer memory (the reference has no multi-GPU code).
- * bufs[r] (host array, `world` <= 8 entries) is rank r's bucket of `count` floats (a multiple of 4) as mapped into THIS
- * process (CUDA IPC / symmetric memory), bufs[rank] the local one.  The call sums slice `rank` of all buckets in rank
- * order and stores the sum into every bucket (reduce-scatter + all-gather in one kernel, peer loads and stores).
- * The caller orders it against the other ranks: all buckets written before, all slices stored after (a cross-rank
- * barrier on the same stream on both sides; omnigs-fork_b200/parallel.py uses torch.distributed's symmetric memory).
+ * bufs[r] (host array, `world` <= 8 entries) is rank r's bucket (count_sum + count_max floats, both multiples of 4) as
+ * mapped into THIS process (CUDA IPC / symmetric memory), bufs[rank] the local one.  The call reduces slice `rank` of all
+ * buckets in rank order and stores the result into every bucket (reduce-scatter + all-gather in one kernel, peer loads
+ * and stores): the first count_sum floats are summed, the count_max floats behind them (non-negative values such as radii,
+ * which order like their bit patterns) are max-reduced — one call replaces the all-reduce(SUM) plus the separate
+ * all-reduce(MAX) of the densification statistics.  The caller orders it against the other ranks: all buckets written
+ * before, all slices stored after (a cross-rank barrier on the same stream on both sides; omnigs-fork_b200/parallel.py
+ * uses torch.distributed's symmetric memory).
+ * ogs_multimem_allreduce: the same contract through the bucket's NVLink multicast address (NVSwitch in-switch reduction:
+ * multimem.ld_reduce / multimem.st on slice `rank`); `multicast` is the multicast mapping of the symmetric buffer.
  */
-OGS_API int ogs_peer_allreduce_sum(float* const* bufs, int world, int rank, size_t count, void* stream);
-/* Same contract through the bucket's NVLink multicast address (NVSwitch in-switch reduction: multimem.ld_reduce /
- * multimem.st on slice `rank`); `multicast` is the multicast mapping of the symmetric buffer. */
-OGS_API int ogs_multimem_allreduce_sum(float* multicast, int world, int rank, size_t count, void* stream);
-/* Both with a second section: the first count_sum floats are summed, the count_max floats behind them (non-negative
- * values such as radii, which order like their bit patterns) are max-reduced — one call replaces the all-reduce(SUM)
- * plus the separate all-reduce(MAX) of the densification statistics. */
 OGS_API int ogs_peer_allreduce(float* const* bufs, int world, int rank, size_t count_sum, size_t count_max, void* stream);
 OGS_API int ogs_multimem_allreduce(float* multicast, int world, int rank, size_t count_sum, size_t count_max, void* stream);
 /* Latitude bands: store pixel rows [y0, y1) of the three planes of `src` ([3,H,W], this rank's

@@ -52,8 +52,6 @@ SYMBOLS = {
     "ogs_adam_step": (_c_int, [_c_int] + [_p] * 6 + [_c_i64] + [ctypes.c_double] * 3 + [_p]),
     "ogs_densify_stats": (_c_int, [_c_int] + [_p] * 5 + [_p]),
     "ogs_view_stats": (_c_int, [_c_int] + [_p] * 5 + [_p]),
-    "ogs_multimem_allreduce_sum": (_c_int, [_p, _c_int, _c_int, _c_sz, _p]),
-    "ogs_peer_allreduce_sum": (_c_int, [_p, _c_int, _c_int, _c_sz, _p]),
     "ogs_set_seam_wrap": (_c_int, [_c_int]),
     "ogs_get_seam_wrap": (_c_int, []),
     "ogs_profile_enable": (_c_int, [_c_int]),

@@ -892,14 +892,6 @@ OGS_API int ogs_densify_stats(
 	return launch_densify_stats(P, radii, dL_dmean2D, max_radii2D, xyz_gradient_accum, denom, (cudaStream_t)stream);
 }
 
-OGS_API int ogs_multimem_allreduce_sum(float* multicast, int world, int rank, size_t count, void* stream)
-{
-	if (world < 1 || rank < 0 || rank >= world) return fail(OGS_ERR_INVALID_ARG, "0 <= rank < world");
-	if (!multicast || (reinterpret_cast<uintptr_t>(multicast) & 15u) || (count & 3u))
-		return fail(OGS_ERR_INVALID_ARG, "multicast pointer must be 16-byte aligned, count a multiple of 4 floats");
-	return launch_multimem_allreduce_sum(multicast, world, rank, count, (cudaStream_t)stream);
-}
-
 OGS_API int ogs_peer_allreduce(float* const* bufs, int world, int rank, size_t count_sum, size_t count_max, void* stream)
 {
 	if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(OGS_ERR_INVALID_ARG, "1 <= world <= 8, 0 <= rank < world");
@@ -935,15 +927,6 @@ OGS_API int ogs_view_stats(int P, const int* radii, const float* dL_dmean2D, flo
 	if (P < 0 || (P > 0 && (!radii || !dL_dmean2D || !grad_norm || !visible || !radius)))
 		return fail(OGS_ERR_INVALID_ARG, "bad argument to view_stats");
 	return launch_view_stats(P, radii, dL_dmean2D, grad_norm, visible, radius, (cudaStream_t)stream);
-}
-
-OGS_API int ogs_peer_allreduce_sum(float* const* bufs, int world, int rank, size_t count, void* stream)
-{
-	if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(OGS_ERR_INVALID_ARG, "1 <= world <= 8, 0 <= rank < world");
-	if (!bufs || (count & 3u)) return fail(OGS_ERR_INVALID_ARG, "count must be a multiple of 4 floats");
-	for (int r = 0; r < world; r++)
-		if (!bufs[r] || (reinterpret_cast<uintptr_t>(bufs[r]) & 15u)) return fail(OGS_ERR_INVALID_ARG, "peer buffers must be 16-byte aligned");
-	return launch_peer_allreduce_sum(bufs, world, rank, count, (cudaStream_t)stream);
 }
 
 OGS_API int ogs_mark_all_visible(int P, uint8_t* present, void* stream)
